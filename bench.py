@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the PINN training hot path (BASELINE.json metric: collocation-points/sec per training step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- 1D Burgers, [2,20x8,1] tanh MLP, N_f = 100 000 collocation
+points per GPU (+ N_u = 100 data points), one Adam training step = fused loss/gradient evaluation + on-device
+Adam update.  A "step" is one pass of that hot path.  N > 1 (torchrun): collocation points are sharded, weak
+scaling (100 000 per GPU), one ncclAllReduce of [gradient | loss] per step.
+
+value   : whole-job collocation points / second, inputs resident in HBM, each step timed with CUDA events on the
+          launching stream (L2 flushed between timed iterations), max over ranks.
+e2e     : the same metric through the public API with HOST buffers: every step uploads that step's collocation
+          batch from pinned host memory (pinn_set_collocation) and reads the loss back (pinn_adam_step(&loss)).
+roofline: fused kernel alone (CUDA events); algorithmic FLOPs = 24*S per collocation point + 6*S per data point
+          (S = 2860 weight entries) against the MEASURED FP64 pipe peak of this pool's B200
+          (profiles/microbench/fp64_peak_r01.jsonl: DMMA.8x8x4 37.0 TFLOP/s; MEASURED_PEAKS.json has no FP64 figure).
+          The path is FP64-pipe-bound (4 300 FLOP per HBM byte); the HBM fraction is reported beside it.
+cpu_baseline / --impl reference: the restated reference (oracle/reference_port.py: nested reverse-mode autograd,
+          torch CPU fp64, TF-2.0 Adam semantics) timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pinns-tf2.0_b200")
+for p in (ROOT, PKG, os.path.join(PKG, "utils")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+LAYERS = [2] + [20] * 8 + [1]
+S_WEIGHTS = 2 * 20 + 7 * 400 + 20            # 2860
+FLOP_PER_COLLOC = 24 * S_WEIGHTS             # 68 640 (forward 8S, input adjoint 8S, weight gradient 8S)
+FLOP_PER_DATA = 6 * S_WEIGHTS                # one stream
+N_F_PER_GPU = 100_000
+N_U = 100
+LB, UB = np.array([-1.0, 0.0]), np.array([1.0, 0.99])
+NU = 0.01 / np.pi
+ADAM_LR = 1e-3
+FP64_PEAK_TFLOPS_FALLBACK = 37.0
+
+
+def fp64_peak():
+    path = os.path.join(ROOT, "profiles", "microbench", "fp64_peak_r01.jsonl")
+    best = None
+    try:
+        for line in open(path):
+            d = json.loads(line)
+            if "dmma_tflops" in d:
+                best = max(best or 0.0, d["dmma_tflops"])
+    except Exception:
+        pass
+    return (best, "measured (profiles/microbench/fp64_peak_r01.jsonl, DMMA.8x8x4)") if best else \
+        (FP64_PEAK_TFLOPS_FALLBACK, "fallback")
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def synthetic_problem(seed, n_f):
+    rng = np.random.default_rng(seed)
+    X_f = LB + (UB - LB) * rng.random((n_f, 2))
+    X_u = LB + (UB - LB) * rng.random((N_U, 2))
+    u = rng.uniform(-1, 1, (N_U, 1))
+    return X_f, X_u, u
+
+
+def init_weights():
+    from neuralnetwork import _glorot_normal
+    return _glorot_normal(LAYERS, np.random.default_rng(1234))
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=10)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def time_reference_port(n_f, steps, warmup, seed=1234):
+    """The restated reference on the host cores: loss + flat gradient (nested reverse mode) + Adam update."""
+    import torch
+    from oracle import reference_port as rp
+    X_f, X_u, u = synthetic_problem(seed, n_f)
+    pb = rp.BurgersInference(LAYERS, LB, UB, NU, X_f, X_u, u)
+    w = init_weights()
+    st = rp.adam_init(w.size)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        f, g = rp.loss_and_flat_grad(pb, w)
+        w = rp.adam_update(w, g, st, ADAM_LR)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)), torch.get_num_threads(), f
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    n_f = N_F_PER_GPU
+    sec, cores, _ = time_reference_port(n_f, args.steps, args.warmup)
+    val = n_f / sec
+    line = {
+        "impl": "reference", "metric": "collocation-points/sec per training step (1D Burgers 8x20 tanh, Adam step)",
+        "value": val, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "1d-burgers inf_cont [2,20x8,1] tanh, N_f=100000 per step sample, N_u=100, Adam lr 1e-3 (BASELINE configs[1])"},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} Adam steps of N_f={n_f} after {args.warmup} warm-up, oracle/reference_port.py "
+                                   "(TF-free restatement; TensorFlow 2.0 is not installable here)"},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-f", type=int, default=N_F_PER_GPU, help="collocation points per GPU (default: BASELINE configs[1])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 10
+        args.warmup = args.warmup if args.warmup is not None else 3
+        run_reference_arm(args, rank, world)
+        return
+    args.steps = args.steps if args.steps is not None else 50
+    args.warmup = args.warmup if args.warmup is not None else 10
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import pinn_cabi
+    dist = None
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [pinn_cabi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_f = args.n_f
+    n_f_global = n_f * world
+    X_f, X_u, u = synthetic_problem(1234 + rank, n_f)
+    _, X_u, u = synthetic_problem(1234, 1)     # data term identical on all ranks
+    p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, LAYERS, LB, UB, device=local_rank, rank=rank, world=world, nccl_uid=uid)
+    p.set_pde_params([NU])
+    p.set_data(X_u, u, weight=1.0 if rank == 0 else 0.0)
+    # pinned host copies of this rank's collocation batch (e2e leg uploads them every step)
+    hx, hx_ptr = pinn_cabi.host_alloc(n_f)
+    ht, ht_ptr = pinn_cabi.host_alloc(n_f)
+    hx[:] = X_f[:, 0]; ht[:] = X_f[:, 1]
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    p.set_collocation_ptr(C.cast(hx_ptr, dp), C.cast(ht_ptr, dp), n_f, n_f_global)
+    p.set_weights(init_weights())
+
+    # ---------------- device-resident steps, CUDA events per step, L2 flushed between timed iterations
+    for _ in range(args.warmup):
+        p.adam_step(ADAM_LR, sync=False)
+    barrier()
+    l0 = p.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            p.flush_l2()
+            p.event_record(2 * i)
+            p.adam_step(ADAM_LR, sync=False)
+            p.event_record(2 * i + 1)
+        p.sync()
+        barrier()
+        wall = time.perf_counter() - t_wall0
+        # keep the sampler alive for at least ~1.5 s of load so that it sees clocks under load
+        t_end = time.perf_counter() + max(0.0, 1.5 - wall)
+        while time.perf_counter() < t_end:
+            p.adam_step(ADAM_LR, sync=False)
+            p.sync()
+    launches = None
+    ms_steps = [p.event_elapsed_ms(2 * i, 2 * i + 1) for i in range(args.steps)]
+    ms_step = float(np.mean(ms_steps))
+    # launches inside the timed region: (fused + reduce + adam_update + adam_advance) per step
+    launches_per_step = 4
+    launches = launches_per_step * args.steps
+    if dist is not None:
+        tt = torch.tensor([ms_step], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_step = float(tt.item())
+    value = n_f_global / (ms_step * 1e-3)
+
+    # ---------------- fused kernel alone (roofline)
+    barrier()
+    p.time_kernel_ms(3)
+    k_iters = 20
+    ms_kernel = p.time_kernel_ms(k_iters) / k_iters
+    flops = n_f * FLOP_PER_COLLOC + (N_U * FLOP_PER_DATA if rank == 0 else 0)
+    peak, peak_src = fp64_peak()
+    hbm, hbm_src = hbm_peak()
+    achieved = flops / (ms_kernel * 1e-3) / 1e12
+    alg_bytes = 16.0 * n_f + 8.0 * 3021 + 8.0 * 3024
+    roofline = {"bound": "tensor", "pipe": "fp64 (DMMA.8x8x4 + DFMA share one pipe)", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "kernel": "pinn::burgers::fused_loss_grad", "kernel_ms": ms_kernel,
+                "hbm": {"achieved": alg_bytes / (ms_kernel * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": alg_bytes / (ms_kernel * 1e-3) / 1e9 / hbm, "peak_source": hbm_src,
+                        "note": "algorithmic bytes 16 B/point + weights in + gradient out; the path is FP64-bound"}}
+
+    # ---------------- end to end through the public API with host buffers
+    barrier()
+    for _ in range(3):
+        p.set_collocation_ptr(C.cast(hx_ptr, dp), C.cast(ht_ptr, dp), n_f, n_f_global)
+        p.adam_step(ADAM_LR, sync=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        p.set_collocation_ptr(C.cast(hx_ptr, dp), C.cast(ht_ptr, dp), n_f, n_f_global)
+        loss = p.adam_step(ADAM_LR, sync=True)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if dist is not None:
+        tt = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e = {"value": n_f_global / e2e_s, "unit": "points/s", "h2d_bytes_per_step": 16 * n_f, "d2h_bytes_per_step": 8,
+           "ms_per_step": e2e_s * 1e3, "timing": "wall clock around the API calls, barrier+synchronize both sides"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, cores, _ = time_reference_port(n_f, 12, 3)
+        cpu = {"value": n_f / sec, "unit": "points/s", "cores": cores, "kind": "port",
+               "sample": f"12 Adam steps of N_f={n_f} after 3 warm-up, oracle/reference_port.py (nested reverse-mode, torch CPU fp64)"}
+
+    if rank == 0:
+        line = {
+            "metric": "collocation-points/sec per training step (1D Burgers 8x20 tanh, Adam step)",
+            "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "1d-burgers inf_cont [2,20x8,1] tanh, N_f=%d per GPU (%d global), N_u=100, Adam lr 1e-3 "
+                                   "(BASELINE configs[1])" % (n_f, n_f_global),
+                       "l2": "flushed (256 MB memset) between timed iterations; inputs are 1.6 MB, the path is compute-bound",
+                       "parallelism": "dp%d (collocation shards, one ncclAllReduce of 3024 doubles per step)" % world},
+            "clocks": clocks.summary(),
+            "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches_per_step,
+            "roofline": roofline, "kernel_info": p.kernel_info(), "final_loss": loss,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        p.close()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

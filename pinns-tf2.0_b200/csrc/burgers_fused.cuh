@@ -1,0 +1,506 @@
+// Fused Burgers PINN loss + parameter-gradient kernel for the [2, 20 x 8, 1] tanh MLP, fp64, sm_100a.
+//
+// Replaces (reference file:line): utils/neuralnetwork.py:27-37 (model forward), :55-59 (grad),
+// 1d-burgers/inf_cont_burgers.py:59-90 (loss + f_model nested tapes), 1d-burgers/ide_cont_burgers.py:56-91.
+//
+// One launch evaluates, for every point of the set, the tanh MLP in forward Taylor mode (streams
+// h, h_x, h_t, h_xx), the residual f = u_t + l1 u u_x - kappa u_xx, the loss terms, and the reverse
+// sweep that yields d(loss)/d(params), accumulated per CTA and written as one partial vector per CTA.
+//
+// Work decomposition: a warp owns a tile of 8 points.  The 4 streams of those 8 points are four 8-row
+// M-tiles of DMMA.8x8x4; the hidden index (20, padded to 24 = 3 N-tiles) is N (forward / input adjoint)
+// or M and N (weight gradient).  Accumulator fragments stay in registers from layer to layer: with lane =
+// 4g+q a C fragment holds (point g, columns 8nt+2q+e), and an A fragment wants (row g, k-column q), so the
+// contraction index is *permuted* -- k-step (nt,e) contracts hidden units {8nt+2q+e : q=0..3}, and the B
+// fragment (weights, from shared memory) is gathered with the same permutation.  Only the 5th k-step (units
+// 16..19) needs one quad shuffle.  No padding in K (5 k-steps for 20), 24/20 padding in N.
+// The reverse sweep needs the contraction over points (weight gradient), which is across lanes: Z-bar and the
+// layer inputs are transposed through a per-warp shared-memory staging area and fed to DMMA as a
+// [20(+1 ones row = bias) x 32 rows] x [32 rows x 20] GEMM.  Per-CTA accumulation is deterministic
+// (fixed warp order), the cross-CTA reduction is a second tiny kernel (reduce_partials).
+#pragma once
+#include "pinn_common.cuh"
+
+namespace pinn {
+namespace burgers {
+
+constexpr int W = 20;             // hidden width
+constexpr int NHID = 8;           // hidden layers
+constexpr int P_NET = 3021;       // 2*20+20 + 7*(400+20) + 20+1
+constexpr int WPAD = 3024;        // weight buffer padded to a multiple of 16 bytes for the TMA bulk copy
+constexpr int WARPS = 4;          // one warp per SM sub-partition
+constexpr int THREADS = WARPS * 32;
+constexpr int TILE = 8;           // points per warp tile
+constexpr int ROUND = WARPS * TILE;
+constexpr int PSTRIDE = 3040;     // partial vector stride: P_NET + [dl1, dl2, loss_d, loss_f] + padding
+constexpr int IDX_DL1 = 3021, IDX_DL2 = 3022, IDX_LD = 3024, IDX_LF = 3025;
+
+__host__ __device__ constexpr int woff(int l) { return l == 0 ? 0 : (l <= 7 ? 60 + (l - 1) * 420 : 3000); }
+__host__ __device__ constexpr int boff(int l) { return l == 0 ? 40 : (l <= 7 ? 60 + (l - 1) * 420 + 400 : 3020); }
+
+// shared memory carve-up (in doubles)
+constexpr int STASH0 = 160;                       // layer 0: a only (z_x, z_t are per-column constants, z_xx = 0)
+constexpr int STASHL = 640;                       // layers 1..6: a, z_x, z_t, z_xx   (layer 7 lives in registers)
+constexpr int STASH_PER_WARP = STASH0 + 6 * STASHL;   // 4000
+constexpr int STAGE_PER_WARP = 2 * 640;           // ZB[32][20] + HA[32][20]
+constexpr int SM_W = 0;
+constexpr int SM_G = SM_W + WPAD;
+constexpr int SM_STASH = SM_G + WPAD;
+constexpr int SM_STAGE = SM_STASH + WARPS * STASH_PER_WARP;
+constexpr int SM_RED = SM_STAGE + WARPS * STAGE_PER_WARP;
+constexpr int SM_BAR = SM_RED + 32;
+constexpr int SM_DOUBLES = SM_BAR + 2;
+constexpr int SMEM_BYTES = SM_DOUBLES * 8;        // 218,128 B  (< 227 KB)
+
+struct Args {
+  const double* w;        // flat weights, WPAD doubles (zero padded); ide: [.., l1, l2] at P_NET, P_NET+1
+  const double* x;        // n_total
+  const double* t;        // n_total
+  const double* utgt;     // n_d targets (point d0+i <-> utgt[i])
+  long long n_total;      // points in the set
+  long long c0, n_c;      // points [c0, c0+n_c) carry the residual term with weight wf
+  long long d0, n_d;      // points [d0, d0+n_d) carry the data term with weight wd
+  double wf, wd;          // 1/N_f(global);  data_weight/N_u
+  double lb0, lb1, dx0, dx1;   // lb and (ub-lb)
+  double nu;              // inference: kappa = nu, l1 = 1
+  int ide;                // identification: l1 = w[P_NET], kappa = exp(w[P_NET+1])
+  double* partials;       // [gridDim.x][PSTRIDE]
+  const int* run_flag;    // optional: skip the whole launch when *run_flag != 0 (L-BFGS stopped on device)
+};
+
+// ---------------------------------------------------------------------------------------------------
+// fragment index helpers (lane = 4g + q)
+// ---------------------------------------------------------------------------------------------------
+// hidden unit contracted by lane-quad position q in k-step ks (see header comment)
+__device__ __forceinline__ int feat_k(int ks, int q) {
+  return ks < 4 ? 8 * (ks >> 1) + 2 * q + (ks & 1) : (q < 2 ? 16 + 2 * q : 13 + 2 * q);
+}
+
+// A operand of k-step KS taken straight from a stream's C fragments.
+template <int KS>
+__device__ __forceinline__ double a_from_c(const double (&C)[3][2], int lane) {
+  if (KS < 4) {
+    return C[KS >> 1][KS & 1];
+  } else {
+    // units 16,18 are own C[2][0] of q=0,1; units 17,19 are C[2][1] of q=0,1 -> lanes q=2,3 fetch them.
+    double v = __shfl_sync(0xffffffffu, C[2][1], (lane & ~3) | (lane & 1));
+    return (lane & 2) ? v : C[2][0];
+  }
+}
+
+// Z[s][nt][:] += A_s(k-steps from Hs) * Bmat, Bmat[k][n] = Wl[k*ldk + n*ldn]  (forward: ldk=20, ldn=1;
+// input-adjoint: ldk=1, ldn=20, i.e. the transposed weight).  N columns >= 20 read as zero.
+template <int KS>
+__device__ __forceinline__ void mma_kstep(double (&Z)[4][3][2], const double (&Hs)[4][3][2], const double* Wl, int ldk,
+                                          int ldn, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  const int k = feat_k(KS, q);
+  double b[3];
+#pragma unroll
+  for (int nt = 0; nt < 3; nt++) {
+    const int n = 8 * nt + g;
+    b[nt] = (n < W) ? Wl[k * ldk + n * ldn] : 0.0;
+  }
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const double a = a_from_c<KS>(Hs[s], lane);
+#pragma unroll
+    for (int nt = 0; nt < 3; nt++) dmma(Z[s][nt], a, b[nt]);
+  }
+}
+
+__device__ __forceinline__ void mma_layer(double (&Z)[4][3][2], const double (&Hs)[4][3][2], const double* Wl, int ldk,
+                                          int ldn, int lane) {
+  mma_kstep<0>(Z, Hs, Wl, ldk, ldn, lane);
+  mma_kstep<1>(Z, Hs, Wl, ldk, ldn, lane);
+  mma_kstep<2>(Z, Hs, Wl, ldk, ldn, lane);
+  mma_kstep<3>(Z, Hs, Wl, ldk, ldn, lane);
+  mma_kstep<4>(Z, Hs, Wl, ldk, ldn, lane);
+}
+
+// tanh layer, forward: Z (pre-activations of the 4 streams) -> S (stash: a, z_x, z_t, z_xx)
+__device__ __forceinline__ void act_stash(double (&S)[4][3][2], const double (&Z)[4][3][2]) {
+#pragma unroll
+  for (int nt = 0; nt < 3; nt++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      S[0][nt][e] = tanh(Z[0][nt][e]);
+      S[1][nt][e] = Z[1][nt][e];
+      S[2][nt][e] = Z[2][nt][e];
+      S[3][nt][e] = Z[3][nt][e];
+    }
+}
+
+// layer outputs from the stash: (a, s z_x, s z_t, s (z_xx - 2 a z_x^2)),  s = 1 - a^2
+__device__ __forceinline__ void outputs_from_stash(double (&H)[4][3][2], const double (&S)[4][3][2]) {
+#pragma unroll
+  for (int nt = 0; nt < 3; nt++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const double a = S[0][nt][e], zx = S[1][nt][e];
+      const double s = fma(-a, a, 1.0);
+      H[0][nt][e] = a;
+      H[1][nt][e] = s * zx;
+      H[2][nt][e] = s * S[2][nt][e];
+      H[3][nt][e] = s * fma(-2.0 * a * zx, zx, S[3][nt][e]);
+    }
+}
+
+// tanh layer, reverse: adjoints of the outputs (in A, overwritten) -> adjoints of the pre-activations
+__device__ __forceinline__ void act_backward(double (&A)[4][3][2], const double (&S)[4][3][2]) {
+#pragma unroll
+  for (int nt = 0; nt < 3; nt++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const double a = S[0][nt][e], zx = S[1][nt][e], zt = S[2][nt][e], zxx = S[3][nt][e];
+      const double s = fma(-a, a, 1.0);
+      const double A0 = A[0][nt][e], Ax = A[1][nt][e], At = A[2][nt][e], Axx = A[3][nt][e];
+      const double two_a = 2.0 * a;
+      // Z = s [A - 2a z_x Ax - 2a z_t At + Axx(-2a z_xx - 2 z_x^2 (1 - 3a^2))]
+      const double inner = fma(-two_a, zxx, -2.0 * zx * zx * fma(-3.0 * a, a, 1.0));
+      double acc = fma(Axx, inner, A0);
+      acc = fma(-two_a * zx, Ax, acc);
+      acc = fma(-two_a * zt, At, acc);
+      A[0][nt][e] = s * acc;
+      A[1][nt][e] = s * fma(-2.0 * two_a * zx, Axx, Ax);   // s (Ax - 4 a z_x Axx)
+      A[2][nt][e] = s * At;
+      A[3][nt][e] = s * Axx;
+    }
+}
+
+// thread-private stash slots: [v][nt][lane][e] for nt < 2, compact [v][(g*2+q)][e] for nt == 2 (q < 2 only)
+__device__ __forceinline__ void stash_store(double* st, const double (&S)[4][3][2], int nv, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int v = 0; v < 4; v++) {
+    if (v >= nv) break;
+    double* base = st + v * 160;
+    *reinterpret_cast<double2*>(base + lane * 2) = make_double2(S[v][0][0], S[v][0][1]);
+    *reinterpret_cast<double2*>(base + 64 + lane * 2) = make_double2(S[v][1][0], S[v][1][1]);
+    if (q < 2) *reinterpret_cast<double2*>(base + 128 + (g * 2 + q) * 2) = make_double2(S[v][2][0], S[v][2][1]);
+  }
+}
+__device__ __forceinline__ void stash_load(double (&S)[4][3][2], const double* st, int nv, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int v = 0; v < 4; v++) {
+    if (v >= nv) break;
+    const double* base = st + v * 160;
+    double2 c0 = *reinterpret_cast<const double2*>(base + lane * 2);
+    double2 c1 = *reinterpret_cast<const double2*>(base + 64 + lane * 2);
+    double2 c2 = make_double2(0.0, 0.0);
+    if (q < 2) c2 = *reinterpret_cast<const double2*>(base + 128 + (g * 2 + q) * 2);
+    S[v][0][0] = c0.x; S[v][0][1] = c0.y;
+    S[v][1][0] = c1.x; S[v][1][1] = c1.y;
+    S[v][2][0] = c2.x; S[v][2][1] = c2.y;
+  }
+}
+
+// stage a [4 streams][8 points][20 units] register tile into shared memory as T[row = 8s+g][unit], ld = 20
+__device__ __forceinline__ void stage_rows(double* T, const double (&V)[4][3][2], int lane) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    double* row = T + (8 * s + g) * W;
+    *reinterpret_cast<double2*>(row + 2 * q) = make_double2(V[s][0][0], V[s][0][1]);
+    *reinterpret_cast<double2*>(row + 8 + 2 * q) = make_double2(V[s][1][0], V[s][1][1]);
+    if (q < 2) *reinterpret_cast<double2*>(row + 16 + 2 * q) = make_double2(V[s][2][0], V[s][2][1]);
+  }
+}
+
+// Weight gradient of one layer for this warp's 8 points: G[i][j] = sum_rows HA[row][i] * ZB[row][j],
+// rows = 4 streams x 8 points (K = 32 -> 8 k-steps), i in [0,in_dim] where i == in_dim is a virtual
+// "ones on the value stream" unit that produces the bias gradient.  Result fragments acc[mt][nt][e] hold
+// G[8mt+g][8nt+2q+e].
+template <int MT, int NT>
+__device__ __forceinline__ void wgrad_mma(double (&acc)[MT][NT][2], const double* HA, const double* ZB, int in_dim,
+                                          int out_dim, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < 8; ks++) {
+    const int row = 4 * ks + q;
+    double a[MT], b[NT];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      const int i = 8 * mt + g;
+      a[mt] = (i < in_dim) ? HA[row * W + i] : ((i == in_dim && ks < 2) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      const int j = 8 * nt + g;
+      b[nt] = (j < out_dim) ? ZB[row * W + j] : 0.0;
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) dmma(acc[mt][nt], a[mt], b[nt]);
+  }
+}
+
+// write this warp's partial weight gradient to its scratch PS[i][j] (ld = 20), i <= in_dim, j < out_dim
+template <int MT, int NT>
+__device__ __forceinline__ void wgrad_store(double* PS, const double (&acc)[MT][NT][2], int in_dim, int out_dim, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++) {
+    const int i = 8 * mt + g;
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int j = 8 * nt + 2 * q + e;
+        if (i <= in_dim && j < out_dim) PS[i * W + j] = acc[mt][nt][e];
+      }
+  }
+}
+
+// CTA-wide, fixed-order accumulation of the 4 warps' partial gradients of one layer into Gacc (flat layout)
+__device__ __forceinline__ void cta_accumulate(double* Gacc, const double* stage_base, int in_dim, int out_dim, int w_off,
+                                               int b_off) {
+  __syncthreads();
+  const int n = (in_dim + 1) * out_dim;
+  for (int e = threadIdx.x; e < n; e += THREADS) {
+    const int i = e / out_dim, j = e - i * out_dim;
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) s += stage_base[w * STAGE_PER_WARP + 640 + i * W + j];
+    const int idx = (i < in_dim) ? w_off + i * out_dim + j : b_off + j;
+    Gacc[idx] += s;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
+  extern __shared__ __align__(16) double sm[];
+  if (p.run_flag && *p.run_flag != 0) return;
+  double* Wsm = sm + SM_W;
+  double* Gacc = sm + SM_G;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SM_BAR);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  double* stash = sm + SM_STASH + warp * STASH_PER_WARP;
+  double* ZB = sm + SM_STAGE + warp * STAGE_PER_WARP;
+  double* HA = ZB + 640;   // also this warp's partial-gradient scratch PS after the weight-gradient MMAs
+
+  // ---- stage the flat weight vector with one TMA bulk copy; zero the CTA gradient accumulator meanwhile
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, WPAD * 8);
+    tma_bulk_g2s(Wsm, p.w, WPAD * 8, bar);
+  }
+  for (int i = threadIdx.x; i < WPAD; i += THREADS) Gacc[i] = 0.0;
+  mbar_wait(bar, 0);
+  __syncthreads();
+
+  const double l1 = p.ide ? Wsm[P_NET] : 1.0;
+  const double kap = p.ide ? exp(Wsm[P_NET + 1]) : p.nu;
+  const double sc0 = 2.0 / p.dx0, sc1 = 2.0 / p.dx1;
+  double loss_d = 0.0, loss_f = 0.0, gl1 = 0.0, gl2 = 0.0;
+
+  const long long n_rounds = (p.n_total + ROUND - 1) / ROUND;
+  for (long long rnd = blockIdx.x; rnd < n_rounds; rnd += gridDim.x) {
+    // ---------------- this lane's point (all 4 lanes of a quad share point g)
+    const long long pt = rnd * ROUND + warp * TILE + g;
+    const bool in_set = pt < p.n_total;
+    const long long pc = in_set ? pt : p.n_total - 1;
+    const double xr = __ldg(p.x + pc), tr = __ldg(p.t + pc);
+    const double wf = (in_set && pt >= p.c0 && pt < p.c0 + p.n_c) ? p.wf : 0.0;
+    const bool has_d = in_set && pt >= p.d0 && pt < p.d0 + p.n_d;
+    const double wd = has_d ? p.wd : 0.0;
+    const double ut = has_d ? __ldg(p.utgt + (pt - p.d0)) : 0.0;
+    const double xh = 2.0 * (xr - p.lb0) / p.dx0 - 1.0;   // utils/neuralnetwork.py:29-30
+    const double th = 2.0 * (tr - p.lb1) / p.dx1 - 1.0;
+
+    double S[4][3][2];   // stash of the current layer (a, z_x, z_t, z_xx)
+    double H[4][3][2];   // layer outputs / adjoints
+
+    // ---------------- layer 0 (2 -> 20): direct
+#pragma unroll
+    for (int nt = 0; nt < 3; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = 8 * nt + 2 * q + e;
+        const bool ok = c < W;
+        const double w0 = ok ? Wsm[c] : 0.0, w1 = ok ? Wsm[W + c] : 0.0, b = ok ? Wsm[2 * W + c] : 0.0;
+        S[0][nt][e] = tanh(fma(xh, w0, fma(th, w1, b)));
+        S[1][nt][e] = sc0 * w0;
+        S[2][nt][e] = sc1 * w1;
+        S[3][nt][e] = 0.0;
+      }
+    stash_store(stash, S, 1, lane);
+    outputs_from_stash(H, S);
+
+    // ---------------- hidden layers 1..7: DMMA chain
+    for (int l = 1; l < NHID; l++) {
+      const double* Wl = Wsm + woff(l);
+      double Z[4][3][2];
+#pragma unroll
+      for (int nt = 0; nt < 3; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = 8 * nt + 2 * q + e;
+          Z[0][nt][e] = (c < W) ? Wl[W * W + c] : 0.0;   // bias on the value stream
+          Z[1][nt][e] = Z[2][nt][e] = Z[3][nt][e] = 0.0;
+        }
+      mma_layer(Z, H, Wl, W, 1, lane);
+      act_stash(S, Z);
+      if (l < NHID - 1) stash_store(stash + STASH0 + (l - 1) * STASHL, S, 4, lane);   // layer 7 stays in registers
+      outputs_from_stash(H, S);
+    }
+
+    // ---------------- output layer (20 -> 1) + residual + seeds
+    double out[4];
+    {
+      const double* W8 = Wsm + woff(8);
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 3; nt++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int c = 8 * nt + 2 * q + e;
+            acc = fma(H[s][nt][e], (c < W) ? W8[c] : 0.0, acc);
+          }
+        acc += shfl_xor_d(acc, 1);
+        acc += shfl_xor_d(acc, 2);
+        out[s] = acc;
+      }
+      out[0] += Wsm[boff(8)];
+    }
+    double seed[4];
+    {
+      const double u = out[0], ux = out[1], utt = out[2], uxx = out[3];
+      const double f = utt + l1 * u * ux - kap * uxx;        // inf_cont_burgers.py:90 / ide_cont_burgers.py:85
+      const double r = u - ut;
+      const double c = 2.0 * wf * f;
+      seed[0] = fma(c * l1, ux, 2.0 * wd * r);
+      seed[1] = c * l1 * u;
+      seed[2] = c;
+      seed[3] = -c * kap;
+      if (q == 0) {
+        loss_d = fma(wd * r, r, loss_d);
+        loss_f = fma(wf * f, f, loss_f);
+        gl1 = fma(c * u, ux, gl1);
+        gl2 = fma(-c * kap, uxx, gl2);
+      }
+    }
+
+    // ---------------- reverse: output layer.  HA <- outputs of layer 7 (still in H), ZB[row][0] <- seeds
+    stage_rows(HA, H, lane);
+    if (q == 0) {
+#pragma unroll
+      for (int s = 0; s < 4; s++) ZB[(8 * s + g) * W] = seed[s];
+    }
+    __syncwarp();
+    {
+      double acc[3][1][2];
+      wgrad_mma<3, 1>(acc, HA, ZB, W, 1, lane);
+      __syncwarp();
+      wgrad_store<3, 1>(HA, acc, W, 1, lane);
+    }
+    // adjoint of layer-7 outputs: rank-1
+    {
+      const double* W8 = Wsm + woff(8);
+#pragma unroll
+      for (int nt = 0; nt < 3; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = 8 * nt + 2 * q + e;
+          const double wv = (c < W) ? W8[c] : 0.0;
+#pragma unroll
+          for (int s = 0; s < 4; s++) H[s][nt][e] = seed[s] * wv;
+        }
+    }
+    cta_accumulate(Gacc, sm + SM_STAGE, W, 1, woff(8), boff(8));
+
+    // ---------------- reverse: hidden layers 7..1.  S = stash of layer l, H = adjoint of its outputs
+    for (int l = NHID - 1; l >= 1; l--) {
+      act_backward(H, S);                      // H := Z-bar (adjoint of pre-activations), 4 streams
+      stage_rows(ZB, H, lane);
+      // inputs of layer l = outputs of layer l-1, recomputed from its stash
+      if (l - 1 == 0) {
+        stash_load(S, stash, 1, lane);
+#pragma unroll
+        for (int nt = 0; nt < 3; nt++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int c = 8 * nt + 2 * q + e;
+            const bool ok = c < W;
+            S[1][nt][e] = ok ? sc0 * Wsm[c] : 0.0;
+            S[2][nt][e] = ok ? sc1 * Wsm[W + c] : 0.0;
+            S[3][nt][e] = 0.0;
+          }
+      } else {
+        stash_load(S, stash + STASH0 + (l - 2) * STASHL, 4, lane);
+      }
+      {
+        double Hin[4][3][2];
+        outputs_from_stash(Hin, S);
+        stage_rows(HA, Hin, lane);
+      }
+      __syncwarp();
+      {
+        double acc[3][3][2];
+        wgrad_mma<3, 3>(acc, HA, ZB, W, W, lane);
+        __syncwarp();
+        wgrad_store<3, 3>(HA, acc, W, W, lane);
+      }
+      // adjoint of the layer inputs: A_new = Z-bar * W_l^T
+      {
+        const double* Wl = Wsm + woff(l);
+        double An[4][3][2];
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+#pragma unroll
+          for (int nt = 0; nt < 3; nt++) An[s][nt][0] = An[s][nt][1] = 0.0;
+        mma_layer(An, H, Wl, 1, W, lane);
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+#pragma unroll
+          for (int nt = 0; nt < 3; nt++) { H[s][nt][0] = An[s][nt][0]; H[s][nt][1] = An[s][nt][1]; }
+      }
+      cta_accumulate(Gacc, sm + SM_STAGE, W, W, woff(l), boff(l));
+    }
+
+    // ---------------- reverse: layer 0.  inputs (x^, t^) on the value stream, (sc0,0) on x, (0,sc1) on t
+    act_backward(H, S);
+    stage_rows(ZB, H, lane);
+    if (q == 0) {
+      HA[(0 + g) * W + 0] = xh;   HA[(0 + g) * W + 1] = th;
+      HA[(8 + g) * W + 0] = sc0;  HA[(8 + g) * W + 1] = 0.0;
+      HA[(16 + g) * W + 0] = 0.0; HA[(16 + g) * W + 1] = sc1;
+      HA[(24 + g) * W + 0] = 0.0; HA[(24 + g) * W + 1] = 0.0;
+    }
+    __syncwarp();
+    {
+      double acc[1][3][2];
+      wgrad_mma<1, 3>(acc, HA, ZB, 2, W, lane);
+      __syncwarp();
+      wgrad_store<1, 3>(HA, acc, 2, W, lane);
+    }
+    cta_accumulate(Gacc, sm + SM_STAGE, 2, W, woff(0), boff(0));
+  }
+
+  // ---------------- CTA partial out
+  double* red = sm + SM_RED;
+  loss_d = warp_sum(loss_d); loss_f = warp_sum(loss_f); gl1 = warp_sum(gl1); gl2 = warp_sum(gl2);
+  if (lane == 0) { red[warp * 4 + 0] = loss_d; red[warp * 4 + 1] = loss_f; red[warp * 4 + 2] = gl1; red[warp * 4 + 3] = gl2; }
+  __syncthreads();
+  double* outp = p.partials + (size_t)blockIdx.x * PSTRIDE;
+  for (int i = threadIdx.x; i < P_NET; i += THREADS) outp[i] = Gacc[i];
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = 0, d = 0;
+    for (int w = 0; w < WARPS; w++) { a += red[w * 4 + 0]; b += red[w * 4 + 1]; c += red[w * 4 + 2]; d += red[w * 4 + 3]; }
+    outp[IDX_LD] = a; outp[IDX_LF] = b; outp[IDX_DL1] = c; outp[IDX_DL2] = d;
+    outp[3023] = 0.0;
+  }
+}
+
+}  // namespace burgers
+}  // namespace pinn

@@ -1,0 +1,348 @@
+// Cross-CTA reduction, on-device Adam (TF-2.0 semantics) and the device-resident two-loop L-BFGS.
+// Replaces: utils/neuralnetwork.py:112-116 (+ Keras Adam), utils/custom_lbfgs.py:39-236.
+#pragma once
+#include "pinn_common.cuh"
+
+namespace pinn {
+
+// Layout of the reduced vector R: [0, P) gradient; [P, P+3) loss parts (data|ic, boundary, residual).
+// It is contiguous so that one ncclAllReduce(P+3) covers gradient and loss.
+
+struct LbfgsState {
+  int status;       // PINN_LBFGS_*; 0 = running
+  int n_iter;
+  int n_eval;
+  int k;            // history length
+  int head;         // ring slot of the oldest pair
+  int pending;      // 1: an evaluation has been enqueued whose stop tests have not run yet
+  int max_iter;
+  int n_corr;
+  double max_eval;
+  double lr, tol_fun, tol_x;
+  double h_diag, t, f, f_old;
+};
+
+// ------------------------------------------------------------------------------------------------
+// reduce the per-CTA partial vectors (fixed order -> deterministic).  src index map: gradient entries
+// [0,P_net) map 1:1; extra entries are gathered through `extra_src` (parameter and loss-part slots).
+// ------------------------------------------------------------------------------------------------
+struct ReduceMap {
+  int n_out;          // entries of R to produce
+  int p_net;          // first p_net entries copy 1:1
+  int extra_src[8];   // source column for R[p_net + i]
+  int n_extra;
+};
+
+__global__ void reduce_partials(const double* __restrict__ partials, int n_cta, int stride, double* __restrict__ R,
+                                ReduceMap map, const int* __restrict__ run_flag) {
+  if (run_flag && *run_flag != 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= map.n_out) return;
+  const int src = i < map.p_net ? i : map.extra_src[i - map.p_net];
+  double s = 0.0;
+  for (int b = 0; b < n_cta; b++) s += partials[(size_t)b * stride + src];
+  R[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (ResourceApplyAdam of TF 2.0):  alpha_t = lr sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1);
+// v += (g^2-v)(1-b2); w -= alpha_t m / (sqrt(v)+eps).   step[0] = t (completed steps).
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_update(double* __restrict__ w, double* __restrict__ m, double* __restrict__ v,
+                            const double* __restrict__ R, int P, int* __restrict__ step, double lr, double b1, double b2,
+                            double eps, double* __restrict__ loss_ring, int ring) {
+  const int t = step[0] + 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) {
+    const double alpha = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
+    const double g = R[i];
+    const double mi = m[i] + (g - m[i]) * (1.0 - b1);
+    const double vi = v[i] + (g * g - v[i]) * (1.0 - b2);
+    m[i] = mi;
+    v[i] = vi;
+    w[i] -= (mi * alpha) / (sqrt(vi) + eps);
+  }
+  if (i == 0) loss_ring[(t - 1) % ring] = R[P] + R[P + 1] + R[P + 2];
+}
+// separate, so that no block of adam_update can observe the incremented counter
+__global__ void adam_advance(int* step) { step[0] += 1; }
+
+// ------------------------------------------------------------------------------------------------
+// L-BFGS iteration kernel: ONE CTA; each thread keeps EPT entries of the working vector in registers.
+// Runs (a) the stop tests of the previous iteration's evaluation, (b) the memory update and two-loop
+// recursion, (c) the step, exactly in the reference order (utils/custom_lbfgs.py:81-221).
+// ------------------------------------------------------------------------------------------------
+constexpr int LB_THREADS = 1024;
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();   // protect red[] from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = (lane < (LB_THREADS / 32)) ? red[lane] : 0.0;
+  s = warp_sum(s);
+  return s;   // every thread holds the total
+}
+
+template <int EPT>
+__global__ void __launch_bounds__(LB_THREADS, 1)
+lbfgs_iterate(LbfgsState* __restrict__ st, double* __restrict__ w, const double* __restrict__ R, int P,
+              double* __restrict__ g_old, double* __restrict__ d, double* __restrict__ S, double* __restrict__ Y,
+              double* __restrict__ x_final, double* __restrict__ f_hist, int* __restrict__ logged, int finalize_only) {
+  __shared__ double red[32];
+  __shared__ double ro[128], al[128];
+  const int tid = threadIdx.x;
+  if (st->status != 0) return;
+
+  double gv[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; e++) {
+    const int i = tid + e * LB_THREADS;
+    gv[e] = i < P ? R[i] : 0.0;
+  }
+  const double f_new = R[P] + R[P + 1] + R[P + 2];
+
+  // ---- (a) bookkeeping + stop tests for the evaluation that has just completed
+  if (st->pending) {
+    const int n_iter = st->n_iter;
+    const int n_eval = st->n_eval + 1;
+    double a1 = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; e++) a1 += fabs(gv[e]);
+    a1 = block_sum(a1, red);
+    int status = 0;
+    if (n_iter == 0) {
+      // initial evaluation (custom_lbfgs.py:65-76)
+      if (a1 <= st->tol_fun) status = 7;
+    } else {
+      double a2 = 0.0;
+      const double t = st->t;
+#pragma unroll
+      for (int e = 0; e < EPT; e++) {
+        const int i = tid + e * LB_THREADS;
+        a2 += i < P ? fabs(d[i] * t) : 0.0;
+      }
+      a2 = block_sum(a2, red);
+      if ((double)n_eval >= st->max_eval) status = 2;                    // :195
+      else if (a1 <= st->tol_fun) status = 3;                            // :200-204
+      else if (a2 <= st->tol_x) status = 4;                              // :206-210
+      else if (fabs(f_new - st->f_old) < st->tol_x) status = 5;          // :212-215
+    }
+    __syncthreads();
+    if (tid == 0) {
+      st->n_eval = n_eval;
+      st->f = f_new;
+      st->pending = 0;
+      f_hist[n_eval - 1] = f_new;
+      if (n_iter > 0 && status == 0) logged[n_iter] = 1;                 // :217-218 (log after the stop tests)
+      st->status = status;
+    }
+    __syncthreads();
+    if (status != 0) return;
+  }
+  if (finalize_only) return;
+
+  // ---- (b) direction
+  const int n_iter = st->n_iter + 1;
+  const int n_corr = st->n_corr;
+  double dv[EPT];
+  if (n_iter == 1) {                                                     // :91-95
+#pragma unroll
+    for (int e = 0; e < EPT; e++) dv[e] = -gv[e];
+  } else {
+    const double t_prev = st->t;
+    double yv[EPT], sv[EPT];
+    double ys = 0.0, yy = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+      const int i = tid + e * LB_THREADS;
+      yv[e] = i < P ? gv[e] - g_old[i] : 0.0;                            // :98
+      sv[e] = i < P ? d[i] * t_prev : 0.0;                               // :99
+      ys += yv[e] * sv[e];
+      yy += yv[e] * yv[e];
+    }
+    ys = block_sum(ys, red);
+    int k = st->k, head = st->head;
+    double h_diag = st->h_diag;
+    if (ys > 1e-10) {                                                    // :102-114
+      yy = block_sum(yy, red);
+      int slot;
+      if (k == n_corr) { slot = head; head = (head + 1) % n_corr; }      // drop the oldest pair
+      else { slot = (head + k) % n_corr; k++; }
+#pragma unroll
+      for (int e = 0; e < EPT; e++) {
+        const int i = tid + e * LB_THREADS;
+        if (i < P) { S[(size_t)slot * P + i] = sv[e]; Y[(size_t)slot * P + i] = yv[e]; }
+      }
+      h_diag = ys / yy;
+      __syncthreads();
+    }
+    // ro_i = 1 / (y_i . s_i)   (:121-123), i = 0 oldest
+    for (int i = 0; i < k; i++) {
+      const size_t base = (size_t)((head + i) % n_corr) * P;
+      double a = 0.0;
+#pragma unroll
+      for (int e = 0; e < EPT; e++) {
+        const int j = tid + e * LB_THREADS;
+        a += j < P ? Y[base + j] * S[base + j] : 0.0;
+      }
+      a = block_sum(a, red);
+      if (tid == 0) ro[i] = 1.0 / a;
+    }
+    __syncthreads();
+    double qv[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; e++) qv[e] = -gv[e];                        // :130
+    for (int i = k - 1; i >= 0; i--) {                                   // :131-133
+      const size_t base = (size_t)((head + i) % n_corr) * P;
+      double a = 0.0;
+#pragma unroll
+      for (int e = 0; e < EPT; e++) {
+        const int j = tid + e * LB_THREADS;
+        a += j < P ? S[base + j] * qv[e] : 0.0;
+      }
+      a = block_sum(a, red) * ro[i];
+      if (tid == 0) al[i] = a;
+#pragma unroll
+      for (int e = 0; e < EPT; e++) {
+        const int j = tid + e * LB_THREADS;
+        if (j < P) qv[e] -= a * Y[base + j];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < EPT; e++) qv[e] *= h_diag;                       // :136
+    for (int i = 0; i < k; i++) {                                        // :137-139
+      const size_t base = (size_t)((head + i) % n_corr) * P;
+      double a = 0.0;
+#pragma unroll
+      for (int e = 0; e < EPT; e++) {
+        const int j = tid + e * LB_THREADS;
+        a += j < P ? Y[base + j] * qv[e] : 0.0;
+      }
+      const double be = block_sum(a, red) * ro[i];
+      const double c = al[i] - be;
+#pragma unroll
+      for (int e = 0; e < EPT; e++) {
+        const int j = tid + e * LB_THREADS;
+        if (j < P) qv[e] += c * S[base + j];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; e++) dv[e] = qv[e];
+    if (tid == 0) { st->k = k; st->head = head; st->h_diag = h_diag; }
+  }
+
+  // ---- (c) step
+  double gtd = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int e = 0; e < EPT; e++) { gtd += gv[e] * dv[e]; a1 += fabs(gv[e]); }
+  gtd = block_sum(gtd, red);                                             // :151
+  a1 = block_sum(a1, red);
+  // g_old = g, f_old = f happen before the progress test (:144-145)
+#pragma unroll
+  for (int e = 0; e < EPT; e++) {
+    const int i = tid + e * LB_THREADS;
+    if (i < P) { g_old[i] = gv[e]; d[i] = dv[e]; }
+  }
+  const double f_cur = st->f;
+  if (gtd > -st->tol_x) {                                                // :154-156
+    __syncthreads();
+    if (tid == 0) { st->n_iter = n_iter; st->f_old = f_cur; st->status = 6; }
+    return;
+  }
+  const double t = (n_iter == 1) ? fmin(1.0, 1.0 / a1) : st->lr;         // :159-163
+  const bool last = (n_iter == st->max_iter);
+#pragma unroll
+  for (int e = 0; e < EPT; e++) {
+    const int i = tid + e * LB_THREADS;
+    if (i < P) {
+      const double xn = w[i] + t * dv[e];                                // :174
+      if (last) x_final[i] = xn;       // no evaluation follows (:176-182): the model keeps the previous weights
+      else w[i] = xn;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    st->n_iter = n_iter;
+    st->f_old = f_cur;
+    st->t = t;
+    if (last) st->status = 1;                                            // :192
+    else st->pending = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic (any layer sizes, width <= MAXW) thread-per-point kernels, off the per-step path:
+// forward (predict, utils/neuralnetwork.py:151-153) and forward Taylor-mode derivatives (parity probes,
+// f_model on the stored points).  Weights are read through the read-only path (warp-uniform addresses).
+// ------------------------------------------------------------------------------------------------
+constexpr int MAXW = 128;
+constexpr int MAXL = 16;
+
+struct NetDesc {
+  int n_layers;            // number of Dense layers
+  int dims[MAXL + 1];      // layer sizes
+  int woff[MAXL], boff[MAXL];
+  double lb0, lb1, dx0, dx1;
+};
+
+// NS = 1: values only; NS = 4: (h, h_x, h_t, h_xx)
+template <int NS>
+__global__ void mlp_forward_generic(const double* __restrict__ w, NetDesc nd, const double* __restrict__ X,
+                                    const double* __restrict__ Tsoa, long long n, int in_dim, double* __restrict__ out) {
+  // points either interleaved X[n][in_dim] (Tsoa == nullptr) or SoA (X = x[n], Tsoa = t[n])
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double h[NS][MAXW], z[NS][MAXW];
+  const double x = Tsoa ? X[p] : X[p * in_dim];
+  const double t = Tsoa ? Tsoa[p] : (in_dim == 1 ? x : X[p * in_dim + 1]);
+  h[0][0] = 2.0 * (x - nd.lb0) / nd.dx0 - 1.0;
+  h[0][1] = 2.0 * (t - nd.lb1) / nd.dx1 - 1.0;
+  if (NS == 4) {
+    h[1][0] = 2.0 / nd.dx0; h[1][1] = 0.0;
+    h[2][0] = 0.0;          h[2][1] = 2.0 / nd.dx1;
+    h[3][0] = 0.0;          h[3][1] = 0.0;
+  }
+  for (int l = 0; l < nd.n_layers; l++) {
+    const int fi = nd.dims[l], fo = nd.dims[l + 1];
+    const double* Wl = w + nd.woff[l];
+    const double* bl = w + nd.boff[l];
+    for (int j = 0; j < fo; j++) {
+      double acc[NS];
+      acc[0] = __ldg(bl + j);
+#pragma unroll
+      for (int s = 1; s < NS; s++) acc[s] = 0.0;
+      for (int i = 0; i < fi; i++) {
+        const double wv = __ldg(Wl + i * fo + j);
+#pragma unroll
+        for (int s = 0; s < NS; s++) acc[s] = fma(h[s][i], wv, acc[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < NS; s++) z[s][j] = acc[s];
+    }
+    const bool last = (l == nd.n_layers - 1);
+    for (int j = 0; j < fo; j++) {
+      if (last) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) h[s][j] = z[s][j];
+      } else {
+        const double a = tanh(z[0][j]);
+        h[0][j] = a;
+        if (NS == 4) {
+          const double sd = fma(-a, a, 1.0);
+          const double zx = z[1][j];
+          h[1][j] = sd * zx;
+          h[2][j] = sd * z[2][j];
+          h[3][j] = sd * fma(-2.0 * a * zx, zx, z[3][j]);
+        }
+      }
+    }
+  }
+  const int no = nd.dims[nd.n_layers];
+  for (int s = 0; s < NS; s++)
+    for (int j = 0; j < no; j++) out[p * (NS * no) + s * no + j] = h[s][j];
+}
+
+}  // namespace pinn

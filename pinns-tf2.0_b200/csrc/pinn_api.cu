@@ -1,0 +1,738 @@
+// libpinn_b200.so -- C ABI (include/pinn_b200.h) over the fused sm_100a PINN kernels.
+#include "../../include/pinn_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "burgers_fused.cuh"
+#include "nls_fused.cuh"
+#include "optim_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return -1; }
+
+#define CUDA_TRY(expr)                                                                                         \
+  do {                                                                                                         \
+    cudaError_t _e = (expr);                                                                                   \
+    if (_e != cudaSuccess)                                                                                     \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+// ---- NCCL, resolved at run time (torch's bundled libnccl.so.2 is already in the process under torchrun;
+// otherwise the system one is opened).  Only the five entry points the path needs.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& why) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { why = "NCCL symbols missing"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8;   // ncclDouble
+constexpr int NCCL_SUM = 0;       // ncclSum
+
+constexpr int LOSS_RING = 4096;
+
+}  // namespace
+
+struct pinn_handle {
+  int pde = 0, device = 0, rank = 0, world = 1;
+  std::vector<int> layers;
+  double lb[2] = {0, 0}, ub[2] = {1, 1};
+  int P_net = 0, P = 0;             // net parameters; P = P_net (+2 identification)
+  double nu = 0.0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int n_sm = 0;
+  long long launches = 0;
+
+  // parameters and optimiser state
+  double* d_w = nullptr;            // WPAD-padded flat weights
+  int w_cap = 0;
+  double* d_R = nullptr;            // [P grad | 3 loss parts | pad]
+  double* d_partials = nullptr;
+  int n_cta = 0, pstride = 0;
+  double *d_m = nullptr, *d_v = nullptr;
+  int* d_step = nullptr;
+  double* d_loss_ring = nullptr;
+  long long adam_steps = 0;
+
+  // point sets (device SoA x[], t[]).  Layout: [data region, capacity dcap | collocation region, capacity ccap];
+  // data points are stored right-aligned in their region so that [data | collocation] is contiguous:
+  // kernel point 0 is at offset dcap - n_d.  A per-step collocation upload touches only its own region.
+  double *d_x = nullptr, *d_t = nullptr, *d_u = nullptr;
+  long long dcap = 0, ccap = 0, u_cap = 0;
+  long long n_c = 0, n_c_global = 0, n_d = 0, n_b = 0;
+  int d_out_dim = 1;
+  double data_weight = 1.0;
+  std::vector<double> h_tb;                 // NLS boundary times
+  std::vector<double> stage_x, stage_t;     // host staging for set_data (de-interleave)
+
+  // measurement
+  std::vector<cudaEvent_t> events;
+  double* d_flush = nullptr;
+  size_t flush_bytes = 0;
+
+  // L-BFGS
+  pinn::LbfgsState* d_lb = nullptr;
+  double *d_gold = nullptr, *d_d = nullptr, *d_S = nullptr, *d_Y = nullptr, *d_xfinal = nullptr, *d_fhist = nullptr;
+  int* d_logged = nullptr;
+  int lb_corr_cap = 0, lb_iter_cap = 0;
+
+  // scratch for predict / derivatives
+  double *d_px = nullptr, *d_pout = nullptr;
+  long long px_cap = 0, pout_cap = 0;
+
+  ncclComm_t comm = nullptr;
+};
+
+namespace {
+
+bool is_burgers_net(const std::vector<int>& L) {
+  if (L.size() != 10 || L[0] != 2 || L[9] != 1) return false;
+  for (int i = 1; i <= 8; i++) if (L[i] != 20) return false;
+  return true;
+}
+bool is_nls_net(const std::vector<int>& L) {
+  if (L.size() != 6 || L[0] != 2 || L[5] != 2) return false;
+  for (int i = 1; i <= 4; i++) if (L[i] != 100) return false;
+  return true;
+}
+
+int nls_upload_points(pinn_t* h);
+int nls_launch_eval(pinn_t* h, const int* run_flag);
+
+pinn::NetDesc net_desc(const pinn_t* h) {
+  pinn::NetDesc nd{};
+  nd.n_layers = (int)h->layers.size() - 1;
+  int o = 0;
+  for (int l = 0; l < nd.n_layers; l++) {
+    nd.dims[l] = h->layers[l];
+    nd.woff[l] = o; o += h->layers[l] * h->layers[l + 1];
+    nd.boff[l] = o; o += h->layers[l + 1];
+  }
+  nd.dims[nd.n_layers] = h->layers.back();
+  nd.lb0 = h->lb[0]; nd.lb1 = h->lb[1];
+  nd.dx0 = h->ub[0] - h->lb[0]; nd.dx1 = h->ub[1] - h->lb[1];
+  return nd;
+}
+
+int ensure(double** p, long long* cap, long long need) {
+  if (need <= *cap) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  long long c = need + need / 8 + 64;
+  if (cudaMalloc((void**)p, (size_t)c * sizeof(double)) != cudaSuccess) return fail("cudaMalloc failed");
+  *cap = c;
+  return 0;
+}
+
+// grow the point arrays, preserving both regions
+int ensure_points(pinn_t* h, long long need_d, long long need_c) {
+  if (need_d <= h->dcap && need_c <= h->ccap && h->d_x) return 0;
+  long long nd = h->dcap, nc = h->ccap;
+  if (need_d > nd) nd = need_d + need_d / 4 + 1024;
+  if (need_c > nc) nc = need_c + need_c / 8 + 1024;
+  if (nd < 1024) nd = 1024;
+  double *nx = nullptr, *nt = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&nx, (size_t)(nd + nc) * 8));
+  CUDA_TRY(cudaMalloc((void**)&nt, (size_t)(nd + nc) * 8));
+  if (h->d_x) {
+    if (h->n_d) {
+      CUDA_TRY(cudaMemcpyAsync(nx + nd - h->n_d, h->d_x + h->dcap - h->n_d, h->n_d * 8, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(cudaMemcpyAsync(nt + nd - h->n_d, h->d_t + h->dcap - h->n_d, h->n_d * 8, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (h->n_c) {
+      CUDA_TRY(cudaMemcpyAsync(nx + nd, h->d_x + h->dcap, h->n_c * 8, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(cudaMemcpyAsync(nt + nd, h->d_t + h->dcap, h->n_c * 8, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_x); cudaFree(h->d_t);
+  }
+  h->d_x = nx; h->d_t = nt; h->dcap = nd; h->ccap = nc;
+  return 0;
+}
+
+int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
+  if (h->pde == PINN_BURGERS_INF || h->pde == PINN_BURGERS_IDE) {
+    namespace B = pinn::burgers;
+    const bool ide = h->pde == PINN_BURGERS_IDE;
+    const long long n_total = ide ? h->n_d : h->n_d + h->n_c;
+    if (n_total <= 0) return fail("no points set (pinn_set_collocation / pinn_set_data)");
+    B::Args a{};
+    a.w = h->d_w;
+    a.x = h->d_x + (h->dcap - h->n_d); a.t = h->d_t + (h->dcap - h->n_d); a.utgt = h->d_u;
+    a.n_total = n_total;
+    a.c0 = ide ? 0 : h->n_d;
+    a.n_c = ide ? h->n_d : h->n_c;
+    a.d0 = 0;
+    a.n_d = h->n_d;
+    const long long nfg = ide ? h->n_d : h->n_c_global;
+    a.wf = nfg > 0 ? 1.0 / (double)nfg : 0.0;
+    a.wd = h->n_d > 0 ? h->data_weight / (double)h->n_d : 0.0;
+    a.lb0 = h->lb[0]; a.lb1 = h->lb[1];
+    a.dx0 = h->ub[0] - h->lb[0]; a.dx1 = h->ub[1] - h->lb[1];
+    a.nu = h->nu; a.ide = ide ? 1 : 0;
+    a.partials = h->d_partials;
+    a.run_flag = run_flag;
+    const long long rounds = (n_total + B::ROUND - 1) / B::ROUND;
+    int grid = (int)(rounds < h->n_cta ? rounds : h->n_cta);
+    B::fused_loss_grad<<<grid, B::THREADS, B::SMEM_BYTES, h->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    if (fused_only) return 0;
+    pinn::ReduceMap map{};
+    map.p_net = B::P_NET;
+    map.n_extra = 0;
+    if (ide) { map.extra_src[map.n_extra++] = B::IDX_DL1; map.extra_src[map.n_extra++] = B::IDX_DL2; }
+    map.extra_src[map.n_extra++] = B::IDX_LD;
+    map.extra_src[map.n_extra++] = 3023;        // (boundary part: always 0 for Burgers)
+    map.extra_src[map.n_extra++] = B::IDX_LF;
+    map.n_out = map.p_net + map.n_extra;
+    pinn::reduce_partials<<<(map.n_out + 127) / 128, 128, 0, h->stream>>>(h->d_partials, grid, B::PSTRIDE, h->d_R, map, run_flag);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  } else {
+    if (nls_launch_eval(h, run_flag)) return -1;
+  }
+  if (h->world > 1) {
+    // one allreduce over [gradient | loss parts].  A skipped evaluation (L-BFGS stopped) still
+    // joins the collective with stale but rank-identical participation so that ranks never diverge.
+    int rc = g_nccl.AllReduce(h->d_R, h->d_R, (size_t)h->P + 3, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+    if (rc != 0) return fail(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+  }
+  return 0;
+}
+
+int nls_upload_points(pinn_t*) { return fail("NLS fused kernel: not built yet"); }
+int nls_launch_eval(pinn_t*, const int*) { return fail("NLS fused kernel: not built yet"); }
+
+}  // namespace
+
+extern "C" {
+
+const char* pinn_last_error(void) { return g_err.c_str(); }
+const char* pinn_version(void) { return "pinn_b200 0.1 (sm_100a, fp64 DMMA)"; }
+
+int pinn_nccl_unique_id(void* out128) {
+  std::string why;
+  if (!g_nccl.load(why)) return fail(why);
+  ncclUniqueId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail("ncclGetUniqueId failed");
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const double lb[2], const double ub[2],
+                int device, int rank, int world, const void* nccl_uid) {
+  if (!out || !layers || !lb || !ub) return fail("pinn_create: null argument");
+  if (n_layers < 3 || n_layers > pinn::MAXL) return fail("pinn_create: need 3..16 layer sizes");
+  if (pde_id < 0 || pde_id > 2) return fail("pinn_create: unknown pde_id");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("pinn_create: no CUDA device -- this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail("pinn_create: bad device index");
+  pinn_t* h = new pinn_t();
+  h->pde = pde_id; h->device = device; h->rank = rank; h->world = world < 1 ? 1 : world;
+  h->layers.assign(layers, layers + n_layers);
+  for (int v : h->layers) if (v < 1 || v > pinn::MAXW) { delete h; return fail("pinn_create: layer width out of range (1..128)"); }
+  if (h->layers[0] != 2) { delete h; return fail("pinn_create: input dimension must be 2 (x,t)"); }
+  h->lb[0] = lb[0]; h->lb[1] = lb[1]; h->ub[0] = ub[0]; h->ub[1] = ub[1];
+  if (!(ub[0] > lb[0]) || !(ub[1] > lb[1])) { delete h; return fail("pinn_create: need ub > lb"); }
+  bool ok_net = (pde_id == PINN_NLS_INF) ? is_nls_net(h->layers) : is_burgers_net(h->layers);
+  if (!ok_net) {
+    delete h;
+    return fail(pde_id == PINN_NLS_INF ? "pinn_create: the fused NLS kernel is specialised for layers [2,100,100,100,100,2]"
+                                        : "pinn_create: the fused Burgers kernel is specialised for layers [2,20x8,1]");
+  }
+  h->P_net = 0;
+  for (int l = 0; l + 1 < n_layers; l++) h->P_net += layers[l] * layers[l + 1] + layers[l + 1];
+  h->P = h->P_net + (pde_id == PINN_BURGERS_IDE ? 2 : 0);
+
+#define CREATE_TRY(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      fail(std::string(#expr) + ": " + cudaGetErrorString(_e));                                   \
+      pinn_destroy(h);                                                                            \
+      return -1;                                                                                  \
+    }                                                                                             \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    fail(std::string("pinn_create: device '") + prop.name + "' is not sm_100 class; this library is built for sm_100a only");
+    pinn_destroy(h);
+    return -1;
+  }
+  h->n_sm = prop.multiProcessorCount;
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CREATE_TRY(cudaEventCreate(&h->ev0));
+  CREATE_TRY(cudaEventCreate(&h->ev1));
+  h->w_cap = ((h->P + 3 + 63) / 64) * 64 + 64;
+  if (h->w_cap < pinn::burgers::WPAD) h->w_cap = pinn::burgers::WPAD;
+  CREATE_TRY(cudaMalloc((void**)&h->d_w, h->w_cap * 8));
+  CREATE_TRY(cudaMemset(h->d_w, 0, h->w_cap * 8));
+  CREATE_TRY(cudaMalloc((void**)&h->d_R, h->w_cap * 8));
+  CREATE_TRY(cudaMemset(h->d_R, 0, h->w_cap * 8));
+  CREATE_TRY(cudaMalloc((void**)&h->d_m, h->w_cap * 8));
+  CREATE_TRY(cudaMalloc((void**)&h->d_v, h->w_cap * 8));
+  CREATE_TRY(cudaMemset(h->d_m, 0, h->w_cap * 8));
+  CREATE_TRY(cudaMemset(h->d_v, 0, h->w_cap * 8));
+  CREATE_TRY(cudaMalloc((void**)&h->d_step, 16));
+  CREATE_TRY(cudaMemset(h->d_step, 0, 16));
+  CREATE_TRY(cudaMalloc((void**)&h->d_loss_ring, LOSS_RING * 8));
+  CREATE_TRY(cudaMemset(h->d_loss_ring, 0, LOSS_RING * 8));
+  CREATE_TRY(cudaMalloc((void**)&h->d_lb, sizeof(pinn::LbfgsState)));
+  CREATE_TRY(cudaMemset(h->d_lb, 0, sizeof(pinn::LbfgsState)));
+  if (pde_id == PINN_NLS_INF) {
+    h->n_cta = pinn::nls::grid_size(h->n_sm);
+    h->pstride = pinn::nls::PSTRIDE;
+    CREATE_TRY(cudaFuncSetAttribute(pinn::nls::fused_loss_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, pinn::nls::SMEM_BYTES));
+  } else {
+    h->n_cta = h->n_sm;
+    h->pstride = pinn::burgers::PSTRIDE;
+    CREATE_TRY(cudaFuncSetAttribute(pinn::burgers::fused_loss_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, pinn::burgers::SMEM_BYTES));
+  }
+  CREATE_TRY(cudaMalloc((void**)&h->d_partials, (size_t)h->n_cta * h->pstride * 8));
+  CREATE_TRY(cudaMemset(h->d_partials, 0, (size_t)h->n_cta * h->pstride * 8));
+  if (h->world > 1) {
+    std::string why;
+    if (!nccl_uid) { fail("pinn_create: world > 1 needs an ncclUniqueId"); pinn_destroy(h); return -1; }
+    if (!g_nccl.load(why)) { fail(why); pinn_destroy(h); return -1; }
+    ncclUniqueId id;
+    memcpy(&id, nccl_uid, 128);
+    int rc = g_nccl.CommInitRank(&h->comm, h->world, id, h->rank);
+    if (rc != 0) { fail(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); pinn_destroy(h); return -1; }
+  }
+  *out = h;
+  return 0;
+}
+
+int pinn_destroy(pinn_t* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  double* bufs[] = {h->d_w, h->d_R, h->d_partials, h->d_m, h->d_v, h->d_loss_ring, h->d_x, h->d_t, h->d_u, h->d_gold,
+                    h->d_d, h->d_S, h->d_Y, h->d_xfinal, h->d_fhist, h->d_px, h->d_pout};
+  for (double* b : bufs) if (b) cudaFree(b);
+  if (h->d_step) cudaFree(h->d_step);
+  if (h->d_lb) cudaFree(h->d_lb);
+  if (h->d_logged) cudaFree(h->d_logged);
+  for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+  if (h->d_flush) cudaFree(h->d_flush);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int64_t pinn_num_params(const pinn_t* h) { return h ? h->P : -1; }
+
+int pinn_set_pde_params(pinn_t* h, const double* p, int n) {
+  if (!h) return fail("null handle");
+  if (h->pde == PINN_BURGERS_INF) {
+    if (n != 1 || !p) return fail("pinn_set_pde_params: BURGERS_INF takes exactly one parameter (nu)");
+    h->nu = p[0];
+    return 0;
+  }
+  if (n != 0) return fail("pinn_set_pde_params: this PDE takes no constants");
+  return 0;
+}
+
+int pinn_set_collocation(pinn_t* h, const double* x, const double* t, int64_t n, int64_t n_global) {
+  if (!h) return fail("null handle");
+  if (h->pde == PINN_BURGERS_IDE) return fail("pinn_set_collocation: identification uses the data points as residual points");
+  if (n < 0 || (n > 0 && (!x || !t))) return fail("pinn_set_collocation: bad arguments");
+  if (n_global < n) return fail("pinn_set_collocation: n_global < n");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (ensure_points(h, h->n_d, n)) return -1;
+  if (n) {
+    // straight from the caller's buffer into the collocation region (truly asynchronous when it is pinned)
+    CUDA_TRY(cudaMemcpyAsync(h->d_x + h->dcap, x, n * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_t + h->dcap, t, n * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));   // the buffers are only borrowed for the call
+  }
+  h->n_c = n; h->n_c_global = n_global;
+  return 0;
+}
+
+int pinn_set_data(pinn_t* h, const double* X, int64_t n, int in_dim, const double* u, int out_dim, double weight) {
+  if (!h) return fail("null handle");
+  if (n < 0 || (n > 0 && (!X || !u))) return fail("pinn_set_data: bad arguments");
+  if (in_dim != 1 && in_dim != 2) return fail("pinn_set_data: in_dim must be 1 (broadcast quirk) or 2");
+  if (out_dim != h->layers.back()) return fail("pinn_set_data: out_dim does not match the network head");
+  CUDA_TRY(cudaSetDevice(h->device));
+  // shrinking/growing the data set moves its right-aligned start; the collocation region is untouched
+  if (ensure_points(h, n, h->n_c)) return -1;
+  h->stage_x.resize(n); h->stage_t.resize(n);
+  for (int64_t i = 0; i < n; i++) {
+    h->stage_x[i] = X[i * in_dim];
+    h->stage_t[i] = in_dim == 1 ? X[i] : X[i * in_dim + 1];   // (N,1) input broadcast by the Lambda: t := x
+  }
+  if (n) {
+    if (ensure(&h->d_u, &h->u_cap, n * out_dim)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(h->d_x + h->dcap - n, h->stage_x.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_t + h->dcap - n, h->stage_t.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_u, u, n * out_dim * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  h->n_d = n; h->d_out_dim = out_dim; h->data_weight = weight;
+  return 0;
+}
+
+int pinn_set_boundary(pinn_t* h, const double* tb, int64_t n_b) {
+  if (!h) return fail("null handle");
+  if (h->pde != PINN_NLS_INF) return fail("pinn_set_boundary: only the NLS problem has a boundary term");
+  if (n_b < 0 || (n_b > 0 && !tb)) return fail("pinn_set_boundary: bad arguments");
+  h->h_tb.assign(tb, tb + n_b);
+  h->n_b = n_b;
+  return 0;
+}
+
+int pinn_set_weights(pinn_t* h, const double* w, int64_t n) {
+  if (!h || !w) return fail("pinn_set_weights: null argument");
+  if (n != h->P) return fail("pinn_set_weights: expected " + std::to_string(h->P) + " values, got " + std::to_string(n));
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(h->d_w, w, n * 8, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pinn_get_weights(pinn_t* h, double* w, int64_t n) {
+  if (!h || !w) return fail("pinn_get_weights: null argument");
+  if (n != h->P) return fail("pinn_get_weights: expected " + std::to_string(h->P) + " values, got " + std::to_string(n));
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(w, h->d_w, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pinn_loss_grad(pinn_t* h, const double* w_or_null, double* loss_out, double* grad_out_or_null,
+                   double* parts_out_or_null) {
+  if (!h) return fail("null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (w_or_null) CUDA_TRY(cudaMemcpyAsync(h->d_w, w_or_null, h->P * 8, cudaMemcpyHostToDevice, h->stream));
+  if (launch_eval(h, nullptr)) return -1;
+  double parts[3];
+  CUDA_TRY(cudaMemcpyAsync(parts, h->d_R + h->P, 24, cudaMemcpyDeviceToHost, h->stream));
+  if (grad_out_or_null) CUDA_TRY(cudaMemcpyAsync(grad_out_or_null, h->d_R, h->P * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (loss_out) *loss_out = parts[0] + parts[1] + parts[2];
+  if (parts_out_or_null) { parts_out_or_null[0] = parts[0]; parts_out_or_null[1] = parts[1]; parts_out_or_null[2] = parts[2]; }
+  return 0;
+}
+
+int pinn_adam_step(pinn_t* h, double lr, double b1, double b2, double eps, double* loss_out_or_null) {
+  if (!h) return fail("null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (launch_eval(h, nullptr)) return -1;
+  pinn::adam_update<<<(h->P + 127) / 128, 128, 0, h->stream>>>(h->d_w, h->d_m, h->d_v, h->d_R, h->P, h->d_step, lr, b1, b2,
+                                                                 eps, h->d_loss_ring, LOSS_RING);
+  CUDA_TRY(cudaGetLastError());
+  pinn::adam_advance<<<1, 1, 0, h->stream>>>(h->d_step);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 2;
+  h->adam_steps++;
+  if (loss_out_or_null) {
+    CUDA_TRY(cudaMemcpyAsync(loss_out_or_null, h->d_loss_ring + ((h->adam_steps - 1) % LOSS_RING), 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+int pinn_adam_reset(pinn_t* h) {
+  if (!h) return fail("null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_m, 0, h->w_cap * 8, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_v, 0, h->w_cap * 8, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_step, 0, 16, h->stream));
+  h->adam_steps = 0;
+  return 0;
+}
+
+int pinn_last_loss(pinn_t* h, double* loss_out) {
+  if (!h || !loss_out) return fail("null argument");
+  if (h->adam_steps == 0) return fail("pinn_last_loss: no Adam step has run");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpyAsync(loss_out, h->d_loss_ring + ((h->adam_steps - 1) % LOSS_RING), 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, double tol_fun, double tol_x,
+               int sync_every, pinn_log_cb log_cb, void* user, int* n_iter_out, int* n_eval_out, int* reason_out,
+               double* x_final_or_null) {
+  if (!h) return fail("null handle");
+  if (n_iter_out) *n_iter_out = 0;
+  if (n_eval_out) *n_eval_out = 0;
+  if (reason_out) *reason_out = PINN_LBFGS_RUNNING;
+  if (max_iter == 0) return 0;                                      // custom_lbfgs.py:43-44
+  if (max_iter < 0) return fail("pinn_lbfgs: max_iter < 0");
+  if (n_correction <= 0) n_correction = 100;                        // :52 (`or 100`)
+  if (n_correction > 128) return fail("pinn_lbfgs: n_correction > 128 not supported");
+  if (learning_rate == 0.0) learning_rate = 1.0;                    // :55
+  if (tol_fun == 0.0) tol_fun = 1e-5;                               // :50
+  if (tol_x == 0.0) tol_x = 1e-19;                                  // :51
+  if (sync_every < 1) sync_every = 1;
+  const int P = h->P;
+  const int ept = (P + pinn::LB_THREADS - 1) / pinn::LB_THREADS;
+  if (ept > 32) return fail("pinn_lbfgs: parameter vector too large for the single-CTA L-BFGS kernel");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->d_gold) {
+    CUDA_TRY(cudaMalloc((void**)&h->d_gold, h->w_cap * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_d, h->w_cap * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_xfinal, h->w_cap * 8));
+  }
+  if (n_correction > h->lb_corr_cap) {
+    if (h->d_S) cudaFree(h->d_S);
+    if (h->d_Y) cudaFree(h->d_Y);
+    h->d_S = h->d_Y = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&h->d_S, (size_t)n_correction * P * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_Y, (size_t)n_correction * P * 8));
+    h->lb_corr_cap = n_correction;
+  }
+  if (max_iter + 2 > h->lb_iter_cap) {
+    if (h->d_fhist) cudaFree(h->d_fhist);
+    if (h->d_logged) cudaFree(h->d_logged);
+    h->d_fhist = nullptr; h->d_logged = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&h->d_fhist, (size_t)(max_iter + 2) * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_logged, (size_t)(max_iter + 2) * 4));
+    h->lb_iter_cap = max_iter + 2;
+  }
+  CUDA_TRY(cudaMemsetAsync(h->d_logged, 0, (size_t)(max_iter + 2) * 4, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->d_fhist, 0, (size_t)(max_iter + 2) * 8, h->stream));
+  pinn::LbfgsState st{};
+  st.status = 0; st.n_iter = 0; st.n_eval = 0; st.k = 0; st.head = 0; st.pending = 1;
+  st.max_iter = max_iter; st.n_corr = n_correction;
+  st.max_eval = max_iter * 1.25;                                    // :49
+  st.lr = learning_rate; st.tol_fun = tol_fun; st.tol_x = tol_x;
+  st.h_diag = 1.0; st.t = 0.0; st.f = 0.0; st.f_old = 0.0;
+  CUDA_TRY(cudaMemcpyAsync(h->d_lb, &st, sizeof(st), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));   // st is a stack object
+  const int* run_flag = &h->d_lb->status;
+  if (launch_eval(h, run_flag)) return -1;      // initial f, g (:65)
+
+  std::vector<double> fh(max_iter + 2);
+  std::vector<int> lg(max_iter + 2);
+  int reported = 0;
+  auto iterate = [&](int fin) -> int {
+#define LB_LAUNCH(E)                                                                                                   \
+  pinn::lbfgs_iterate<E><<<1, pinn::LB_THREADS, 0, h->stream>>>(h->d_lb, h->d_w, h->d_R, P, h->d_gold, h->d_d, h->d_S, \
+                                                                h->d_Y, h->d_xfinal, h->d_fhist, h->d_logged, fin)
+    if (ept <= 3) LB_LAUNCH(3);
+    else if (ept <= 8) LB_LAUNCH(8);
+    else LB_LAUNCH(32);
+#undef LB_LAUNCH
+    if (cudaGetLastError() != cudaSuccess) return fail("lbfgs_iterate launch failed");
+    h->launches++;
+    return 0;
+  };
+  while (true) {
+    for (int b = 0; b < sync_every; b++) {
+      if (iterate(0)) return -1;
+      if (launch_eval(h, run_flag)) return -1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(&st, h->d_lb, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(fh.data(), h->d_fhist, (size_t)(max_iter + 2) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(lg.data(), h->d_logged, (size_t)(max_iter + 2) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    // iterations whose stop tests have run: all < n_iter, plus n_iter itself unless its evaluation is pending
+    const int upto = st.pending ? st.n_iter - 1 : st.n_iter;
+    for (int it = reported + 1; it <= upto; it++)
+      if (lg[it] && log_cb) log_cb(it, fh[it], user);
+    if (upto > reported) reported = upto;
+    if (st.status != 0) break;
+  }
+  if (n_iter_out) *n_iter_out = st.n_iter;
+  if (n_eval_out) *n_eval_out = st.n_eval;
+  if (reason_out) *reason_out = st.status;
+  if (x_final_or_null) {
+    // x after the loop: differs from the model weights only when the loop ended on max_iter (the last update
+    // is not evaluated, utils/custom_lbfgs.py:176-182; utils/neuralnetwork.py:131-136 ignores the return).
+    const double* src = (st.status == PINN_LBFGS_MAX_ITER) ? h->d_xfinal : h->d_w;
+    CUDA_TRY(cudaMemcpyAsync(x_final_or_null, src, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+// generic thread-per-point forward on host points (X != nullptr) or on a device SoA range (dx, dt)
+static int forward_generic(pinn_t* h, const double* X, const double* dx, const double* dt, int64_t n, int in_dim, double* out,
+                           int ns) {
+  if (!h || !out || (!X && !dx)) return fail("null argument");
+  if (n <= 0) return 0;
+  if (in_dim != 1 && in_dim != 2) return fail("in_dim must be 1 or 2");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int no = h->layers.back();
+  if (ensure(&h->d_pout, &h->pout_cap, n * no * ns)) return -1;
+  if (X) {
+    if (ensure(&h->d_px, &h->px_cap, n * in_dim)) return -1;
+    CUDA_TRY(cudaMemcpyAsync(h->d_px, X, n * in_dim * 8, cudaMemcpyHostToDevice, h->stream));
+    dx = h->d_px; dt = nullptr;
+  }
+  pinn::NetDesc nd = net_desc(h);
+  const int threads = 64;
+  const int blocks = (int)((n + threads - 1) / threads);
+  if (ns == 1) pinn::mlp_forward_generic<1><<<blocks, threads, 0, h->stream>>>(h->d_w, nd, dx, dt, n, in_dim, h->d_pout);
+  else pinn::mlp_forward_generic<4><<<blocks, threads, 0, h->stream>>>(h->d_w, nd, dx, dt, n, in_dim, h->d_pout);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  CUDA_TRY(cudaMemcpyAsync(out, h->d_pout, n * no * ns * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pinn_predict(pinn_t* h, const double* X, int64_t n, int in_dim, double* out) {
+  return forward_generic(h, X, nullptr, nullptr, n, in_dim, out, 1);
+}
+
+int pinn_derivatives(pinn_t* h, const double* X, int64_t n, double* out) {
+  return forward_generic(h, X, nullptr, nullptr, n, 2, out, 4);
+}
+
+int pinn_residual(pinn_t* h, double* f_out) {
+  if (!h || !f_out) return fail("null argument");
+  const bool ide = h->pde == PINN_BURGERS_IDE;
+  const int64_t n = ide ? h->n_d : h->n_c;
+  if (n == 0) return 0;
+  const long long off = ide ? h->dcap - h->n_d : h->dcap;
+  std::vector<double> D(n * 4 * h->layers.back());
+  if (forward_generic(h, nullptr, h->d_x + off, h->d_t + off, n, 2, D.data(), 4)) return -1;
+  if (h->pde == PINN_NLS_INF) {
+    for (int64_t i = 0; i < n; i++) {
+      const double* d = &D[i * 8];
+      const double u = d[0], v = d[1], ut = d[4], vt = d[5], uxx = d[6], vxx = d[7];
+      const double h2 = u * u + v * v;
+      f_out[2 * i] = ut + 0.5 * vxx + h2 * v;
+      f_out[2 * i + 1] = vt - 0.5 * uxx - h2 * u;
+    }
+    return 0;
+  }
+  double l1 = 1.0, kap = h->nu;
+  if (ide) {
+    double lam[2];
+    CUDA_TRY(cudaMemcpy(lam, h->d_w + h->P_net, 16, cudaMemcpyDeviceToHost));
+    l1 = lam[0]; kap = std::exp(lam[1]);
+  }
+  for (int64_t i = 0; i < n; i++) {
+    const double* d = &D[i * 4];
+    f_out[i] = d[2] + l1 * d[0] * d[1] - kap * d[3];
+  }
+  return 0;
+}
+
+int pinn_sync(pinn_t* h) {
+  if (!h) return fail("null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pinn_host_alloc(void** out, int64_t bytes) {
+  if (!out || bytes <= 0) return fail("pinn_host_alloc: bad arguments");
+  CUDA_TRY(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+  return 0;
+}
+int pinn_host_free(void* p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return 0;
+}
+
+int pinn_time_loss_grad_kernel(pinn_t* h, int iters, float* ms_total_out) {
+  if (!h || !ms_total_out || iters < 1) return fail("pinn_time_loss_grad_kernel: bad arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int world = h->world;
+  h->world = 1;   // kernel only: no collective inside the timed region
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  int rc = 0;
+  for (int i = 0; i < iters && rc == 0; i++) rc = launch_eval(h, nullptr, true);
+  h->world = world;
+  if (rc) return -1;
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  CUDA_TRY(cudaEventElapsedTime(ms_total_out, h->ev0, h->ev1));
+  return 0;
+}
+
+int pinn_event_record(pinn_t* h, int idx) {
+  if (!h || idx < 0 || idx >= 65536) return fail("pinn_event_record: bad arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  while ((int)h->events.size() <= idx) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    h->events.push_back(e);
+  }
+  CUDA_TRY(cudaEventRecord(h->events[idx], h->stream));
+  return 0;
+}
+
+int pinn_event_elapsed_ms(pinn_t* h, int i, int j, float* ms_out) {
+  if (!h || !ms_out || i < 0 || j < 0 || i >= (int)h->events.size() || j >= (int)h->events.size())
+    return fail("pinn_event_elapsed_ms: bad arguments");
+  CUDA_TRY(cudaEventSynchronize(h->events[j]));
+  CUDA_TRY(cudaEventElapsedTime(ms_out, h->events[i], h->events[j]));
+  return 0;
+}
+
+int pinn_flush_l2(pinn_t* h) {
+  if (!h) return fail("null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->d_flush) {
+    h->flush_bytes = (size_t)256 << 20;   // > 126 MB L2
+    CUDA_TRY(cudaMalloc((void**)&h->d_flush, h->flush_bytes));
+  }
+  CUDA_TRY(cudaMemsetAsync(h->d_flush, 0, h->flush_bytes, h->stream));
+  return 0;
+}
+
+int64_t pinn_launch_count(const pinn_t* h) { return h ? h->launches : -1; }
+
+int pinn_kernel_info(pinn_t* h, char* buf, int buflen) {
+  if (!h || !buf || buflen < 1) return fail("bad arguments");
+  cudaFuncAttributes fa{};
+  int smem = 0, threads = 0;
+  if (h->pde == PINN_NLS_INF) {
+    CUDA_TRY(cudaFuncGetAttributes(&fa, pinn::nls::fused_loss_grad));
+    smem = pinn::nls::SMEM_BYTES; threads = pinn::nls::THREADS;
+  } else {
+    CUDA_TRY(cudaFuncGetAttributes(&fa, pinn::burgers::fused_loss_grad));
+    smem = pinn::burgers::SMEM_BYTES; threads = pinn::burgers::THREADS;
+  }
+  snprintf(buf, buflen, "{\"grid\": %d, \"block\": %d, \"dyn_smem\": %d, \"regs\": %d, \"local_bytes\": %zu, \"sms\": %d}",
+           h->n_cta, threads, smem, fa.numRegs, fa.localSizeBytes, h->n_sm);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+"""CPU: libpinn_b200.so builds for sm_100a, loads, and exports every symbol include/pinn_b200.h declares.
+No compute calls here (no GPU in the build container)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "pinn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(pinn_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(n for n in names if n not in ("pinn_log_cb",)))
+
+
+def test_header_declares_the_survey_contract():
+    names = header_functions()
+    for need in ("pinn_create", "pinn_set_collocation", "pinn_set_data", "pinn_set_boundary", "pinn_set_weights",
+                 "pinn_get_weights", "pinn_loss_grad", "pinn_adam_step", "pinn_lbfgs", "pinn_predict", "pinn_residual",
+                 "pinn_sync", "pinn_destroy", "pinn_last_error"):
+        assert need in names
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    lib = ctypes.CDLL(lib_built)
+    for name in header_functions():
+        assert hasattr(lib, name), f"{name} declared in include/pinn_b200.h but not exported"
+
+
+def test_binding_covers_header(lib_built):
+    import pinn_cabi
+    assert sorted(pinn_cabi.SIGNATURES) == header_functions()
+    pinn_cabi.load()
+
+
+def test_sass_is_sm100a_with_dmma_and_tma(lib_built):
+    out = subprocess.run(["cuobjdump", "-sass", lib_built], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "DMMA.8x8x4" in out          # FP64 tensor-core MMA in the fused kernel
+    assert "UBLKCP" in out              # TMA bulk copy staging the weights
+
+
+def test_create_fails_loudly_without_gpu(lib_built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import pinn_cabi
+    with pytest.raises(pinn_cabi.PinnError, match="no CUDA device|no CPU fallback"):
+        pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, [2] + [20] * 8 + [1], [-1, 0], [1, 1])
