@@ -135,6 +135,8 @@ int64_t pinn_launch_count(const pinn_t* h);
 int pinn_event_record(pinn_t* h, int idx);
 int pinn_event_elapsed_ms(pinn_t* h, int i, int j, float* ms_out);
 int pinn_flush_l2(pinn_t* h);
+/* Test hook: the kernels' branch-free fp64 tanh evaluated on the device (tests compare it with libm). */
+int pinn_test_tanh(const double* x, int n, double* y);
 /* Kernel configuration string (grid, block, dynamic smem, registers) for DESIGN/bench reporting. */
 int pinn_kernel_info(pinn_t* h, char* buf, int buflen);
 

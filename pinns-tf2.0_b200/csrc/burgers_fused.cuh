@@ -124,7 +124,7 @@ __device__ __forceinline__ void act_stash(double (&S)[4][3][2], const double (&Z
   for (int nt = 0; nt < 3; nt++)
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      S[0][nt][e] = tanh(Z[0][nt][e]);
+      S[0][nt][e] = tanh_fast(Z[0][nt][e]);
       S[1][nt][e] = Z[1][nt][e];
       S[2][nt][e] = Z[2][nt][e];
       S[3][nt][e] = Z[3][nt][e];
@@ -196,9 +196,15 @@ __device__ __forceinline__ void stash_load(double (&S)[4][3][2], const double* s
   }
 }
 
-// stage a [4 streams][8 points][20 units] register tile into shared memory as T[row = 8s+g][unit], ld = 20
+// physical row of point g inside a stream's 8-row block.  The weight-gradient GEMM contracts over rows, so any
+// permutation is allowed as long as both operands use it; swapping bits 0 and 1 puts the two rows written by one
+// quarter-warp (g = 2k, 2k+1) two rows (= 8 banks of 8 bytes) apart, which makes the 16-byte stores below
+// conflict-free while the fragment reads (rows 4ks+q, column 8t+g) stay conflict-free with ld = 20.
+__device__ __forceinline__ int prow(int g) { return (g & 4) | ((g & 1) << 1) | ((g & 2) >> 1); }
+
+// stage a [4 streams][8 points][20 units] register tile into shared memory as T[row = 8s+prow(g)][unit], ld = 20
 __device__ __forceinline__ void stage_rows(double* T, const double (&V)[4][3][2], int lane) {
-  const int g = lane >> 2, q = lane & 3;
+  const int g = prow(lane >> 2), q = lane & 3;
 #pragma unroll
   for (int s = 0; s < 4; s++) {
     double* row = T + (8 * s + g) * W;
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         const int c = 8 * nt + 2 * q + e;
         const bool ok = c < W;
         const double w0 = ok ? Wsm[c] : 0.0, w1 = ok ? Wsm[W + c] : 0.0, b = ok ? Wsm[2 * W + c] : 0.0;
-        S[0][nt][e] = tanh(fma(xh, w0, fma(th, w1, b)));
+        S[0][nt][e] = tanh_fast(fma(xh, w0, fma(th, w1, b)));
         S[1][nt][e] = sc0 * w0;
         S[2][nt][e] = sc1 * w1;
         S[3][nt][e] = 0.0;
@@ -395,7 +401,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     stage_rows(HA, H, lane);
     if (q == 0) {
 #pragma unroll
-      for (int s = 0; s < 4; s++) ZB[(8 * s + g) * W] = seed[s];
+      for (int s = 0; s < 4; s++) ZB[(8 * s + prow(g)) * W] = seed[s];
     }
     __syncwarp();
     {
@@ -472,10 +478,11 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     act_backward(H, S);
     stage_rows(ZB, H, lane);
     if (q == 0) {
-      HA[(0 + g) * W + 0] = xh;   HA[(0 + g) * W + 1] = th;
-      HA[(8 + g) * W + 0] = sc0;  HA[(8 + g) * W + 1] = 0.0;
-      HA[(16 + g) * W + 0] = 0.0; HA[(16 + g) * W + 1] = sc1;
-      HA[(24 + g) * W + 0] = 0.0; HA[(24 + g) * W + 1] = 0.0;
+      const int pg = prow(g);
+      HA[(0 + pg) * W + 0] = xh;   HA[(0 + pg) * W + 1] = th;
+      HA[(8 + pg) * W + 0] = sc0;  HA[(8 + pg) * W + 1] = 0.0;
+      HA[(16 + pg) * W + 0] = 0.0; HA[(16 + pg) * W + 1] = sc1;
+      HA[(24 + pg) * W + 0] = 0.0; HA[(24 + pg) * W + 1] = 0.0;
     }
     __syncwarp();
     {

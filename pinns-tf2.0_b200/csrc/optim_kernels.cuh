@@ -33,15 +33,22 @@ struct ReduceMap {
   int n_extra;
 };
 
+// 8 lanes per output entry: coalesced 64-byte... each lane sums every 8th CTA partial, then a 3-step shuffle
+// tree in fixed order (deterministic).  blockDim = 256 -> 32 entries per block.
 __global__ void reduce_partials(const double* __restrict__ partials, int n_cta, int stride, double* __restrict__ R,
                                 ReduceMap map, const int* __restrict__ run_flag) {
   if (run_flag && *run_flag != 0) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= map.n_out) return;
-  const int src = i < map.p_net ? i : map.extra_src[i - map.p_net];
+  const int sub = threadIdx.x & 7;
+  const int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const bool ok = i < map.n_out;
+  const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
   double s = 0.0;
-  for (int b = 0; b < n_cta; b++) s += partials[(size_t)b * stride + src];
-  R[i] = s;
+  if (ok)
+    for (int b = sub; b < n_cta; b += 8) s += partials[(size_t)b * stride + src];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && sub == 0) R[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -343,6 +350,12 @@ __global__ void mlp_forward_generic(const double* __restrict__ w, NetDesc nd, co
   const int no = nd.dims[nd.n_layers];
   for (int s = 0; s < NS; s++)
     for (int j = 0; j < no; j++) out[p * (NS * no) + s * no + j] = h[s][j];
+}
+
+
+__global__ void tanh_fast_kernel(const double* __restrict__ x, int n, double* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = tanh_fast(x[i]);
 }
 
 }  // namespace pinn

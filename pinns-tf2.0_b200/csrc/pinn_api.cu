@@ -216,7 +216,7 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
     map.extra_src[map.n_extra++] = 3023;        // (boundary part: always 0 for Burgers)
     map.extra_src[map.n_extra++] = B::IDX_LF;
     map.n_out = map.p_net + map.n_extra;
-    pinn::reduce_partials<<<(map.n_out + 127) / 128, 128, 0, h->stream>>>(h->d_partials, grid, B::PSTRIDE, h->d_R, map, run_flag);
+    pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, B::PSTRIDE, h->d_R, map, run_flag);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   } else {
@@ -714,6 +714,19 @@ int pinn_flush_l2(pinn_t* h) {
     CUDA_TRY(cudaMalloc((void**)&h->d_flush, h->flush_bytes));
   }
   CUDA_TRY(cudaMemsetAsync(h->d_flush, 0, h->flush_bytes, h->stream));
+  return 0;
+}
+
+int pinn_test_tanh(const double* x, int n, double* y) {
+  if (!x || !y || n < 1) return fail("pinn_test_tanh: bad arguments");
+  double *dx = nullptr, *dy = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&dx, (size_t)n * 8));
+  CUDA_TRY(cudaMalloc((void**)&dy, (size_t)n * 8));
+  CUDA_TRY(cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+  pinn::tanh_fast_kernel<<<(n + 255) / 256, 256>>>(dx, n, dy);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dy);
   return 0;
 }
 

@@ -44,6 +44,47 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---- branch-free fp64 tanh (<= 2.5 ulp, full relative accuracy down to denormals), built so that several
+// evaluations interleave (no divergent branches; libdevice tanh serialises into 11-cycle DFMA chains):
+//   em = expm1(-2|x|) = 2^n p(r) + (2^n - 1),  p(r) = e^r - 1 (degree-13 Taylor, |r| <= ln2/2)
+//   tanh|x| = -em / (2 + em),  division by MUFU.RCP64H seed + 2 Newton steps + one residual correction.
+__device__ __forceinline__ double tanh_fast(double x) {
+  const double ax = fmin(fabs(x), 20.0);        // tanh(20) rounds to 1.0
+  const double y = -2.0 * ax;
+  const double SHIFT = 6755399441055744.0;      // 1.5 * 2^52: round-to-nearest-integer trick
+  const double t = fma(y, 1.4426950408889634, SHIFT);
+  const int n = __double2loint(t);
+  const double nd = t - SHIFT;
+  double r = fma(nd, -6.93147180369123816490e-01, y);
+  r = fma(nd, -1.90821492927058770002e-10, r);
+  double q = 1.6059043836821613e-10;            // 1/13!
+  q = fma(q, r, 2.08767569878681e-09);          // 1/12!
+  q = fma(q, r, 2.505210838544172e-08);         // 1/11!
+  q = fma(q, r, 2.755731922398589e-07);         // 1/10!
+  q = fma(q, r, 2.7557319223985893e-06);        // 1/9!
+  q = fma(q, r, 2.48015873015873e-05);          // 1/8!
+  q = fma(q, r, 0.0001984126984126984);         // 1/7!
+  q = fma(q, r, 0.001388888888888889);          // 1/6!
+  q = fma(q, r, 0.008333333333333333);          // 1/5!
+  q = fma(q, r, 0.041666666666666664);          // 1/4!
+  q = fma(q, r, 0.16666666666666666);           // 1/3!
+  q = fma(q, r, 0.5);                           // 1/2!
+  const double p = fma(r * r, q, r);            // e^r - 1
+  const double scale = __hiloint2double((1023 + n) << 20, 0);   // 2^n, n in [-58, 0]
+  const double em = fma(scale, p, scale - 1.0);
+  const double den = 2.0 + em;                  // in [1, 2]
+  double rc;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
+  double e = fma(-den, rc, 1.0);
+  rc = fma(rc, e, rc);
+  e = fma(-den, rc, 1.0);
+  rc = fma(rc, e, rc);
+  const double num = -em;
+  double qd = num * rc;
+  qd = fma(fma(-den, qd, num), rc, qd);
+  return copysign(qd, x);
+}
+
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -51,6 +51,7 @@ SIGNATURES = {
     "pinn_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "pinn_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "pinn_flush_l2": (C.c_int, [C.c_void_p]),
+    "pinn_test_tanh": (C.c_int, [_dp, C.c_int, _dp]),
     "pinn_kernel_info": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
 }
 
@@ -247,6 +248,15 @@ class Pinn(object):
         buf = C.create_string_buffer(512)
         self._ck(self.lib.pinn_kernel_info(self.h, buf, 512))
         return json.loads(buf.value.decode())
+
+
+def device_tanh(x):
+    lib = load()
+    x = _arr(x).reshape(-1)
+    y = np.empty_like(x)
+    if lib.pinn_test_tanh(_p(x), x.size, _p(y)) != 0:
+        raise PinnError(lib.pinn_last_error().decode())
+    return y
 
 
 def nccl_unique_id():
