@@ -7,10 +7,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
 #include "burgers_fused.cuh"
+#include "burgers_fused_v2.cuh"
 #include "nls_fused.cuh"
 #include "optim_kernels.cuh"
 
@@ -72,6 +74,7 @@ struct pinn_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_sm = 0;
   long long launches = 0;
+  int burgers_kernel = 2;           // 2: warp-specialised (default); 1: single-role v1 (PINN_BURGERS_KERNEL=v1)
 
   // parameters and optimiser state
   double* d_w = nullptr;            // WPAD-padded flat weights
@@ -204,7 +207,10 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
     a.run_flag = run_flag;
     const long long rounds = (n_total + B::ROUND - 1) / B::ROUND;
     int grid = (int)(rounds < h->n_cta ? rounds : h->n_cta);
-    B::fused_loss_grad<<<grid, B::THREADS, B::SMEM_BYTES, h->stream>>>(a);
+    if (h->burgers_kernel == 2)
+      pinn::burgers2::fused_loss_grad<<<grid, pinn::burgers2::THREADS, pinn::burgers2::SMEM_BYTES, h->stream>>>(a);
+    else
+      B::fused_loss_grad<<<grid, B::THREADS, B::SMEM_BYTES, h->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     if (fused_only) return 0;
@@ -322,6 +328,9 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
     h->n_cta = h->n_sm;
     h->pstride = pinn::burgers::PSTRIDE;
     CREATE_TRY(cudaFuncSetAttribute(pinn::burgers::fused_loss_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, pinn::burgers::SMEM_BYTES));
+    CREATE_TRY(cudaFuncSetAttribute(pinn::burgers2::fused_loss_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, pinn::burgers2::SMEM_BYTES));
+    const char* kv = getenv("PINN_BURGERS_KERNEL");
+    if (kv && (!strcmp(kv, "v1") || !strcmp(kv, "1"))) h->burgers_kernel = 1;
   }
   CREATE_TRY(cudaMalloc((void**)&h->d_partials, (size_t)h->n_cta * h->pstride * 8));
   CREATE_TRY(cudaMemset(h->d_partials, 0, (size_t)h->n_cta * h->pstride * 8));
@@ -740,8 +749,13 @@ int pinn_kernel_info(pinn_t* h, char* buf, int buflen) {
     CUDA_TRY(cudaFuncGetAttributes(&fa, pinn::nls::fused_loss_grad));
     smem = pinn::nls::SMEM_BYTES; threads = pinn::nls::THREADS;
   } else {
-    CUDA_TRY(cudaFuncGetAttributes(&fa, pinn::burgers::fused_loss_grad));
-    smem = pinn::burgers::SMEM_BYTES; threads = pinn::burgers::THREADS;
+    if (h->burgers_kernel == 2) {
+      CUDA_TRY(cudaFuncGetAttributes(&fa, pinn::burgers2::fused_loss_grad));
+      smem = pinn::burgers2::SMEM_BYTES; threads = pinn::burgers2::THREADS;
+    } else {
+      CUDA_TRY(cudaFuncGetAttributes(&fa, pinn::burgers::fused_loss_grad));
+      smem = pinn::burgers::SMEM_BYTES; threads = pinn::burgers::THREADS;
+    }
   }
   snprintf(buf, buflen, "{\"grid\": %d, \"block\": %d, \"dyn_smem\": %d, \"regs\": %d, \"local_bytes\": %zu, \"sms\": %d}",
            h->n_cta, threads, smem, fa.numRegs, fa.localSizeBytes, h->n_sm);
