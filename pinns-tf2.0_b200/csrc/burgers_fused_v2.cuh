@@ -186,14 +186,14 @@ __device__ __forceinline__ void wgrad_task(double (&acc)[3][2], const Own& o, co
 }
 
 template <int L>
-__device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it, const double* sm, uint64_t* bars,
+__device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it, int half, const double* sm, uint64_t* bars,
                                             double sc0, double sc1, int lane) {
   constexpr int J = 7 - L;                  // task index within a tile (layers 7..0)
   constexpr int SLOT = J & 1;
   const uint32_t use = 4u * (uint32_t)it + (J >> 1);
   const Own o = ownership(L, wg);
 #pragma unroll 1
-  for (int c = 0; c < CHAINS; c++) {
+  for (int c = 2 * half; c < 2 * half + 2; c++) {
     uint64_t* full = bars + 1 + (c * RING + SLOT) * 2;
     uint64_t* empty = full + 1;
     mbar_wait(full, use & 1);
@@ -264,15 +264,19 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       for (int e = 0; e < 2; e++)
         a0[s][e] = a1[s][e] = a2[s][e] = a3[s][e] = a4[s][e] = a5[s][e] = a6[s][e] = a7[s][e] = 0.0;
 #pragma unroll 1
-    for (int it = 0; it < my_rounds; it++) {
-      wgrad_layer<7>(a7, wg, it, sm, bars, sc0, sc1, lane);
-      wgrad_layer<6>(a6, wg, it, sm, bars, sc0, sc1, lane);
-      wgrad_layer<5>(a5, wg, it, sm, bars, sc0, sc1, lane);
-      wgrad_layer<4>(a4, wg, it, sm, bars, sc0, sc1, lane);
-      wgrad_layer<3>(a3, wg, it, sm, bars, sc0, sc1, lane);
-      wgrad_layer<2>(a2, wg, it, sm, bars, sc0, sc1, lane);
-      wgrad_layer<1>(a1, wg, it, sm, bars, sc0, sc1, lane);
-      wgrad_layer<0>(a0, wg, it, sm, bars, sc0, sc1, lane);
+    // The chain warps are consumed in two halves (chains 0,1 then chains 2,3).  Ring back-pressure then shifts the
+    // halves by one phase: while one half runs its forward pass (which produces no weight-gradient work), the other
+    // half runs its backward pass and keeps these warps -- and the FP64 pipe of every sub-partition -- busy.
+    for (int it2 = 0; it2 < 2 * my_rounds; it2++) {
+      const int it = it2 >> 1, half = it2 & 1;
+      wgrad_layer<7>(a7, wg, it, half, sm, bars, sc0, sc1, lane);
+      wgrad_layer<6>(a6, wg, it, half, sm, bars, sc0, sc1, lane);
+      wgrad_layer<5>(a5, wg, it, half, sm, bars, sc0, sc1, lane);
+      wgrad_layer<4>(a4, wg, it, half, sm, bars, sc0, sc1, lane);
+      wgrad_layer<3>(a3, wg, it, half, sm, bars, sc0, sc1, lane);
+      wgrad_layer<2>(a2, wg, it, half, sm, bars, sc0, sc1, lane);
+      wgrad_layer<1>(a1, wg, it, half, sm, bars, sc0, sc1, lane);
+      wgrad_layer<0>(a0, wg, it, half, sm, bars, sc0, sc1, lane);
     }
     wgrad_flush<0>(a0, wg, outp, lane);
     wgrad_flush<1>(a1, wg, outp, lane);
