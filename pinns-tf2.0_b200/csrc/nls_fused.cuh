@@ -1,10 +1,460 @@
-// Fused NLS (Schrodinger) kernel -- placeholder until the [2,100x4,2] kernel lands.
+// Fused nonlinear-Schrodinger PINN loss + gradient kernel for the [2, 100 x 4, 2] tanh MLP, fp64, sm_100a.
+//
+// Replaces (reference file:line): 1dcomplex-schrodinger/inf_cont_schrodinger.py:60-76 (uvx_model), :79-105 (f_model),
+// :107-129 (loss: mse_0 + mse_b + mse_f), and the outer tape of utils/neuralnetwork.py:55-59.
+//
+// One launch, one persistent CTA per SM.  The 100x100 fp64 weight matrices (80 KB each, 246 KB in total) do not fit
+// in shared memory together, so a CTA owns a contiguous block of points and walks the network LAYER BY LAYER:
+//   F0        layer 0 (2 -> 100), direct;                              outputs -> scratch H[0]
+//   F1..F3    W_l staged once per pass with ONE TMA bulk copy; 16-point rounds of H[l-1] stream in through
+//             cp.async (double buffered); DMMA GEMM [64 rows x 100] x [100 x 100]; tanh + Taylor streams in the
+//             epilogue;                                                outputs -> scratch H[l]
+//   OUT       head (100 -> 2), residuals f_u, f_v, initial/boundary terms, loss parts, seeds; head gradient
+//   B3..B1    per round: Z-bar from (H[l], A-bar[l]) -> smem; input adjoint A-bar[l-1] = Z-bar W_l^T (DMMA);
+//             weight gradient G_l += H[l-1]^T Z-bar (DMMA, K = 64 rows per round).  The 13x13 output tiles of G_l
+//             are OWNED by warps, so their accumulators stay in registers for the whole pass over the CTA's points
+//             and are written once (bias gradient = virtual ones-row 100).
+//   B0        layer-0 gradient, direct.
+// The activations (4 streams x 100 units x 4 layers = 12.8 KB per point) live in a per-CTA global scratch that is
+// streamed, not re-read: algorithmic HBM traffic is 16 B/point, implementation traffic ~67 KB/point.
+//
+// Point list: [initial-condition points n0 | boundary pairs (lb_k, ub_k) interleaved, 2 nb | collocation nc].
+// Every point is carried with 4 streams (value, x, t, xx); only the seeds differ.
 #pragma once
 #include "pinn_common.cuh"
-namespace pinn { namespace nls {
-constexpr int THREADS = 128;
-constexpr int SMEM_BYTES = 1024;
-constexpr int PSTRIDE = 30816;
+
+namespace pinn {
+namespace nls {
+
+constexpr int W = 100;                // hidden width
+constexpr int NT = 13;                // N tiles of 8 (104)
+constexpr int KS = 25;                // k-steps of 4
+constexpr int P_NET = 30802;
+constexpr int WPAD = 30816;
+constexpr int PSTRIDE = 30816;        // [P_NET grad | mse_0, mse_b, mse_f | pad]
+constexpr int IDX_L0 = 30802, IDX_LB = 30803, IDX_LF = 30804;
+constexpr int THREADS = 256;
+constexpr int WARPS = 8;
+constexpr int RPTS = 16;              // points per round
+constexpr int RROWS = 4 * RPTS;       // 64 rows per round
+constexpr int SLAB = RROWS * W;       // doubles per staged round tile (51.2 KB)
+
+__host__ __device__ constexpr int woff(int l) { return l == 0 ? 0 : (l <= 3 ? 300 + (l - 1) * 10100 : 30600); }
+__host__ __device__ constexpr int boff(int l) { return l == 0 ? 200 : (l <= 3 ? 300 + (l - 1) * 10100 + 10000 : 30800); }
+
+// shared memory (doubles): W_l | two staging slabs | barrier
+constexpr int SM_W = 0;
+constexpr int SM_S0 = SM_W + W * W;
+constexpr int SM_S1 = SM_S0 + SLAB;
+constexpr int SM_RED = SM_S1 + SLAB;
+constexpr int SM_BAR = SM_RED + 64;
+constexpr int SM_DOUBLES = SM_BAR + 2;
+constexpr int SMEM_BYTES = SM_DOUBLES * 8;     // 182,928 B
+
 inline int grid_size(int n_sm) { return n_sm; }
-__global__ void fused_loss_grad() {}
-}}
+
+struct Args {
+  const double* w;
+  const double* x;
+  const double* t;
+  const double* uv0;        // [n0][2]
+  long long n_total, n0, n0p, nb, nc;   // n0p: n0 rounded up to even (start of the boundary-pair block)
+  double w0, wb, wf;        // aux/n0, aux/nb, 1/nc_global
+  double lb0, lb1, dx0, dx1;
+  double* scratchH;         // [grid][4 layers][4 streams][pts][W]
+  double* scratchA;         // [grid][2 buffers][4 streams][pts][W]
+  double* scratchS;         // [grid][pts][8]  seeds (u,v | u_x,v_x | u_t,v_t | u_xx,v_xx)
+  int pts;                  // points per CTA (multiple of 16)
+  double* partials;         // [grid][PSTRIDE]
+  const int* run_flag;
+};
+
+__device__ __forceinline__ int prow(int g) { return (g & 4) | ((g & 1) << 1) | ((g & 2) >> 1); }
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// stage one round (16 points x 4 streams x 100 units) of a scratch layer [4][pts][W] into a slab [64 rows][W],
+// row = 16*s + p.  51 200 B = 3200 x 16 B -> 12.5 cp.async per thread.
+__device__ __forceinline__ void stage_round(double* slab, const double* src, int pts, int p0) {
+  for (int i = threadIdx.x; i < RROWS * (W / 2); i += THREADS) {
+    const int row = i / (W / 2), c2 = i - row * (W / 2);
+    const int s = row >> 4, p = row & 15;
+    cp_async16(slab + row * W + 2 * c2, src + ((size_t)s * pts + p0 + p) * W + 2 * c2);
+  }
+}
+
+// warp -> (point group, N tiles) for the row-parallel GEMMs (forward, input adjoint): 2 groups x 13 tiles over 8 warps;
+// the 4-tile warp sits on a different sub-partition in each group (loads 7,7,6,6).
+__device__ __forceinline__ void gemm_role(int warp, int& pg, int& nt0, int& ntn) {
+  pg = warp >> 2;
+  const int k = warp & 3;
+  if (pg == 0) { nt0 = k == 0 ? 0 : 3 * k + 1; ntn = k == 0 ? 4 : 3; }
+  else { nt0 = k == 0 ? 0 : (k == 1 ? 3 : 3 * k + 1); ntn = k == 1 ? 4 : 3; }
+}
+
+// C[s][j][:] (+)= A(rows of group pg, streams s) * B,   B[k][n] = Wsm[k*ldk + n*ldn];  n >= 100 reads as zero
+__device__ __forceinline__ void gemm_rows(double (&C)[4][4][2], const double* slab, const double* Wsm, int ldk, int ldn,
+                                          int pg, int nt0, int ntn, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  const int prow_g = prow(g);
+#pragma unroll 1
+  for (int ks = 0; ks < KS; ks++) {
+    double a[4], b[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) a[s] = slab[(16 * s + 8 * pg + prow_g) * W + 4 * ks + q];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int n = 8 * (nt0 + j) + g;
+      b[j] = (j < ntn && n < W) ? Wsm[(4 * ks + q) * ldk + n * ldn] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (j < ntn) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) dmma(C[s][j], a[s], b[j]);
+      }
+  }
+}
+
+__device__ __forceinline__ void load_weights_tma(double* Wsm, const double* src, uint64_t* bar, uint32_t& phase) {
+  __syncthreads();                       // everybody is done with the previous contents of Wsm
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, W * W * 8);
+    tma_bulk_g2s(Wsm, src, W * W * 8, bar);
+  }
+  mbar_wait(bar, phase);
+  phase ^= 1;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
+  extern __shared__ __align__(16) double sm[];
+  if (p.run_flag && *p.run_flag != 0) return;
+  double* Wsm = sm + SM_W;
+  double* S0 = sm + SM_S0;
+  double* S1 = sm + SM_S1;
+  double* red = sm + SM_RED;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SM_BAR);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  uint32_t wphase = 0;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+
+  const int pts = p.pts;
+  const long long base = (long long)blockIdx.x * pts;              // first point of this CTA
+  long long navail = p.n_total - base;
+  const int npts = navail <= 0 ? 0 : (navail < pts ? (int)navail : pts);   // valid points
+  const int nrounds = (npts + RPTS - 1) / RPTS;
+  double* H = p.scratchH + (size_t)blockIdx.x * 16 * pts * W;      // H[l][s][pt][W]
+  double* A = p.scratchA + (size_t)blockIdx.x * 8 * pts * W;       // A[buf][s][pt][W]
+  double* SEED = p.scratchS + (size_t)blockIdx.x * pts * 8;
+  double* outp = p.partials + (size_t)blockIdx.x * PSTRIDE;
+  const double sc0 = 2.0 / p.dx0, sc1 = 2.0 / p.dx1;
+  const size_t LSZ = (size_t)4 * pts * W;                          // one layer of H
+  const size_t SSZ = (size_t)pts * W;                              // one stream
+
+  // =============================== F0: layer 0 (2 -> 100), direct ===============================
+  for (int i = tid; i < nrounds * RPTS * W; i += THREADS) {
+    const int pt = i / W, u = i - pt * W;
+    const long long gp = base + (pt < npts ? pt : npts - 1);       // padded points replicate the last valid one
+    const double xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;   // utils/neuralnetwork.py:29-30
+    const double th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
+    const double w0 = __ldg(p.w + u), w1 = __ldg(p.w + W + u), b = __ldg(p.w + 2 * W + u);
+    const double a = tanh_fast(fma(xh, w0, fma(th, w1, b)));
+    const double s = fma(-a, a, 1.0), zx = sc0 * w0, zt = sc1 * w1;
+    H[0 * SSZ + (size_t)pt * W + u] = a;
+    H[1 * SSZ + (size_t)pt * W + u] = s * zx;
+    H[2 * SSZ + (size_t)pt * W + u] = s * zt;
+    H[3 * SSZ + (size_t)pt * W + u] = -2.0 * a * s * zx * zx;
+  }
+  __syncthreads();
+
+  int pg, nt0, ntn;
+  gemm_role(warp, pg, nt0, ntn);
+  const int myp = 8 * pg + prow(g);                                 // this lane's point within a round
+
+  // =============================== F1..F3: hidden layers ===============================
+  for (int l = 1; l <= 3; l++) {
+    load_weights_tma(Wsm, p.w + woff(l), bar, wphase);
+    const double* Hin = H + (size_t)(l - 1) * LSZ;
+    double* Hout = H + (size_t)l * LSZ;
+    const double* bias = p.w + boff(l);
+    if (nrounds > 0) { stage_round(S0, Hin, pts, 0); cp_async_commit(); }
+    for (int r = 0; r < nrounds; r++) {
+      double* cur = (r & 1) ? S1 : S0;
+      if (r + 1 < nrounds) { stage_round((r & 1) ? S0 : S1, Hin, pts, (r + 1) * RPTS); cp_async_commit(); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncthreads();
+      double C[4][4][2];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int u = 8 * (nt0 + j) + 2 * q + e;
+          C[0][j][e] = (j < ntn && u < W) ? __ldg(bias + u) : 0.0;
+          C[1][j][e] = C[2][j][e] = C[3][j][e] = 0.0;
+        }
+      gemm_rows(C, cur, Wsm, W, 1, pg, nt0, ntn, lane);
+      const int pt = r * RPTS + myp;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int u = 8 * (nt0 + j) + 2 * q;
+        if (j < ntn && u < W) {
+          double o[4][2];
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const double a = tanh_fast(C[0][j][e]);
+            const double s = fma(-a, a, 1.0), zx = C[1][j][e];
+            o[0][e] = a;
+            o[1][e] = s * zx;
+            o[2][e] = s * C[2][j][e];
+            o[3][e] = s * fma(-2.0 * a * zx, zx, C[3][j][e]);
+          }
+#pragma unroll
+          for (int s = 0; s < 4; s++)
+            *reinterpret_cast<double2*>(Hout + s * SSZ + (size_t)pt * W + u) = make_double2(o[s][0], o[s][1]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // =============================== OUT: head (100 -> 2), residuals, seeds ===============================
+  {
+    const double* H3 = H + (size_t)3 * LSZ;
+    const double* W4 = p.w + woff(4);
+    // head outputs out[pt][2s+o] -> OUTV (the adjoint scratch is still unused at this point)
+    double* OUTV = A;
+    for (int i = tid; i < nrounds * RPTS * 8; i += THREADS) {
+      const int pt = i >> 3, so = i & 7, s = so >> 1, o = so & 1;
+      const double* h = H3 + s * SSZ + (size_t)pt * W;
+      double acc = (s == 0) ? __ldg(p.w + boff(4) + o) : 0.0;
+      for (int k = 0; k < W; k++) acc = fma(h[k], __ldg(W4 + 2 * k + o), acc);
+      OUTV[i] = acc;
+    }
+    __syncthreads();
+    double l0 = 0.0, lbd = 0.0, lf = 0.0;
+    // one thread per point; a boundary point reads its partner's outputs (pairs are adjacent and never straddle a
+    // CTA: the pair block starts at the even index n0p and CTA ranges start at multiples of 16)
+    for (int pt = tid; pt < nrounds * RPTS; pt += THREADS) {
+      const long long gp = base + pt;
+      double sd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const double* o = OUTV + pt * 8;
+      if (pt >= npts) {
+        // padding point of the last round: inert
+      } else if (gp < p.n0) {                                          // initial condition (:118-119)
+        const double ru = o[0] - __ldg(p.uv0 + 2 * gp), rv = o[1] - __ldg(p.uv0 + 2 * gp + 1);
+        l0 += p.w0 * (ru * ru + rv * rv);
+        sd[0] = 2.0 * p.w0 * ru; sd[1] = 2.0 * p.w0 * rv;
+      } else if (gp < p.n0p) {
+        // alignment padding between the initial-condition block and the boundary pairs: inert
+      } else if (gp < p.n0p + 2 * p.nb) {                              // periodic boundary (:120-123)
+        const bool is_lb = ((gp - p.n0p) & 1) == 0;
+        const double* op = is_lb ? o + 8 : o - 8;                      // partner outputs
+        const double sgn = is_lb ? 1.0 : -1.0;
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {                                  // u, v, u_x, v_x: lb minus ub
+          const double d = sgn * (o[c] - op[c]);
+          acc = fma(d, d, acc);
+          sd[c] = sgn * 2.0 * p.wb * d;
+        }
+        if (is_lb) lbd += p.wb * acc;
+      } else {                                                         // collocation (:79-105)
+        const double u = o[0], v = o[1], ut = o[4], vt = o[5], uxx = o[6], vxx = o[7];
+        const double h2 = u * u + v * v;
+        const double fu = ut + 0.5 * vxx + h2 * v;                     // :101
+        const double fv = vt - 0.5 * uxx - h2 * u;                     // :102
+        lf += p.wf * (fu * fu + fv * fv);
+        const double cu = 2.0 * p.wf * fu, cv = 2.0 * p.wf * fv;
+        sd[0] = cu * 2.0 * u * v - cv * (3.0 * u * u + v * v);
+        sd[1] = cu * (u * u + 3.0 * v * v) - cv * 2.0 * u * v;
+        sd[4] = cu; sd[5] = cv;
+        sd[6] = -0.5 * cv; sd[7] = 0.5 * cu;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) SEED[pt * 8 + c] = sd[c];
+    }
+    __syncthreads();
+    // loss parts
+    l0 = warp_sum(l0); lbd = warp_sum(lbd); lf = warp_sum(lf);
+    if (lane == 0) { red[warp * 3 + 0] = l0; red[warp * 3 + 1] = lbd; red[warp * 3 + 2] = lf; }
+    __syncthreads();
+    if (tid < 3) {
+      double s = 0.0;
+      for (int w8 = 0; w8 < WARPS; w8++) s += red[w8 * 3 + tid];
+      outp[IDX_L0 + tid] = s;
+    }
+    // head gradient: G4[k][o] = sum_pt sum_s H3[s][pt][k] seed[pt][s][o];  bias: sum_pt seed[pt][0][o]
+    if (tid < 2 * W) {
+      const int k = tid >> 1, o = tid & 1;
+      double acc = 0.0;
+      for (int pt = 0; pt < nrounds * RPTS; pt++)
+#pragma unroll
+        for (int s = 0; s < 4; s++) acc = fma(H3[s * SSZ + (size_t)pt * W + k], SEED[pt * 8 + 2 * s + o], acc);
+      outp[woff(4) + 2 * k + o] = acc;
+    } else if (tid < 2 * W + 2) {
+      const int o = tid - 2 * W;
+      double acc = 0.0;
+      for (int pt = 0; pt < nrounds * RPTS; pt++) acc += SEED[pt * 8 + o];
+      outp[boff(4) + o] = acc;
+    }
+    __syncthreads();
+  }
+
+  // =============================== B3..B1: hidden layers, reverse ===============================
+  // weight-gradient tile ownership: tiles t = 13*mt + nt in [t0, t0 + tn)
+  const int t0 = 21 * warp + (warp > 0 ? 1 : 0), tn = warp == 0 ? 22 : 21;
+  for (int l = 3; l >= 1; l--) {
+    load_weights_tma(Wsm, p.w + woff(l), bar, wphase);
+    const double* Hl = H + (size_t)l * LSZ;              // outputs of layer l (for the activation adjoint)
+    const double* Hin = H + (size_t)(l - 1) * LSZ;       // inputs of layer l (A operand of the weight gradient)
+    const double* Ain = A + (size_t)((l & 1) ? 0 : 1) * 4 * SSZ;    // adjoint of layer-l outputs (l < 3)
+    double* Aout = A + (size_t)((l & 1) ? 1 : 0) * 4 * SSZ;         // adjoint of layer-(l-1) outputs
+    const double* W4 = p.w + woff(4);
+    double G[22][2];
+#pragma unroll
+    for (int i = 0; i < 22; i++) G[i][0] = G[i][1] = 0.0;
+
+    for (int r = 0; r < nrounds; r++) {
+      // (1) stage the layer inputs of this round (A operand of the weight gradient)
+      stage_round(S0, Hin, pts, r * RPTS);
+      cp_async_commit();
+      // (2) activation adjoint Z-bar for this lane's point and units -> S1 (row layout)
+      const int pt = r * RPTS + myp;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int u = 8 * (nt0 + j) + 2 * q;
+        if (j < ntn && u < W) {
+          double hv[4][2], av[4][2];
+#pragma unroll
+          for (int s = 0; s < 4; s++) {
+            const double2 h2 = *reinterpret_cast<const double2*>(Hl + s * SSZ + (size_t)pt * W + u);
+            hv[s][0] = h2.x; hv[s][1] = h2.y;
+            if (l == 3) {
+              // adjoint of the last hidden layer's outputs straight from the seeds: A[s][u] = sum_o seed[s][o] W4[u][o]
+              const double s0 = SEED[pt * 8 + 2 * s], s1 = SEED[pt * 8 + 2 * s + 1];
+              av[s][0] = fma(s0, __ldg(W4 + 2 * u), s1 * __ldg(W4 + 2 * u + 1));
+              av[s][1] = fma(s0, __ldg(W4 + 2 * u + 2), s1 * __ldg(W4 + 2 * u + 3));
+            } else {
+              const double2 a2 = *reinterpret_cast<const double2*>(Ain + s * SSZ + (size_t)pt * W + u);
+              av[s][0] = a2.x; av[s][1] = a2.y;
+            }
+          }
+          double z[4][2];
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const double a = hv[0][e], ax = hv[1][e], at = hv[2][e], axx = hv[3][e];
+            const double A0 = av[0][e], Ax = av[1][e], At = av[2][e], Axx = av[3][e];
+            const double s = fma(-a, a, 1.0);
+            const double u1 = fma(ax, Ax, at * At);
+            const double u2 = fma(a, axx, ax * ax);
+            double zz = fma(-2.0 * a, u1, s * A0);
+            zz = fma(-2.0 * Axx, u2, zz);
+            z[0][e] = zz;
+            z[1][e] = fma(-4.0 * a * ax, Axx, s * Ax);
+            z[2][e] = s * At;
+            z[3][e] = s * Axx;
+          }
+#pragma unroll
+          for (int s = 0; s < 4; s++)
+            *reinterpret_cast<double2*>(S1 + (16 * s + myp) * W + u) = make_double2(z[s][0], z[s][1]);
+        }
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+      // (3) input adjoint: A-bar[l-1] = Z-bar * W_l^T   (K = units of layer l)
+      {
+        double C[4][4][2];
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) C[s][j][0] = C[s][j][1] = 0.0;
+        gemm_rows(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int u = 8 * (nt0 + j) + 2 * q;
+          if (j < ntn && u < W) {
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+              *reinterpret_cast<double2*>(Aout + s * SSZ + (size_t)pt * W + u) = make_double2(C[s][j][0], C[s][j][1]);
+          }
+        }
+      }
+      // (4) weight gradient: G[i][j] += sum_rows S0[row][i] * S1[row][j]   (unit i == 100: ones on the value stream)
+#pragma unroll 1
+      for (int ks = 0; ks < RROWS / 4; ks++) {
+        const int row = 4 * ks + q;
+        const bool vrow = ks < 4;                      // rows 0..15 are the value stream
+#pragma unroll
+        for (int i = 0; i < 22; i++) {
+          if (i < tn) {
+            const int t = t0 + i;
+            const int mt = t / NT, nt = t - mt * NT;
+            const int iu = 8 * mt + g, ju = 8 * nt + g;
+            const double a = iu < W ? S0[row * W + iu] : ((iu == W && vrow) ? 1.0 : 0.0);
+            const double b = ju < W ? S1[row * W + ju] : 0.0;
+            dmma(G[i], a, b);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // (5) flush this warp's tiles of G_l
+#pragma unroll
+    for (int i = 0; i < 22; i++) {
+      if (i < tn) {
+        const int t = t0 + i;
+        const int mt = t / NT, nt = t - mt * NT;
+        const int iu = 8 * mt + g;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int ju = 8 * nt + 2 * q + e;
+          if (ju < W) {
+            if (iu < W) outp[woff(l) + iu * W + ju] = G[i][e];
+            else if (iu == W) outp[boff(l) + ju] = G[i][e];
+          }
+        }
+      }
+    }
+  }
+
+  // =============================== B0: layer-0 gradient, direct ===============================
+  __syncthreads();
+  if (tid < W) {
+    const int u = tid;
+    const double* A0 = A + (size_t)1 * 4 * SSZ;          // written by l = 1 (buffer (1&1)?1:0 = 1)
+    const double zx = sc0 * __ldg(p.w + u), zt = sc1 * __ldg(p.w + W + u);
+    double gx = 0.0, gt = 0.0, gb = 0.0;
+    for (int pt = 0; pt < nrounds * RPTS; pt++) {
+      const long long gp = base + (pt < npts ? pt : npts - 1);
+      const double xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;
+      const double th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
+      const size_t o = (size_t)pt * W + u;
+      const double a = H[o], ax = H[SSZ + o], at = H[2 * SSZ + o], axx = H[3 * SSZ + o];
+      const double B0 = A0[o], Bx = A0[SSZ + o], Bt = A0[2 * SSZ + o], Bxx = A0[3 * SSZ + o];
+      const double s = fma(-a, a, 1.0);
+      const double u1 = fma(ax, Bx, at * Bt);
+      const double u2 = fma(a, axx, ax * ax);
+      double z = fma(-2.0 * a, u1, s * B0);
+      z = fma(-2.0 * Bxx, u2, z);
+      const double zbx = fma(-4.0 * a * ax, Bxx, s * Bx);
+      const double zbt = s * Bt;
+      gx = fma(xh, z, fma(sc0, zbx, gx));
+      gt = fma(th, z, fma(sc1, zbt, gt));
+      gb += z;
+    }
+    (void)zx; (void)zt;
+    outp[woff(0) + u] = gx;
+    outp[woff(0) + W + u] = gt;
+    outp[boff(0) + u] = gb;
+  }
+}
+
+}  // namespace nls
+}  // namespace pinn

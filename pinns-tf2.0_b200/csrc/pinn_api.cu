@@ -96,6 +96,10 @@ struct pinn_handle {
   int d_out_dim = 1;
   double data_weight = 1.0;
   std::vector<double> h_tb;                 // NLS boundary times
+  std::vector<double> h_icx, h_ict;         // NLS initial-condition points (host copy for re-assembly)
+  long long n_aux = 0;                      // points stored in the data region (Burgers: n_d; NLS: n0p + 2 n_b)
+  double *d_scrH = nullptr, *d_scrA = nullptr, *d_scrS = nullptr;   // NLS activation / adjoint / seed scratch
+  int scr_pts = 0;
   std::vector<double> stage_x, stage_t;     // host staging for set_data (de-interleave)
 
   // measurement
@@ -130,7 +134,7 @@ bool is_nls_net(const std::vector<int>& L) {
 }
 
 int nls_upload_points(pinn_t* h);
-int nls_launch_eval(pinn_t* h, const int* run_flag);
+int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only);
 
 pinn::NetDesc net_desc(const pinn_t* h) {
   pinn::NetDesc nd{};
@@ -168,9 +172,9 @@ int ensure_points(pinn_t* h, long long need_d, long long need_c) {
   CUDA_TRY(cudaMalloc((void**)&nx, (size_t)(nd + nc) * 8));
   CUDA_TRY(cudaMalloc((void**)&nt, (size_t)(nd + nc) * 8));
   if (h->d_x) {
-    if (h->n_d) {
-      CUDA_TRY(cudaMemcpyAsync(nx + nd - h->n_d, h->d_x + h->dcap - h->n_d, h->n_d * 8, cudaMemcpyDeviceToDevice, h->stream));
-      CUDA_TRY(cudaMemcpyAsync(nt + nd - h->n_d, h->d_t + h->dcap - h->n_d, h->n_d * 8, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->n_aux) {
+      CUDA_TRY(cudaMemcpyAsync(nx + nd - h->n_aux, h->d_x + h->dcap - h->n_aux, h->n_aux * 8, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(cudaMemcpyAsync(nt + nd - h->n_aux, h->d_t + h->dcap - h->n_aux, h->n_aux * 8, cudaMemcpyDeviceToDevice, h->stream));
     }
     if (h->n_c) {
       CUDA_TRY(cudaMemcpyAsync(nx + nd, h->d_x + h->dcap, h->n_c * 8, cudaMemcpyDeviceToDevice, h->stream));
@@ -226,7 +230,8 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   } else {
-    if (nls_launch_eval(h, run_flag)) return -1;
+    if (nls_launch_eval(h, run_flag, fused_only)) return -1;
+    if (fused_only) return 0;
   }
   if (h->world > 1) {
     // one allreduce over [gradient | loss parts].  A skipped evaluation (L-BFGS stopped) still
@@ -237,8 +242,75 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
   return 0;
 }
 
-int nls_upload_points(pinn_t*) { return fail("NLS fused kernel: not built yet"); }
-int nls_launch_eval(pinn_t*, const int*) { return fail("NLS fused kernel: not built yet"); }
+// NLS: (re)assemble the auxiliary block [initial-condition points | pad to even | (lb_k, ub_k) pairs] right-aligned in
+// the data region (inf_cont_schrodinger.py:50-53 builds X_lb=(lb0,tb), X_ub=(ub0,tb)).
+int nls_upload_points(pinn_t* h) {
+  const long long n0 = h->n_d, n0p = (n0 + 1) & ~1LL, nb = h->n_b;
+  const long long n_aux = n0p + 2 * nb;
+  // the right-aligned start moves with n_aux: grow first with the OLD count so nothing is lost, then rewrite
+  if (ensure_points(h, n_aux > h->n_aux ? n_aux : h->n_aux, h->n_c)) return -1;
+  h->stage_x.assign(n_aux, 0.0); h->stage_t.assign(n_aux, 0.0);
+  for (long long i = 0; i < n0; i++) { h->stage_x[i] = h->h_icx[i]; h->stage_t[i] = h->h_ict[i]; }
+  if (n0p > n0) { h->stage_x[n0] = h->lb[0]; h->stage_t[n0] = h->lb[1]; }     // inert alignment point
+  for (long long k = 0; k < nb; k++) {
+    h->stage_x[n0p + 2 * k] = h->lb[0];     h->stage_t[n0p + 2 * k] = h->h_tb[k];
+    h->stage_x[n0p + 2 * k + 1] = h->ub[0]; h->stage_t[n0p + 2 * k + 1] = h->h_tb[k];
+  }
+  if (n_aux) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_x + h->dcap - n_aux, h->stage_x.data(), n_aux * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_t + h->dcap - n_aux, h->stage_t.data(), n_aux * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  h->n_aux = n_aux;
+  return 0;
+}
+
+int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
+  namespace N = pinn::nls;
+  const long long n0 = h->n_d, n0p = (n0 + 1) & ~1LL, nb = h->n_b;
+  const long long n_total = h->n_aux + h->n_c;
+  if (n_total <= 0) return fail("no points set (pinn_set_collocation / pinn_set_data / pinn_set_boundary)");
+  if (h->n_aux != n0p + 2 * nb) return fail("internal: NLS auxiliary block out of date");
+  const int grid = h->n_cta;
+  long long per = (n_total + grid - 1) / grid;
+  const int pts = (int)((per + N::RPTS - 1) / N::RPTS * N::RPTS);
+  if (pts > h->scr_pts) {
+    if (h->d_scrH) cudaFree(h->d_scrH);
+    if (h->d_scrA) cudaFree(h->d_scrA);
+    if (h->d_scrS) cudaFree(h->d_scrS);
+    h->d_scrH = h->d_scrA = h->d_scrS = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&h->d_scrH, (size_t)grid * 16 * pts * N::W * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_scrA, (size_t)grid * 8 * pts * N::W * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_scrS, (size_t)grid * pts * 8 * 8));
+    h->scr_pts = pts;
+  }
+  N::Args a{};
+  a.w = h->d_w;
+  a.x = h->d_x + (h->dcap - h->n_aux); a.t = h->d_t + (h->dcap - h->n_aux); a.uv0 = h->d_u;
+  a.n_total = n_total; a.n0 = n0; a.n0p = n0p; a.nb = nb; a.nc = h->n_c;
+  a.w0 = n0 > 0 ? h->data_weight / (double)n0 : 0.0;
+  a.wb = nb > 0 ? h->data_weight / (double)nb : 0.0;
+  a.wf = h->n_c_global > 0 ? 1.0 / (double)h->n_c_global : 0.0;
+  a.lb0 = h->lb[0]; a.lb1 = h->lb[1]; a.dx0 = h->ub[0] - h->lb[0]; a.dx1 = h->ub[1] - h->lb[1];
+  a.scratchH = h->d_scrH; a.scratchA = h->d_scrA; a.scratchS = h->d_scrS;
+  a.pts = h->scr_pts;
+  // the kernel derives its point range from a.pts, so keep the distribution even when the scratch is larger
+  a.pts = pts;
+  a.partials = h->d_partials; a.run_flag = run_flag;
+  N::fused_loss_grad<<<grid, N::THREADS, N::SMEM_BYTES, h->stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  if (fused_only) return 0;
+  pinn::ReduceMap map{};
+  map.p_net = N::P_NET;
+  map.n_extra = 3;
+  map.extra_src[0] = N::IDX_L0; map.extra_src[1] = N::IDX_LB; map.extra_src[2] = N::IDX_LF;
+  map.n_out = map.p_net + map.n_extra;
+  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, N::PSTRIDE, h->d_R, map, run_flag);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
 
 }  // namespace
 
@@ -306,6 +378,7 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
   CREATE_TRY(cudaEventCreate(&h->ev1));
   h->w_cap = ((h->P + 3 + 63) / 64) * 64 + 64;
   if (h->w_cap < pinn::burgers::WPAD) h->w_cap = pinn::burgers::WPAD;
+  if (h->w_cap < pinn::nls::WPAD + 64) h->w_cap = pinn::nls::WPAD + 64;
   CREATE_TRY(cudaMalloc((void**)&h->d_w, h->w_cap * 8));
   CREATE_TRY(cudaMemset(h->d_w, 0, h->w_cap * 8));
   CREATE_TRY(cudaMalloc((void**)&h->d_R, h->w_cap * 8));
@@ -352,7 +425,7 @@ int pinn_destroy(pinn_t* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  double* bufs[] = {h->d_w, h->d_R, h->d_partials, h->d_m, h->d_v, h->d_loss_ring, h->d_x, h->d_t, h->d_u, h->d_gold,
+  double* bufs[] = {h->d_w, h->d_R, h->d_partials, h->d_m, h->d_v, h->d_loss_ring, h->d_x, h->d_t, h->d_u, h->d_scrH, h->d_scrA, h->d_scrS, h->d_gold,
                     h->d_d, h->d_S, h->d_Y, h->d_xfinal, h->d_fhist, h->d_px, h->d_pout};
   for (double* b : bufs) if (b) cudaFree(b);
   if (h->d_step) cudaFree(h->d_step);
@@ -386,7 +459,7 @@ int pinn_set_collocation(pinn_t* h, const double* x, const double* t, int64_t n,
   if (n < 0 || (n > 0 && (!x || !t))) return fail("pinn_set_collocation: bad arguments");
   if (n_global < n) return fail("pinn_set_collocation: n_global < n");
   CUDA_TRY(cudaSetDevice(h->device));
-  if (ensure_points(h, h->n_d, n)) return -1;
+  if (ensure_points(h, h->n_aux, n)) return -1;
   if (n) {
     // straight from the caller's buffer into the collocation region (truly asynchronous when it is pinned)
     CUDA_TRY(cudaMemcpyAsync(h->d_x + h->dcap, x, n * 8, cudaMemcpyHostToDevice, h->stream));
@@ -403,6 +476,20 @@ int pinn_set_data(pinn_t* h, const double* X, int64_t n, int in_dim, const doubl
   if (in_dim != 1 && in_dim != 2) return fail("pinn_set_data: in_dim must be 1 (broadcast quirk) or 2");
   if (out_dim != h->layers.back()) return fail("pinn_set_data: out_dim does not match the network head");
   CUDA_TRY(cudaSetDevice(h->device));
+  if (h->pde == PINN_NLS_INF) {
+    h->h_icx.resize(n); h->h_ict.resize(n);
+    for (int64_t i = 0; i < n; i++) {
+      h->h_icx[i] = X[i * in_dim];
+      h->h_ict[i] = in_dim == 1 ? X[i] : X[i * in_dim + 1];   // quirk Q1: (N,1) input broadcast, t := x
+    }
+    if (n) {
+      if (ensure(&h->d_u, &h->u_cap, n * out_dim)) return -1;
+      CUDA_TRY(cudaMemcpyAsync(h->d_u, u, n * out_dim * 8, cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->n_d = n; h->d_out_dim = out_dim; h->data_weight = weight;
+    return nls_upload_points(h);
+  }
   // shrinking/growing the data set moves its right-aligned start; the collocation region is untouched
   if (ensure_points(h, n, h->n_c)) return -1;
   h->stage_x.resize(n); h->stage_t.resize(n);
@@ -417,7 +504,7 @@ int pinn_set_data(pinn_t* h, const double* X, int64_t n, int in_dim, const doubl
     CUDA_TRY(cudaMemcpyAsync(h->d_u, u, n * out_dim * 8, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
-  h->n_d = n; h->d_out_dim = out_dim; h->data_weight = weight;
+  h->n_d = n; h->n_aux = n; h->d_out_dim = out_dim; h->data_weight = weight;
   return 0;
 }
 
@@ -427,7 +514,8 @@ int pinn_set_boundary(pinn_t* h, const double* tb, int64_t n_b) {
   if (n_b < 0 || (n_b > 0 && !tb)) return fail("pinn_set_boundary: bad arguments");
   h->h_tb.assign(tb, tb + n_b);
   h->n_b = n_b;
-  return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  return nls_upload_points(h);
 }
 
 int pinn_set_weights(pinn_t* h, const double* w, int64_t n) {
