@@ -196,7 +196,11 @@ class NeuralNetwork(object):
         return np.float64(loss), grads
 
     def wrap_training_variables(self):
-        return self.model.trainable_variables
+        var = self.model.trainable_variables
+        if self._pde_id() == pinn_cabi.BURGERS_IDE:       # ide_cont_burgers.py:93-96
+            w = self._native().get_weights()
+            var = var + [_t(w[-2:-1]), _t(w[-1:])]
+        return var
 
     def get_params(self, numpy=False):
         return []
@@ -294,11 +298,7 @@ def _native_get_params(self, numpy=False):
 
 
 def _native_wrap_training_variables(self):
-    var = self.model.trainable_variables
-    if self._pde_id() == pinn_cabi.BURGERS_IDE:
-        w = self._native().get_weights()
-        var = var + [_t(w[-2:-1]), _t(w[-1:])]
-    return var
+    return NeuralNetwork.wrap_training_variables(self)
 
 
 def _native_get_weights(self, convert_to_tensor=True):

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
+_HERE = os.path.dirname(os.path.realpath(__file__))
 LIB_PATH = os.path.join(_HERE, "..", "lib", "libpinn_b200.so")
 
 BURGERS_INF, BURGERS_IDE, NLS_INF = 0, 1, 2

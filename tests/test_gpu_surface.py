@@ -1,0 +1,153 @@
+"""GPU: the reference's Python surface end to end: reference-style subclasses -> fit() = Adam epochs then
+L-BFGS through custom_lbfgs.lbfgs -> final MODEL weights equal the oracle's trajectory (incl. the discarded last L-BFGS
+update, utils/neuralnetwork.py:131-136), Logger output, predict()/get_params() shapes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import PKG, load_golden
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(PKG, "shims"))      # `import tensorflow as tf` of the reference scripts
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def hp_burgers(tf_epochs, nt_epochs, lr):
+    return {"N_u": 100, "N_f": 1000, "layers": [2] + [20] * 8 + [1], "tf_epochs": tf_epochs, "tf_lr": lr, "tf_b1": 0.9,
+            "tf_eps": None, "nt_epochs": nt_epochs, "nt_lr": 0.8, "nt_ncorr": 50, "log_frequency": 2}
+
+
+def test_burgers_inference_fit_matches_oracle_trajectory(capsys):
+    from logger import Logger
+    from neuralnetwork import NeuralNetwork
+    from oracle import reference_port as rp
+    import tensorflow as tf
+    g = load_golden("burgers_inf")
+
+    class BurgersInformedNN(NeuralNetwork):              # 1d-burgers/inf_cont_burgers.py:48-98 (tape bodies elided)
+        def __init__(self, hp, logger, X_f, ub, lb, nu):
+            super().__init__(hp, logger, ub, lb)
+            self.nu = nu
+            self.x_f = self.tensor(X_f[:, 0:1])
+            self.t_f = self.tensor(X_f[:, 1:2])
+
+        def loss(self, u, u_pred):
+            f_pred = self.f_model()
+            return tf.reduce_mean(tf.square(u - u_pred)) + tf.reduce_mean(tf.square(f_pred))     # never executed
+
+        def f_model(self):
+            with tf.GradientTape(persistent=True) as tape:                                          # never executed
+                pass
+
+        def get_params(self, numpy=False):
+            return self.nu
+
+        def predict(self, X_star):
+            u_star = self.model(X_star)
+            f_star = self.f_model()
+            return u_star.numpy(), f_star.numpy()
+
+    hp = hp_burgers(3, 4, 0.03)
+    logger = Logger(hp)
+    pinn = BurgersInformedNN(hp, logger, g["X_f"], g["ub"], g["lb"], nu=float(g["nu"]))
+    pinn._w0 = g["w"].copy()                              # identical initial weights on both sides
+    logger.set_error_fn(lambda: float(np.linalg.norm(g["u_star"] - pinn.predict(g["X_star"])[0]) / np.linalg.norm(g["u_star"])))
+    pinn.fit(g["X_u"], g["u"])
+    # oracle: 3 Adam steps, then lbfgs with maxIter=4 -> the model holds the last EVALUATED point
+    pb = rp.BurgersInference(hp["layers"], g["lb"], g["ub"], float(g["nu"]), g["X_f"], g["X_u"], g["u"])
+    w_adam, _, _ = rp.adam_train(pb, g["w"], 3, lr=0.03)
+    tr = rp.lbfgs_fixed_step(lambda x: rp.loss_and_flat_grad(pb, x), w_adam, max_iter=4, learning_rate=0.8, n_correction=50,
+                             tol_fun=np.finfo(float).eps)
+    assert rel(pinn.get_weights().numpy(), tr.x_eval[-1]) < 1e-7
+    assert not np.allclose(pinn.get_weights().numpy(), tr.x_final)
+    out = capsys.readouterr().out
+    assert "-- Starting Adam optimization --" in out and "-- Starting LBFGS optimization --" in out
+    assert "tf_epoch =      0" in out and "nt_epoch =      2" in out and "Training finished (epoch 7)" in out
+    u_pred, f_pred = pinn.predict(g["X_star"])
+    assert u_pred.shape == (g["X_star"].shape[0], 1) and f_pred.shape == (g["X_f"].shape[0], 1)
+    assert pinn.get_params(numpy=True) == float(g["nu"])
+    lv, grads = pinn.grad(g["X_u"], g["u"])
+    assert len(grads) == 18 and grads[0].shape == (2, 20) and grads[-1].shape == (1,)
+    f2, g2 = rp.loss_and_flat_grad(pb, tr.x_eval[-1])
+    assert abs(float(lv) - f2) <= 1e-7 * abs(f2)
+    assert "Dense 20->1 linear" in pinn.summary()
+
+
+def test_identification_surface(capsys):
+    from logger import Logger
+    from neuralnetwork import NeuralNetwork
+    from oracle import reference_port as rp
+    import tensorflow as tf
+    g = load_golden("burgers_ide")
+
+    class BurgersInformedNN(NeuralNetwork):              # 1d-burgers/ide_cont_burgers.py:47-118 (re-indented semantics)
+        def __init__(self, hp, logger, ub, lb):
+            super().__init__(hp, logger, ub, lb)
+            self.lambda_1 = tf.Variable([0.0], dtype=self.dtype)
+            self.lambda_2 = tf.Variable([-6.0], dtype=self.dtype)
+
+        def get_params(self, numpy=False):
+            l1 = self.lambda_1
+            l2 = tf.exp(self.lambda_2)
+            if numpy:
+                return l1.numpy()[0], l2.numpy()[0]
+            return l1, l2
+
+        def fit(self, X_u, u):
+            self.X_u = tf.convert_to_tensor(X_u, dtype=self.dtype)
+            super().fit(X_u, u)
+
+    hp = hp_burgers(3, 3, 0.001)
+    pinn = BurgersInformedNN(hp, Logger(hp), g["ub"], g["lb"])
+    pinn._w0 = g["w"][:-2].copy()
+    pinn.logger.set_error_fn(lambda: 0.0)
+    pinn.fit(g["X_u"], g["u"])
+    pb = rp.BurgersIdentification(hp["layers"], g["lb"], g["ub"], g["X_u"], g["u"])
+    w_adam, _, _ = rp.adam_train(pb, g["w"], 3, lr=0.001)
+    tr = rp.lbfgs_fixed_step(lambda x: rp.loss_and_flat_grad(pb, x), w_adam, max_iter=3, learning_rate=0.8, n_correction=50,
+                             tol_fun=np.finfo(float).eps)
+    w = pinn.get_weights().numpy()
+    assert w.shape == (3023,) and rel(w, tr.x_eval[-1]) < 1e-7
+    l1, l2 = pinn.get_params(numpy=True)
+    assert abs(l1 - tr.x_eval[-1][-2]) < 1e-9 and abs(l2 - np.exp(tr.x_eval[-1][-1])) < 1e-12
+    assert len(pinn.wrap_training_variables()) == 20
+
+
+def test_schrodinger_surface(capsys):
+    from logger import Logger
+    from neuralnetwork import NeuralNetwork
+    from oracle import reference_port as rp
+    import tensorflow as tf
+    g = load_golden("nls_inf")
+
+    class SchrodingerInformedNN(NeuralNetwork):          # 1dcomplex-schrodinger/inf_cont_schrodinger.py:46-135
+        def __init__(self, hp, logger, X_f, tb, ub, lb):
+            super().__init__(hp, logger, ub, lb)
+            X_lb = np.concatenate((0 * tb + lb[0], tb), 1)
+            X_ub = np.concatenate((0 * tb + ub[0], tb), 1)
+            self.X_lb = self.tensor(X_lb)
+            self.X_ub = self.tensor(X_ub)
+            self.x_f = self.tensor(X_f[:, 0:1])
+            self.t_f = self.tensor(X_f[:, 1:2])
+
+        def predict(self, X_star):
+            h_pred = self.model(X_star)
+            return h_pred[:, 0:1].numpy(), h_pred[:, 1:2].numpy()
+
+    hp = {"N_0": 50, "N_b": 50, "N_f": 400, "layers": [2, 100, 100, 100, 100, 2], "tf_epochs": 3, "tf_lr": 0.05, "tf_b1": 0.99,
+          "tf_eps": 1e-1, "nt_epochs": 0, "nt_lr": 1.2, "nt_ncorr": 50, "log_frequency": 1}
+    pinn = SchrodingerInformedNN(hp, Logger(hp), g["X_f"], g["tb"], g["ub"], g["lb"])
+    pinn._w0 = g["w"].copy()
+    pinn.logger.set_error_fn(lambda: 0.0)
+    pinn.fit(g["x0"], tf.concat([g["uv0"][:, 0:1], g["uv0"][:, 1:2]], axis=1))     # (N_0,1) input: quirk Q1 (:164)
+    assert rel(pinn.get_weights().numpy(), g["adam_w"]) < 1e-8
+    u_pred, v_pred = pinn.predict(g["X_star"])
+    assert u_pred.shape == (100, 1) and v_pred.shape == (100, 1)
+    out = capsys.readouterr().out
+    assert "tf_epoch =      2" in out and "Starting LBFGS" in out      # nt_epochs = 0: lbfgs returns immediately (:43-44)

@@ -1,0 +1,98 @@
+"""CPU: the host-side mirror of the reference's Python surface up to the GPU boundary:
+module/symbol names, Struct semantics, hp parsing, flat sizes, PDE recognition, data preparation, and -- when the
+reference checkout is present (build container only) -- the UNMODIFIED inf_cont_burgers.py loading on our modules
+through run_reference_script.py until it needs the GPU."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import PKG, ROOT
+
+REF = "/root/reference"
+HP = {"N_u": 100, "N_f": 1000, "layers": [2] + [20] * 8 + [1], "tf_epochs": 3, "tf_lr": 0.03, "tf_b1": 0.9, "tf_eps": None,
+      "nt_epochs": 4, "nt_lr": 0.8, "nt_ncorr": 50, "log_frequency": 10}
+
+
+def test_module_surface_matches_reference_names():
+    import custom_lbfgs, logger, neuralnetwork
+    for name in ("lbfgs", "dot", "Struct", "reset_time", "record_time", "last_time", "final_loss", "times"):
+        assert hasattr(custom_lbfgs, name)
+    for name in ("get_epoch_duration", "get_elapsed", "get_error_u", "set_error_fn", "log_train_start", "log_train_epoch",
+                 "log_train_opt", "log_train_end"):
+        assert hasattr(logger.Logger, name)
+    for name in ("loss", "grad", "wrap_training_variables", "get_params", "get_weights", "set_weights", "get_loss_and_flat_grad",
+                 "tf_optimization", "tf_optimization_step", "nt_optimization", "nt_optimization_steps", "fit", "predict", "summary",
+                 "tensor"):
+        assert hasattr(neuralnetwork.NeuralNetwork, name)
+
+
+def test_struct_and_lbfgs_contract():
+    from custom_lbfgs import Struct, lbfgs
+    s = Struct()
+    s.maxIter = 0
+    assert s.anything == 0 and s.maxIter == 0
+    assert lbfgs(lambda x: (0.0, x), np.zeros(3), s, Struct(), True, None) is None      # custom_lbfgs.py:43-44
+    s.maxIter = 5
+    with pytest.raises(TypeError, match="no host fallback"):
+        lbfgs(lambda x: (0.0, x), np.zeros(3), s, Struct(), True, None)
+
+
+def test_network_construction_and_pde_recognition(capsys):
+    from logger import Logger
+    from neuralnetwork import NeuralNetwork
+    import pinn_cabi
+
+    class BurgersInformedNN(NeuralNetwork):      # constructor of 1d-burgers/inf_cont_burgers.py:48-56
+        def __init__(self, hp, logger, X_f, ub, lb, nu):
+            super().__init__(hp, logger, ub, lb)
+            self.nu = nu
+            self.x_f = self.tensor(X_f[:, 0:1]); self.t_f = self.tensor(X_f[:, 1:2])
+
+        def loss(self, u, u_pred):               # would be TensorFlow tape code in the reference
+            raise AssertionError("tape body must have been replaced by the fused-kernel loss")
+
+    net = BurgersInformedNN(HP, Logger(HP), np.zeros((10, 2)), np.array([1.0, 1.0]), np.array([-1.0, 0.0]), 0.01 / np.pi)
+    assert net.sizes_w == [40] + [400] * 7 + [20] and net.sizes_b == [20] * 8 + [1]      # neuralnetwork.py:40-45
+    assert net.nt_config.maxIter == 4 and net.nt_config.tolFun == np.finfo(float).eps and net.nt_config.lineSearch == 0
+    assert net.tf_eps == 1e-7 and net.dtype == "float64"
+    assert net._pde_id() == pinn_cabi.BURGERS_INF
+    assert BurgersInformedNN.loss is not BurgersInformedNN._script_loss
+    assert net._w0.shape == (3021,) and np.all(net._w0[40:60] == 0)                       # glorot weights, zero biases
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(pinn_cabi.PinnError, match="no CUDA device"):
+            net.fit(np.zeros((5, 2)), np.zeros((5, 1)))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_prep_data_shapes_against_reference_files():
+    sys.path.insert(0, os.path.join(PKG, "1d-burgers"))
+    import burgersutil
+    np.random.seed(1234)
+    out = burgersutil.prep_data(os.path.join(REF, "1d-burgers", "data", "burgers_shock.mat"), 100, 1000, noise=0.0)
+    x, t, X, T, Exact_u, X_star, u_star, X_u, u, X_f, ub, lb = out
+    assert X_star.shape == (25600, 2) and X_u.shape == (100, 2) and u.shape == (100, 1) and X_f.shape == (1000, 2)
+    assert np.allclose(lb, [-1, 0]) and np.allclose(ub, [1, 0.99])
+    # Latin hypercube: exactly one sample per stratum in each dimension
+    for j in range(2):
+        strata = np.floor((X_f[:, j] - lb[j]) / (ub[j] - lb[j]) * 1000).astype(int)
+        assert sorted(np.clip(strata, 0, 999)) == list(range(1000))
+    # every training point is an initial/boundary point (burgersutil.py:104-118)
+    assert np.all((X_u[:, 1] == 0) | (np.abs(X_u[:, 0]) == 1))
+    ide = burgersutil.prep_data(os.path.join(REF, "1d-burgers", "data", "burgers_shock.mat"), 2000, noise=0.01)
+    assert ide[7].shape == (2000, 2) and len(ide) == 11
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_unmodified_reference_script_runs_up_to_the_gpu_boundary():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    r = subprocess.run([sys.executable, os.path.join(PKG, "run_reference_script.py"),
+                        os.path.join(REF, "1d-burgers", "inf_cont_burgers.py")], capture_output=True, text=True, timeout=300)
+    out = r.stdout + r.stderr
+    assert "Hyperparameters" in out and "Training started" in out      # data prep, Logger, class creation all worked
+    assert "no CUDA device" in out and r.returncode != 0                # and it stops exactly at the GPU boundary
