@@ -34,7 +34,8 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("PINN_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

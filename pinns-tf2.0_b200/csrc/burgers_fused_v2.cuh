@@ -45,7 +45,16 @@ using burgers::Args;
 constexpr int CHAINS = 4;
 constexpr int THREADS = 256;              // 4 chain warps + 4 wgrad warps
 constexpr int ROUND = CHAINS * TILE;      // 32 points per CTA round
-constexpr int RING = 2;                   // Z-bar ring slots per chain warp
+#ifndef PINN_RING
+#define PINN_RING 2
+#endif
+#ifndef PINN_PHASE_OFFSET
+#define PINN_PHASE_OFFSET 0
+#endif
+#ifndef PINN_WG_ROLLED
+#define PINN_WG_ROLLED 0
+#endif
+constexpr int RING = PINN_RING;           // Z-bar ring slots per chain warp
 
 // shared memory carve-up (doubles)
 constexpr int STASH0 = 160;               // layer 0: a only, [8 rows][20]
@@ -57,12 +66,18 @@ constexpr int SM_RING = SM_STASH + CHAINS * STASH_PER_WARP;
 constexpr int SM_XT = SM_RING + CHAINS * RING * 640;
 constexpr int SM_RED = SM_XT + CHAINS * 2 * 16;
 constexpr int SM_BAR = SM_RED + 256;      // 1 + 2*CHAINS*RING mbarriers
-constexpr int SM_DOUBLES = SM_BAR + 1 + 2 * CHAINS * RING + 1;
+constexpr int SM_DOUBLES = SM_BAR + 1 + 2 * CHAINS * RING + 2;   // + phase-offset barrier
 constexpr int SMEM_BYTES = SM_DOUBLES * 8;   // ~195 KB
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Ring bookkeeping: chain warp c numbers its weight-gradient tasks T = 8*tile + J (J = 7 - layer).  Task T lives in ring
+// slot T % RING; it is the (T / RING)-th use of that slot, i.e. phase T / RING of the slot's full and empty barriers.
+__device__ __forceinline__ uint64_t* bar_full(uint64_t* bars, int c, int slot) { return bars + 1 + (c * RING + slot) * 2; }
+__device__ __forceinline__ uint64_t* bar_empty(uint64_t* bars, int c, int slot) { return bars + 2 + (c * RING + slot) * 2; }
+__device__ __forceinline__ void wait_produced(uint64_t* bars, int c, int T) { mbar_wait(bar_full(bars, c, T % RING), (T / RING) & 1); }
+__device__ __forceinline__ void wait_consumed(uint64_t* bars, int c, int T) { mbar_wait(bar_empty(bars, c, T % RING), (T / RING) & 1); }
 
 // C-layout read of a [rows][20] staged tile: stream block s, this lane's point row and columns
 __device__ __forceinline__ void load_rows(double (&V)[4][3][2], const double* T, int lane) {
@@ -154,6 +169,31 @@ __device__ __forceinline__ void wgrad_task(double (&acc)[3][2], const Own& o, co
       w0t[s] = i < W ? sc1 * Wsm[W + i] : 0.0;
     }
   }
+  if (L >= 2 && PINN_WG_ROLLED) {
+    // regular hidden layers: rolled k loop (keeps the kernel within the instruction cache); slots 0,1 always exist
+    const int i0 = 8 * o.mt[0] + g, i1 = 8 * o.mt[1] + g, i2 = 8 * o.mt[2] + g;
+    const int j0 = 8 * o.nt[0] + g, j1 = 8 * o.nt[1] + g, j2 = 8 * o.nt[2] + g;
+    const bool three = o.n == 3;
+#pragma unroll 2
+    for (int ks = 0; ks < 8; ks++) {
+      const int R = 4 * ks + q;
+      const double one = ks < 2 ? 1.0 : 0.0;       // ones-row (bias) on the value stream: rows 0..7
+      const double* ar = Aop + R * W;
+      const double* br = ZB + R * W;
+      const double a0 = i0 < W ? ar[i0] : (i0 == W ? one : 0.0);
+      const double a1 = i1 < W ? ar[i1] : (i1 == W ? one : 0.0);
+      const double b0 = j0 < W ? br[j0] : 0.0;
+      const double b1 = j1 < W ? br[j1] : 0.0;
+      dmma(acc[0], a0, b0);
+      dmma(acc[1], a1, b1);
+      if (three) {
+        const double a2 = i2 < W ? ar[i2] : (i2 == W ? one : 0.0);
+        const double b2 = j2 < W ? br[j2] : 0.0;
+        dmma(acc[2], a2, b2);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int ks = 0; ks < 8; ks++) {
     const int st = ks >> 1;                 // stream of this k-step's rows
@@ -189,20 +229,18 @@ template <int L>
 __device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it, int half, const double* sm, uint64_t* bars,
                                             double sc0, double sc1, int lane) {
   constexpr int J = 7 - L;                  // task index within a tile (layers 7..0)
-  constexpr int SLOT = J & 1;
-  const uint32_t use = 4u * (uint32_t)it + (J >> 1);
+  const int T = 8 * it + J;
+  const int slot = T % RING;
   const Own o = ownership(L, wg);
 #pragma unroll 1
   for (int c = 2 * half; c < 2 * half + 2; c++) {
-    uint64_t* full = bars + 1 + (c * RING + SLOT) * 2;
-    uint64_t* empty = full + 1;
-    mbar_wait(full, use & 1);
+    wait_produced(bars, c, T);
     const double* stash = sm + SM_STASH + c * STASH_PER_WARP;
     const double* Aop = L >= 2 ? stash + STASH0 + (L - 2) * STASHL : (L == 1 ? stash : sm + SM_XT + (c * 2 + (it & 1)) * 16);
-    const double* ZB = sm + SM_RING + (c * RING + SLOT) * 640;
+    const double* ZB = sm + SM_RING + (c * RING + slot) * 640;
     if (o.n > 0) wgrad_task<L>(acc, o, Aop, ZB, sm + SM_W, sc0, sc1, lane);
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty);
+    if (lane == 0) mbar_arrive(bar_empty(bars, c, slot));
   }
 }
 
@@ -241,6 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       mbar_init(bars + 1 + 2 * i, 1);        // full: the producing chain warp's lane 0
       mbar_init(bars + 2 + 2 * i, 4);        // empty: lane 0 of each of the 4 wgrad warps
     }
+    mbar_init(bars + 1 + 2 * CHAINS * RING, 2);   // phase offset: the two chain warps of half A
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -297,6 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
 #pragma unroll
     for (int nt = 0; nt < 3; nt++) g8[nt][0] = g8[nt][1] = 0.0;
     const int pg = prow(g);
+    if (PINN_PHASE_OFFSET && c >= 2) mbar_wait(bars + 1 + 2 * CHAINS * RING, 0);   // start half a tile behind half A
 
 #pragma unroll 1
     for (int it = 0; it < my_rounds; it++) {
@@ -329,9 +369,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           H[3][nt][e] = 0.0;
         }
       act_forward(H);
-      // the a-only stash of layer 0 is the A operand of the previous tile's layer-1 task (ring slot 0, the slot the
-      // first task of this tile will reuse): wait for its release here instead of at the first backward stage
-      mbar_wait(bars + 2 + (c * RING + 0) * 2, ((4u * (uint32_t)it) & 1) ^ 1);
+      // the a-only stash of layer 0 (and, with RING = 3, the layer-1 stash) is still the A operand of the previous
+      // tile's last tasks: wait until the layer-1 task (J = 6) has been consumed; consumers retire tasks in order
+      if (it > 0) wait_consumed(bars, c, 8 * (it - 1) + 6);
       {
         double* r0 = stash + pg * W;
         *reinterpret_cast<double2*>(r0 + 2 * q) = make_double2(H[0][0][0], H[0][0][1]);
@@ -359,6 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           for (int nt = 0; nt < 3; nt++) { H[s][nt][0] = Z[s][nt][0]; H[s][nt][1] = Z[s][nt][1]; }
         if (l < NHID - 1) burgers::stage_rows(stash + STASH0 + (l - 1) * STASHL, H, lane);
       }
+      if (PINN_PHASE_OFFSET && it == 0 && c < 2) { __syncwarp(); if (lane == 0) mbar_arrive(bars + 1 + 2 * CHAINS * RING); }
       // ---------------- output layer (20 -> 1), residual, seeds
       double seed[4];
       double A[4][3][2];
@@ -417,14 +458,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       // ---------------- backward: layers 7..1 (task J = 7-l, ring slot J&1)
 #pragma unroll 1
       for (int l = NHID - 1; l >= 1; l--) {
-        const int J = 7 - l, slot = J & 1;
+        const int T = 8 * it + (7 - l), slot = T % RING;
         if (l < NHID - 1) load_rows(H, stash + STASH0 + (l - 1) * STASHL, lane);   // outputs of layer l (l=7: registers)
         act_backward_out(A, H);                                                      // A := Z-bar
-        uint64_t* full = bars + 1 + (c * RING + slot) * 2;
-        if (J > 0) mbar_wait(full + 1, ((4u * (uint32_t)it + (J >> 1)) & 1) ^ 1);    // J == 0 waited at tile start
+        if (T >= RING) wait_consumed(bars, c, T - RING);                             // the slot's previous task is done
         burgers::stage_rows(sm + SM_RING + (c * RING + slot) * 640, A, lane);
         __syncwarp();
-        if (lane == 0) mbar_arrive(full);
+        if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
         // adjoint of the layer inputs: A_new = Z-bar * W_l^T
         {
           const double* Wl = Wsm + woff(l);
@@ -462,11 +502,11 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
             H[3][nt][e] = -2.0 * a * s * zx * zx;
           }
         act_backward_out(A, H);
-        uint64_t* full = bars + 1 + (c * RING + 1) * 2;
-        mbar_wait(full + 1, ((4u * (uint32_t)it + 3u) & 1) ^ 1);
-        burgers::stage_rows(sm + SM_RING + (c * RING + 1) * 640, A, lane);
+        const int T = 8 * it + 7, slot = T % RING;
+        if (T >= RING) wait_consumed(bars, c, T - RING);
+        burgers::stage_rows(sm + SM_RING + (c * RING + slot) * 640, A, lane);
         __syncwarp();
-        if (lane == 0) mbar_arrive(full);
+        if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
       }
     }
 
