@@ -226,18 +226,17 @@ def main():
             p.event_record(2 * i + 1)
         p.sync()
         barrier()
+        launches = p.launch_count() - l0          # kernels of this library launched inside the timed region
         wall = time.perf_counter() - t_wall0
         # keep the sampler alive for at least ~1.5 s of load so that it sees clocks under load
         t_end = time.perf_counter() + max(0.0, 1.5 - wall)
         while time.perf_counter() < t_end:
             p.adam_step(ADAM_LR, sync=False)
             p.sync()
-    launches = None
     ms_steps = [p.event_elapsed_ms(2 * i, 2 * i + 1) for i in range(args.steps)]
     ms_step = float(np.mean(ms_steps))
-    # launches inside the timed region: (fused + reduce + adam_update + adam_advance) per step
-    launches_per_step = 4
-    launches = launches_per_step * args.steps
+    # launches inside the timed region: world == 1: fused + reduce_adam; world > 1: fused + reduce (+ NCCL) + adam
+    launches_per_step = launches / args.steps
     if dist is not None:
         tt = torch.tensor([ms_step], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -55,24 +55,72 @@ __global__ void reduce_partials(const double* __restrict__ partials, int n_cta, 
 // Adam (ResourceApplyAdam of TF 2.0):  alpha_t = lr sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1);
 // v += (g^2-v)(1-b2); w -= alpha_t m / (sqrt(v)+eps).   step[0] = t (completed steps).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_entry(double* w, double* m, double* v, double g, int i, int t, double lr, double b1,
+                                           double b2, double eps) {
+  const double alpha = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
+  const double mi = m[i] + (g - m[i]) * (1.0 - b1);
+  const double vi = v[i] + (g * g - v[i]) * (1.0 - b2);
+  m[i] = mi;
+  v[i] = vi;
+  w[i] -= (mi * alpha) / (sqrt(vi) + eps);
+}
+
+// step[0] = t (completed steps), step[1] = blocks finished in the current launch.  The LAST block to finish advances t,
+// so no block can observe the incremented counter (replaces a separate one-thread kernel).
+__device__ __forceinline__ void adam_finish(int* step, int nblocks) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(step + 1, 1);
+    if (done == nblocks - 1) { step[1] = 0; step[0] += 1; __threadfence(); }
+  }
+}
+
 __global__ void adam_update(double* __restrict__ w, double* __restrict__ m, double* __restrict__ v,
                             const double* __restrict__ R, int P, int* __restrict__ step, double lr, double b1, double b2,
                             double eps, double* __restrict__ loss_ring, int ring) {
   const int t = step[0] + 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P) {
-    const double alpha = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
-    const double g = R[i];
-    const double mi = m[i] + (g - m[i]) * (1.0 - b1);
-    const double vi = v[i] + (g * g - v[i]) * (1.0 - b2);
-    m[i] = mi;
-    v[i] = vi;
-    w[i] -= (mi * alpha) / (sqrt(vi) + eps);
-  }
+  if (i < P) adam_entry(w, m, v, R[i], i, t, lr, b1, b2, eps);
   if (i == 0) loss_ring[(t - 1) % ring] = R[P] + R[P + 1] + R[P + 2];
+  adam_finish(step, gridDim.x);
 }
-// separate, so that no block of adam_update can observe the incremented counter
-__global__ void adam_advance(int* step) { step[0] += 1; }
+
+// Single-GPU step: fixed-order reduction of the per-CTA partials fused with the Adam update (no collective between).
+__global__ void reduce_adam(const double* __restrict__ partials, int n_cta, int stride, double* __restrict__ R, ReduceMap map,
+                            double* __restrict__ w, double* __restrict__ m, double* __restrict__ v, int P,
+                            int* __restrict__ step, double lr, double b1, double b2, double eps,
+                            double* __restrict__ loss_ring, int ring) {
+  const int t = step[0] + 1;
+  const int sub = threadIdx.x & 7;
+  const int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const bool ok = i < map.n_out;
+  const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
+  double s = 0.0;
+  if (ok)
+    for (int b = sub; b < n_cta; b += 8) s += partials[(size_t)b * stride + src];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && sub == 0) {
+    R[i] = s;
+    if (i < P) adam_entry(w, m, v, s, i, t, lr, b1, b2, eps);
+  }
+  // the loss needs the three part sums, which live in (possibly) different blocks: the last block writes it
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(step + 1, 1);
+    if (done == (int)gridDim.x - 1) {
+      __threadfence();
+      const volatile double* Rv = R;
+      loss_ring[(t - 1) % ring] = Rv[P] + Rv[P + 1] + Rv[P + 2];
+      step[1] = 0;
+      step[0] += 1;
+      __threadfence();
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // L-BFGS iteration kernel: ONE CTA; each thread keeps EPT entries of the working vector in registers.

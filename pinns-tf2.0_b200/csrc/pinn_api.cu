@@ -74,6 +74,8 @@ struct pinn_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_sm = 0;
   long long launches = 0;
+  pinn::ReduceMap last_map{};       // reduction map / grid / stride of the most recent fused launch
+  int last_grid = 0, last_stride = 0;
   int burgers_kernel = 2;           // 2: warp-specialised (default); 1: single-role v1 (PINN_BURGERS_KERNEL=v1)
 
   // parameters and optimiser state
@@ -188,6 +190,7 @@ int ensure_points(pinn_t* h, long long need_d, long long need_c) {
 }
 
 int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
+  const bool skip_reduce = fused_only;
   if (h->pde == PINN_BURGERS_INF || h->pde == PINN_BURGERS_IDE) {
     namespace B = pinn::burgers;
     const bool ide = h->pde == PINN_BURGERS_IDE;
@@ -217,7 +220,6 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
       B::fused_loss_grad<<<grid, B::THREADS, B::SMEM_BYTES, h->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
-    if (fused_only) return 0;
     pinn::ReduceMap map{};
     map.p_net = B::P_NET;
     map.n_extra = 0;
@@ -226,6 +228,8 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
     map.extra_src[map.n_extra++] = 3023;        // (boundary part: always 0 for Burgers)
     map.extra_src[map.n_extra++] = B::IDX_LF;
     map.n_out = map.p_net + map.n_extra;
+    h->last_map = map; h->last_grid = grid; h->last_stride = B::PSTRIDE;
+    if (skip_reduce) return 0;
     pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, B::PSTRIDE, h->d_R, map, run_flag);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -300,12 +304,13 @@ int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
   N::fused_loss_grad<<<grid, N::THREADS, N::SMEM_BYTES, h->stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
-  if (fused_only) return 0;
   pinn::ReduceMap map{};
   map.p_net = N::P_NET;
   map.n_extra = 3;
   map.extra_src[0] = N::IDX_L0; map.extra_src[1] = N::IDX_LB; map.extra_src[2] = N::IDX_LF;
   map.n_out = map.p_net + map.n_extra;
+  h->last_map = map; h->last_grid = grid; h->last_stride = N::PSTRIDE;
+  if (fused_only) return 0;
   pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, N::PSTRIDE, h->d_R, map, run_flag);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
@@ -554,13 +559,22 @@ int pinn_loss_grad(pinn_t* h, const double* w_or_null, double* loss_out, double*
 int pinn_adam_step(pinn_t* h, double lr, double b1, double b2, double eps, double* loss_out_or_null) {
   if (!h) return fail("null handle");
   CUDA_TRY(cudaSetDevice(h->device));
-  if (launch_eval(h, nullptr)) return -1;
-  pinn::adam_update<<<(h->P + 127) / 128, 128, 0, h->stream>>>(h->d_w, h->d_m, h->d_v, h->d_R, h->P, h->d_step, lr, b1, b2,
-                                                                 eps, h->d_loss_ring, LOSS_RING);
-  CUDA_TRY(cudaGetLastError());
-  pinn::adam_advance<<<1, 1, 0, h->stream>>>(h->d_step);
-  CUDA_TRY(cudaGetLastError());
-  h->launches += 2;
+  if (h->world == 1) {
+    // fused kernel, then ONE kernel that reduces the per-CTA partials and applies Adam
+    if (launch_eval(h, nullptr, true)) return -1;
+    const pinn::ReduceMap& map = h->last_map;
+    pinn::reduce_adam<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, h->d_R, map,
+                                                                    h->d_w, h->d_m, h->d_v, h->P, h->d_step, lr, b1, b2, eps,
+                                                                    h->d_loss_ring, LOSS_RING);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+  } else {
+    if (launch_eval(h, nullptr)) return -1;      // fused + reduce + allreduce
+    pinn::adam_update<<<(h->P + 127) / 128, 128, 0, h->stream>>>(h->d_w, h->d_m, h->d_v, h->d_R, h->P, h->d_step, lr, b1, b2,
+                                                                   eps, h->d_loss_ring, LOSS_RING);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+  }
   h->adam_steps++;
   if (loss_out_or_null) {
     CUDA_TRY(cudaMemcpyAsync(loss_out_or_null, h->d_loss_ring + ((h->adam_steps - 1) % LOSS_RING), 8, cudaMemcpyDeviceToHost, h->stream));
