@@ -123,6 +123,12 @@ def time_reference_port(n_f, steps, warmup, seed=1234):
     """The restated reference on the host cores: loss + flat gradient (nested reverse mode) + Adam update."""
     import torch
     from oracle import reference_port as rp
+    # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1, which would cripple this arm)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except Exception:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncpu))
     X_f, X_u, u = synthetic_problem(seed, n_f)
     pb = rp.BurgersInference(LAYERS, LB, UB, NU, X_f, X_u, u)
     w = init_weights()
@@ -186,21 +192,29 @@ def main():
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # Control plane (uid exchange, barriers, max over ranks) on gloo: the ONLY NCCL communicator in this process is
+        # the library's data-path one (gradient allreduce).  Two NCCL communicators with kernels in flight at the same
+        # time can deadlock (observed at 4 ranks when torch's NCCL barrier overlapped the library's allreduce).
+        dist.init_process_group("gloo")
         box = [pinn_cabi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         uid = box[0]
 
+    handle = []
+
     def barrier():
+        for hh in handle:
+            hh.sync()                      # drain the library's stream (incl. its NCCL kernels) first
+        torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
 
     n_f = args.n_f
     n_f_global = n_f * world
     X_f, X_u, u = synthetic_problem(1234 + rank, n_f)
     _, X_u, u = synthetic_problem(1234, 1)     # data term identical on all ranks
     p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, LAYERS, LB, UB, device=local_rank, rank=rank, world=world, nccl_uid=uid)
+    handle.append(p)
     p.set_pde_params([NU])
     p.set_data(X_u, u, weight=1.0 if rank == 0 else 0.0)
     # pinned host copies of this rank's collocation batch (e2e leg uploads them every step)
@@ -238,7 +252,7 @@ def main():
     # launches inside the timed region: world == 1: fused + reduce_adam; world > 1: fused + reduce (+ NCCL) + adam
     launches_per_step = launches / args.steps
     if dist is not None:
-        tt = torch.tensor([ms_step], device="cuda")
+        tt = torch.tensor([ms_step], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_step = float(tt.item())
     value = n_f_global / (ms_step * 1e-3)
@@ -273,7 +287,7 @@ def main():
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
     if dist is not None:
-        tt = torch.tensor([e2e_s], device="cuda")
+        tt = torch.tensor([e2e_s], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e = {"value": n_f_global / e2e_s, "unit": "points/s", "h2d_bytes_per_step": 16 * n_f, "d2h_bytes_per_step": 8,

@@ -22,7 +22,7 @@ def rel(a, b):
 def main():
     rank, local_rank, world = sharding.env_rank_world()
     torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist.init_process_group("gloo")      # control plane only; the data-path NCCL communicator lives inside the library
     uid = sharding.exchange_nccl_uid(dist, rank, pinn_cabi.nccl_unique_id)
     layers = [2] + [20] * 8 + [1]
     rng = np.random.default_rng(5)
@@ -52,7 +52,7 @@ def main():
     rN = p.lbfgs(8, learning_rate=0.8, n_correction=50, tol_fun=np.finfo(float).eps, sync_every=3, want_x_final=True)
     assert rN["n_iter"] == r1["n_iter"] and rel(rN["x_final"], r1["x_final"]) < 1e-8
     # every rank holds identical weights (replicated optimiser state, no broadcast)
-    wt = torch.from_numpy(p.get_weights()).cuda()
+    wt = torch.from_numpy(p.get_weights())
     ws = [torch.empty_like(wt) for _ in range(world)]
     dist.all_gather(ws, wt)
     assert all(torch.equal(ws[0], x) for x in ws)
