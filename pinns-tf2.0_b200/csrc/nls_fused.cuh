@@ -293,11 +293,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     // head gradient: G4[k][o] = sum_pt sum_s H3[s][pt][k] seed[pt][s][o];  bias: sum_pt seed[pt][0][o]
     if (tid < 2 * W) {
       const int k = tid >> 1, o = tid & 1;
-      double acc = 0.0;
+      double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
       for (int pt = 0; pt < nrounds * RPTS; pt++)
 #pragma unroll
-        for (int s = 0; s < 4; s++) acc = fma(H3[s * SSZ + (size_t)pt * W + k], SEED[pt * 8 + 2 * s + o], acc);
-      outp[woff(4) + 2 * k + o] = acc;
+        for (int s = 0; s < 4; s++) acc4[s] = fma(H3[s * SSZ + (size_t)pt * W + k], SEED[pt * 8 + 2 * s + o], acc4[s]);
+      outp[woff(4) + 2 * k + o] = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
     } else if (tid < 2 * W + 2) {
       const int o = tid - 2 * W;
       double acc = 0.0;
@@ -308,8 +309,14 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   }
 
   // =============================== B3..B1: hidden layers, reverse ===============================
-  // weight-gradient tile ownership: tiles t = 13*mt + nt in [t0, t0 + tn)
-  const int t0 = 21 * warp + (warp > 0 ? 1 : 0), tn = warp == 0 ? 22 : 21;
+  // weight-gradient tile ownership (13 x 13 tiles of G_l): warps 0-3 own the 3 x 7 block (M tiles 3b..3b+2, N tiles 0..6),
+  // warps 4-7 the 3 x 6 block (N tiles 7..12) plus a strip of the last M tile (rows 96..103: units 96-99 and the
+  // ones-row 100 = bias): N tiles {0-2}, {3-5}, {6-8}, {9-12}  ->  21, 21, 21, 21, 21, 21, 21, 22 tiles.
+  const int wb = warp & 3;                       // M band
+  const bool wide = warp < 4;                    // 7 N tiles (else 6 + strip)
+  const int n_first = wide ? 0 : 7;
+  const int sn0 = 3 * wb;                        // strip: first N tile
+  const int snn = wide ? 0 : (wb == 3 ? 4 : 3);  // strip: number of N tiles
   for (int l = 3; l >= 1; l--) {
     load_weights_tma(Wsm, p.w + woff(l), bar, wphase);
     const double* Hl = H + (size_t)l * LSZ;              // outputs of layer l (for the activation adjoint)
@@ -317,9 +324,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     const double* Ain = A + (size_t)((l & 1) ? 0 : 1) * 4 * SSZ;    // adjoint of layer-l outputs (l < 3)
     double* Aout = A + (size_t)((l & 1) ? 1 : 0) * 4 * SSZ;         // adjoint of layer-(l-1) outputs
     const double* W4 = p.w + woff(4);
-    double G[22][2];
+    double G[3][7][2], GS[4][2];
 #pragma unroll
-    for (int i = 0; i < 22; i++) G[i][0] = G[i][1] = 0.0;
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+      for (int n = 0; n < 7; n++) G[m][n][0] = G[m][n][1] = 0.0;
+#pragma unroll
+    for (int n = 0; n < 4; n++) GS[n][0] = GS[n][1] = 0.0;
 
     for (int r = 0; r < nrounds; r++) {
       // (1) stage the layer inputs of this round (A operand of the weight gradient)
@@ -387,19 +398,33 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         }
       }
       // (4) weight gradient: G[i][j] += sum_rows S0[row][i] * S1[row][j]   (unit i == 100: ones on the value stream)
-#pragma unroll 1
+#pragma unroll 2
       for (int ks = 0; ks < RROWS / 4; ks++) {
-        const int row = 4 * ks + q;
-        const bool vrow = ks < 4;                      // rows 0..15 are the value stream
+        const double* ar = S0 + (4 * ks + q) * W;
+        const double* br = S1 + (4 * ks + q) * W;
+        double av[3], bv[7];
 #pragma unroll
-        for (int i = 0; i < 22; i++) {
-          if (i < tn) {
-            const int t = t0 + i;
-            const int mt = t / NT, nt = t - mt * NT;
-            const int iu = 8 * mt + g, ju = 8 * nt + g;
-            const double a = iu < W ? S0[row * W + iu] : ((iu == W && vrow) ? 1.0 : 0.0);
-            const double b = ju < W ? S1[row * W + ju] : 0.0;
-            dmma(G[i], a, b);
+        for (int m = 0; m < 3; m++) av[m] = ar[8 * (3 * wb + m) + g];
+#pragma unroll
+        for (int n = 0; n < 7; n++) {
+          const int ju = 8 * (n_first + n) + g;
+          bv[n] = ((n < 6 || wide) && ju < W) ? br[ju] : 0.0;
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+#pragma unroll
+          for (int n = 0; n < 6; n++) dmma(G[m][n], av[m], bv[n]);
+          if (wide) dmma(G[m][6], av[m], bv[6]);
+        }
+        if (!wide) {
+          const int iu = 96 + g;
+          const double as = iu < W ? ar[iu] : ((iu == W && ks < 4) ? 1.0 : 0.0);   // rows 0..15 are the value stream
+#pragma unroll
+          for (int n = 0; n < 4; n++) {
+            if (n < snn) {
+              const int ju = 8 * (sn0 + n) + g;
+              dmma(GS[n], as, ju < W ? br[ju] : 0.0);
+            }
           }
         }
       }
@@ -407,17 +432,31 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     }
     // (5) flush this warp's tiles of G_l
 #pragma unroll
-    for (int i = 0; i < 22; i++) {
-      if (i < tn) {
-        const int t = t0 + i;
-        const int mt = t / NT, nt = t - mt * NT;
-        const int iu = 8 * mt + g;
+    for (int m = 0; m < 3; m++) {
+      const int iu = 8 * (3 * wb + m) + g;                   // < 96
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int ju = 8 * nt + 2 * q + e;
-          if (ju < W) {
-            if (iu < W) outp[woff(l) + iu * W + ju] = G[i][e];
-            else if (iu == W) outp[boff(l) + ju] = G[i][e];
+      for (int n = 0; n < 7; n++) {
+        if (n < 6 || wide) {
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int ju = 8 * (n_first + n) + 2 * q + e;
+            if (ju < W) outp[woff(l) + iu * W + ju] = G[m][n][e];
+          }
+        }
+      }
+    }
+    if (!wide) {
+      const int iu = 96 + g;
+#pragma unroll
+      for (int n = 0; n < 4; n++) {
+        if (n < snn) {
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int ju = 8 * (sn0 + n) + 2 * q + e;
+            if (ju < W) {
+              if (iu < W) outp[woff(l) + iu * W + ju] = GS[n][e];
+              else if (iu == W) outp[boff(l) + ju] = GS[n][e];
+            }
           }
         }
       }
@@ -426,33 +465,41 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
 
   // =============================== B0: layer-0 gradient, direct ===============================
   __syncthreads();
-  if (tid < W) {
-    const int u = tid;
-    const double* A0 = A + (size_t)1 * 4 * SSZ;          // written by l = 1 (buffer (1&1)?1:0 = 1)
-    const double zx = sc0 * __ldg(p.w + u), zt = sc1 * __ldg(p.w + W + u);
+  {
+    const int u = tid & 127, half = tid >> 7;              // 2 point groups x 100 units
     double gx = 0.0, gt = 0.0, gb = 0.0;
-    for (int pt = 0; pt < nrounds * RPTS; pt++) {
-      const long long gp = base + (pt < npts ? pt : npts - 1);
-      const double xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;
-      const double th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
-      const size_t o = (size_t)pt * W + u;
-      const double a = H[o], ax = H[SSZ + o], at = H[2 * SSZ + o], axx = H[3 * SSZ + o];
-      const double B0 = A0[o], Bx = A0[SSZ + o], Bt = A0[2 * SSZ + o], Bxx = A0[3 * SSZ + o];
-      const double s = fma(-a, a, 1.0);
-      const double u1 = fma(ax, Bx, at * Bt);
-      const double u2 = fma(a, axx, ax * ax);
-      double z = fma(-2.0 * a, u1, s * B0);
-      z = fma(-2.0 * Bxx, u2, z);
-      const double zbx = fma(-4.0 * a * ax, Bxx, s * Bx);
-      const double zbt = s * Bt;
-      gx = fma(xh, z, fma(sc0, zbx, gx));
-      gt = fma(th, z, fma(sc1, zbt, gt));
-      gb += z;
+    if (u < W) {
+      const double* A0 = A + (size_t)1 * 4 * SSZ;          // written by l = 1
+      const int npad = nrounds * RPTS;
+      const int p0 = half * (npad / 2), p1 = half ? npad : npad / 2;
+#pragma unroll 4
+      for (int pt = p0; pt < p1; pt++) {
+        const long long gp = base + (pt < npts ? pt : npts - 1);
+        const double xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;
+        const double th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
+        const size_t o = (size_t)pt * W + u;
+        const double a = H[o], ax = H[SSZ + o], at = H[2 * SSZ + o], axx = H[3 * SSZ + o];
+        const double B0 = A0[o], Bx = A0[SSZ + o], Bt = A0[2 * SSZ + o], Bxx = A0[3 * SSZ + o];
+        const double s = fma(-a, a, 1.0);
+        const double u1 = fma(ax, Bx, at * Bt);
+        const double u2 = fma(a, axx, ax * ax);
+        double z = fma(-2.0 * a, u1, s * B0);
+        z = fma(-2.0 * Bxx, u2, z);
+        const double zbx = fma(-4.0 * a * ax, Bxx, s * Bx);
+        const double zbt = s * Bt;
+        gx = fma(xh, z, fma(sc0, zbx, gx));
+        gt = fma(th, z, fma(sc1, zbt, gt));
+        gb += z;
+      }
     }
-    (void)zx; (void)zt;
-    outp[woff(0) + u] = gx;
-    outp[woff(0) + W + u] = gt;
-    outp[boff(0) + u] = gb;
+    double* comb = S0;                                       // staging slab is free now
+    if (half == 1 && u < W) { comb[u] = gx; comb[128 + u] = gt; comb[256 + u] = gb; }
+    __syncthreads();
+    if (half == 0 && u < W) {
+      outp[woff(0) + u] = gx + comb[u];
+      outp[woff(0) + W + u] = gt + comb[128 + u];
+      outp[boff(0) + u] = gb + comb[256 + u];
+    }
   }
 }
 
