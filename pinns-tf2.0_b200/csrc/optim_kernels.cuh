@@ -20,6 +20,8 @@ struct LbfgsState {
   double max_eval;
   double lr, tol_fun, tol_x;
   double h_diag, t, f, f_old;
+  double ro[128];   // 1 / (y_i . s_i) per ring slot, cached when the pair is pushed (same dot product the reference
+                    // recomputes every iteration, utils/custom_lbfgs.py:121-123)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -127,26 +129,32 @@ __global__ void reduce_adam(const double* __restrict__ partials, int n_cta, int 
 // Runs (a) the stop tests of the previous iteration's evaluation, (b) the memory update and two-loop
 // recursion, (c) the step, exactly in the reference order (utils/custom_lbfgs.py:81-221).
 // ------------------------------------------------------------------------------------------------
-constexpr int LB_THREADS = 1024;
-
-__device__ __forceinline__ double block_sum(double v, double* red) {
+// Block-wide sum in a fixed order, ONE barrier per call: the per-warp partials go to alternating halves of `red`, so a
+// call never overwrites values another warp may still be reading (a warp can be at most one call ahead).
+template <int NT>
+__device__ __forceinline__ double block_sum_t(double v, double* red, int& phase) {
   v = warp_sum(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();   // protect red[] from the previous use
-  if (lane == 0) red[warp] = v;
+  double* buf = red + (phase & 1) * 32;
+  phase++;
+  if (lane == 0) buf[warp] = v;
   __syncthreads();
-  double s = (lane < (LB_THREADS / 32)) ? red[lane] : 0.0;
-  s = warp_sum(s);
-  return s;   // every thread holds the total
+  constexpr int NW = NT / 32;
+  double s = (lane < NW) ? buf[lane] : 0.0;
+#pragma unroll
+  for (int m = NW / 2; m > 0; m >>= 1) s += shfl_xor_d(s, m);
+  return __shfl_sync(0xffffffffu, s, 0);   // every thread holds the total
 }
 
-template <int EPT>
+template <int EPT, int LB_THREADS>
 __global__ void __launch_bounds__(LB_THREADS, 1)
 lbfgs_iterate(LbfgsState* __restrict__ st, double* __restrict__ w, const double* __restrict__ R, int P,
               double* __restrict__ g_old, double* __restrict__ d, double* __restrict__ S, double* __restrict__ Y,
               double* __restrict__ x_final, double* __restrict__ f_hist, int* __restrict__ logged, int finalize_only) {
-  __shared__ double red[32];
+  __shared__ double red[64];
   __shared__ double ro[128], al[128];
+  int red_phase = 0;
+  auto block_sum = [&](double v, double*) { return block_sum_t<LB_THREADS>(v, red, red_phase); };
   const int tid = threadIdx.x;
   if (st->status != 0) return;
 
@@ -231,58 +239,80 @@ lbfgs_iterate(LbfgsState* __restrict__ st, double* __restrict__ w, const double*
         if (i < P) { S[(size_t)slot * P + i] = sv[e]; Y[(size_t)slot * P + i] = yv[e]; }
       }
       h_diag = ys / yy;
+      if (tid == 0) st->ro[slot] = 1.0 / ys;
       __syncthreads();
     }
-    // ro_i = 1 / (y_i . s_i)   (:121-123), i = 0 oldest
-    for (int i = 0; i < k; i++) {
-      const size_t base = (size_t)((head + i) % n_corr) * P;
-      double a = 0.0;
-#pragma unroll
-      for (int e = 0; e < EPT; e++) {
-        const int j = tid + e * LB_THREADS;
-        a += j < P ? Y[base + j] * S[base + j] : 0.0;
-      }
-      a = block_sum(a, red);
-      if (tid == 0) ro[i] = 1.0 / a;
-    }
+    // ro_i (i = 0 oldest) from the per-slot cache
+    for (int i = tid; i < k; i += LB_THREADS) ro[i] = st->ro[(head + i) % n_corr];
     __syncthreads();
     double qv[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; e++) qv[e] = -gv[e];                        // :130
-    for (int i = k - 1; i >= 0; i--) {                                   // :131-133
-      const size_t base = (size_t)((head + i) % n_corr) * P;
-      double a = 0.0;
+    // first loop (:131-133), newest to oldest; the next pair is prefetched while the current reduction runs
+    double sn[EPT], yn[EPT];
+    if (k > 0) {
+      const size_t base = (size_t)((head + k - 1) % n_corr) * P;
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
         const int j = tid + e * LB_THREADS;
-        a += j < P ? S[base + j] * qv[e] : 0.0;
+        sn[e] = j < P ? S[base + j] : 0.0;
+        yn[e] = j < P ? Y[base + j] : 0.0;
       }
+    }
+    for (int i = k - 1; i >= 0; i--) {
+      double sc[EPT], yc[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; e++) { sc[e] = sn[e]; yc[e] = yn[e]; }
+      if (i > 0) {
+        const size_t base = (size_t)((head + i - 1) % n_corr) * P;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+          const int j = tid + e * LB_THREADS;
+          sn[e] = j < P ? S[base + j] : 0.0;
+          yn[e] = j < P ? Y[base + j] : 0.0;
+        }
+      }
+      double a = 0.0;
+#pragma unroll
+      for (int e = 0; e < EPT; e++) a += sc[e] * qv[e];
       a = block_sum(a, red) * ro[i];
       if (tid == 0) al[i] = a;
 #pragma unroll
-      for (int e = 0; e < EPT; e++) {
-        const int j = tid + e * LB_THREADS;
-        if (j < P) qv[e] -= a * Y[base + j];
-      }
+      for (int e = 0; e < EPT; e++) qv[e] -= a * yc[e];
     }
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < EPT; e++) qv[e] *= h_diag;                       // :136
-    for (int i = 0; i < k; i++) {                                        // :137-139
-      const size_t base = (size_t)((head + i) % n_corr) * P;
-      double a = 0.0;
+    // second loop (:137-139), oldest to newest
+    if (k > 0) {
+      const size_t base = (size_t)(head % n_corr) * P;
 #pragma unroll
       for (int e = 0; e < EPT; e++) {
         const int j = tid + e * LB_THREADS;
-        a += j < P ? Y[base + j] * qv[e] : 0.0;
+        sn[e] = j < P ? S[base + j] : 0.0;
+        yn[e] = j < P ? Y[base + j] : 0.0;
       }
+    }
+    for (int i = 0; i < k; i++) {
+      double sc[EPT], yc[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; e++) { sc[e] = sn[e]; yc[e] = yn[e]; }
+      if (i + 1 < k) {
+        const size_t base = (size_t)((head + i + 1) % n_corr) * P;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+          const int j = tid + e * LB_THREADS;
+          sn[e] = j < P ? S[base + j] : 0.0;
+          yn[e] = j < P ? Y[base + j] : 0.0;
+        }
+      }
+      double a = 0.0;
+#pragma unroll
+      for (int e = 0; e < EPT; e++) a += yc[e] * qv[e];
       const double be = block_sum(a, red) * ro[i];
       const double c = al[i] - be;
 #pragma unroll
-      for (int e = 0; e < EPT; e++) {
-        const int j = tid + e * LB_THREADS;
-        if (j < P) qv[e] += c * S[base + j];
-      }
+      for (int e = 0; e < EPT; e++) qv[e] += c * sc[e];
     }
 #pragma unroll
     for (int e = 0; e < EPT; e++) dv[e] = qv[e];

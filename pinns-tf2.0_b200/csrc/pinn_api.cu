@@ -618,8 +618,7 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
   if (tol_x == 0.0) tol_x = 1e-19;                                  // :51
   if (sync_every < 1) sync_every = 1;
   const int P = h->P;
-  const int ept = (P + pinn::LB_THREADS - 1) / pinn::LB_THREADS;
-  if (ept > 32) return fail("pinn_lbfgs: parameter vector too large for the single-CTA L-BFGS kernel");
+  if (P > 32 * 1024) return fail("pinn_lbfgs: parameter vector too large for the single-CTA L-BFGS kernel");
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->d_gold) {
     CUDA_TRY(cudaMalloc((void**)&h->d_gold, h->w_cap * 8));
@@ -659,12 +658,12 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
   std::vector<int> lg(max_iter + 2);
   int reported = 0;
   auto iterate = [&](int fin) -> int {
-#define LB_LAUNCH(E)                                                                                                   \
-  pinn::lbfgs_iterate<E><<<1, pinn::LB_THREADS, 0, h->stream>>>(h->d_lb, h->d_w, h->d_R, P, h->d_gold, h->d_d, h->d_S, \
-                                                                h->d_Y, h->d_xfinal, h->d_fhist, h->d_logged, fin)
-    if (ept <= 3) LB_LAUNCH(3);
-    else if (ept <= 8) LB_LAUNCH(8);
-    else LB_LAUNCH(32);
+#define LB_LAUNCH(E, NT)                                                                                       \
+  pinn::lbfgs_iterate<E, NT><<<1, NT, 0, h->stream>>>(h->d_lb, h->d_w, h->d_R, P, h->d_gold, h->d_d, h->d_S, h->d_Y, \
+                                                      h->d_xfinal, h->d_fhist, h->d_logged, fin)
+    if (P <= 12 * 256) LB_LAUNCH(12, 256);        // Burgers-size vectors: 8 warps, 12 entries per thread
+    else if (P <= 8 * 1024) LB_LAUNCH(8, 1024);
+    else LB_LAUNCH(32, 1024);
 #undef LB_LAUNCH
     if (cudaGetLastError() != cudaSuccess) return fail("lbfgs_iterate launch failed");
     h->launches++;
