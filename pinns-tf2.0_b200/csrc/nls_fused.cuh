@@ -102,7 +102,7 @@ __device__ __forceinline__ void gemm_rows(double (&C)[4][4][2], const double* sl
                                           int pg, int nt0, int ntn, int lane) {
   const int g = lane >> 2, q = lane & 3;
   const int prow_g = prow(g);
-#pragma unroll 1
+#pragma unroll 5
   for (int ks = 0; ks < KS; ks++) {
     double a[4], b[4];
 #pragma unroll
@@ -339,42 +339,56 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       // (2) activation adjoint Z-bar for this lane's point and units -> S1 (row layout)
       const int pt = r * RPTS + myp;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int u = 8 * (nt0 + j) + 2 * q;
-        if (j < ntn && u < W) {
-          double hv[4][2], av[4][2];
+      for (int jb = 0; jb < 4; jb += 2) {
+        // issue the global loads of two N tiles back to back, then do the arithmetic (hides the L2/HBM latency)
+        double hv[2][4][2], av[2][4][2];
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+          const int j = jb + jj;
+          const int u = 8 * (nt0 + j) + 2 * q;
+          const bool on = j < ntn && u < W;
 #pragma unroll
           for (int s = 0; s < 4; s++) {
-            const double2 h2 = *reinterpret_cast<const double2*>(Hl + s * SSZ + (size_t)pt * W + u);
-            hv[s][0] = h2.x; hv[s][1] = h2.y;
-            if (l == 3) {
-              // adjoint of the last hidden layer's outputs straight from the seeds: A[s][u] = sum_o seed[s][o] W4[u][o]
-              const double s0 = SEED[pt * 8 + 2 * s], s1 = SEED[pt * 8 + 2 * s + 1];
-              av[s][0] = fma(s0, __ldg(W4 + 2 * u), s1 * __ldg(W4 + 2 * u + 1));
-              av[s][1] = fma(s0, __ldg(W4 + 2 * u + 2), s1 * __ldg(W4 + 2 * u + 3));
-            } else {
-              const double2 a2 = *reinterpret_cast<const double2*>(Ain + s * SSZ + (size_t)pt * W + u);
-              av[s][0] = a2.x; av[s][1] = a2.y;
+            double2 h2 = make_double2(0.0, 0.0), a2 = make_double2(0.0, 0.0);
+            if (on) {
+              h2 = *reinterpret_cast<const double2*>(Hl + s * SSZ + (size_t)pt * W + u);
+              if (l == 3) {
+                // adjoint of the last hidden layer's outputs straight from the seeds: A[s][u] = sum_o seed[s][o] W4[u][o]
+                const double s0 = SEED[pt * 8 + 2 * s], s1 = SEED[pt * 8 + 2 * s + 1];
+                a2.x = fma(s0, __ldg(W4 + 2 * u), s1 * __ldg(W4 + 2 * u + 1));
+                a2.y = fma(s0, __ldg(W4 + 2 * u + 2), s1 * __ldg(W4 + 2 * u + 3));
+              } else {
+                a2 = *reinterpret_cast<const double2*>(Ain + s * SSZ + (size_t)pt * W + u);
+              }
             }
+            hv[jj][s][0] = h2.x; hv[jj][s][1] = h2.y;
+            av[jj][s][0] = a2.x; av[jj][s][1] = a2.y;
           }
-          double z[4][2];
+        }
 #pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const double a = hv[0][e], ax = hv[1][e], at = hv[2][e], axx = hv[3][e];
-            const double A0 = av[0][e], Ax = av[1][e], At = av[2][e], Axx = av[3][e];
-            const double s = fma(-a, a, 1.0);
-            const double u1 = fma(ax, Ax, at * At);
-            const double u2 = fma(a, axx, ax * ax);
-            double zz = fma(-2.0 * a, u1, s * A0);
-            zz = fma(-2.0 * Axx, u2, zz);
-            z[0][e] = zz;
-            z[1][e] = fma(-4.0 * a * ax, Axx, s * Ax);
-            z[2][e] = s * At;
-            z[3][e] = s * Axx;
+        for (int jj = 0; jj < 2; jj++) {
+          const int j = jb + jj;
+          const int u = 8 * (nt0 + j) + 2 * q;
+          if (j < ntn && u < W) {
+            double z[4][2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const double a = hv[jj][0][e], ax = hv[jj][1][e], at = hv[jj][2][e], axx = hv[jj][3][e];
+              const double A0 = av[jj][0][e], Ax = av[jj][1][e], At = av[jj][2][e], Axx = av[jj][3][e];
+              const double s = fma(-a, a, 1.0);
+              const double u1 = fma(ax, Ax, at * At);
+              const double u2 = fma(a, axx, ax * ax);
+              double zz = fma(-2.0 * a, u1, s * A0);
+              zz = fma(-2.0 * Axx, u2, zz);
+              z[0][e] = zz;
+              z[1][e] = fma(-4.0 * a * ax, Axx, s * Ax);
+              z[2][e] = s * At;
+              z[3][e] = s * Axx;
+            }
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+              *reinterpret_cast<double2*>(S1 + (16 * s + myp) * W + u) = make_double2(z[s][0], z[s][1]);
           }
-#pragma unroll
-          for (int s = 0; s < 4; s++)
-            *reinterpret_cast<double2*>(S1 + (16 * s + myp) * W + u) = make_double2(z[s][0], z[s][1]);
         }
       }
       cp_async_wait<0>();
