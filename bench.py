@@ -61,6 +61,85 @@ def fp64_peak():
         (FP64_PEAK_TFLOPS_FALLBACK, "fallback")
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel, per launch, from the committed ncu --set full
+    capture (profiles/ncu_burgers_v2_r01_summary.csv)."""
+    try:
+        tot = 0.0
+        for line in open(os.path.join(ROOT, "profiles", "ncu_burgers_v2_r01_summary.csv")):
+            f = line.strip().split(",")
+            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(f[1], None)
+                if mult is None:
+                    return None
+                tot += float(f[2]) * mult
+        return tot or None
+    except Exception:
+        return None
+
+
+def measure_extras(pinn_cabi, n_f):
+    """Other SURVEY section-8 configurations, measured briefly on the same box (not the headline metric)."""
+    out = {}
+    try:
+        X_f, X_u, u = synthetic_problem(4321, n_f)
+        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, LAYERS, LB, UB)
+        p.set_pde_params([NU]); p.set_data(X_u, u); p.set_collocation(X_f[:, 0], X_f[:, 1]); p.set_weights(init_weights())
+        for _ in range(20):
+            p.adam_step(ADAM_LR, sync=False)
+        p.sync()
+        t0 = time.perf_counter()
+        r = p.lbfgs(60, learning_rate=0.8, n_correction=50, tol_fun=float(np.finfo(float).eps), sync_every=10)
+        dt = time.perf_counter() - t0
+        out["burgers_lbfgs"] = {"config": "BASELINE configs[1] L-BFGS phase: N_f=%d, lr 0.8, 50 corrections, sync every 10 its" % n_f,
+                                "ms_per_iteration": dt / max(1, r["n_iter"]) * 1e3, "points_per_s": n_f * r["n_iter"] / dt,
+                                "iterations": r["n_iter"]}
+        p.close()
+    except Exception as e:  # pragma: no cover
+        out["burgers_lbfgs"] = {"error": str(e)}
+    try:
+        rng = np.random.default_rng(7)
+        X_u = LB + (UB - LB) * rng.random((2000, 2)); u = rng.uniform(-1, 1, (2000, 1))
+        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_IDE, LAYERS, LB, UB)
+        p.set_data(X_u, u); p.set_weights(np.concatenate([init_weights(), [0.0, -6.0]]))
+        for _ in range(10):
+            p.adam_step(ADAM_LR, sync=False)
+        p.sync(); t0 = time.perf_counter()
+        for _ in range(100):
+            p.adam_step(ADAM_LR, sync=False)
+        p.sync(); dt = (time.perf_counter() - t0) / 100
+        out["burgers_identification"] = {"config": "BASELINE configs[3]: N=2000 data=collocation points, lambda_1, lambda_2 trainable",
+                                         "ms_per_step": dt * 1e3, "points_per_s": 2000 / dt}
+        p.close()
+    except Exception as e:  # pragma: no cover
+        out["burgers_identification"] = {"error": str(e)}
+    try:
+        L = [2, 100, 100, 100, 100, 2]
+        lb, ub = np.array([-5.0, 0.0]), np.array([5.0, np.pi / 2])
+        rng = np.random.default_rng(9)
+        X_f = lb + (ub - lb) * rng.random((20000, 2)); tb = rng.uniform(0, ub[1], (50, 1)); x0 = rng.uniform(-5, 5, (50, 1))
+        uv0 = np.stack([2 / np.cosh(x0[:, 0]), 0 * x0[:, 0]], 1)
+        from neuralnetwork import _glorot_normal
+        p = pinn_cabi.Pinn(pinn_cabi.NLS_INF, L, lb, ub)
+        p.set_collocation(X_f[:, 0], X_f[:, 1]); p.set_boundary(tb); p.set_data(x0, uv0)
+        p.set_weights(_glorot_normal(L, np.random.default_rng(1234)))
+        for _ in range(3):
+            p.adam_step(0.05, 0.99, 0.999, 0.1, sync=False)
+        p.sync(); t0 = time.perf_counter()
+        for _ in range(20):
+            p.adam_step(0.05, 0.99, 0.999, 0.1, sync=False)
+        p.sync(); dt = (time.perf_counter() - t0) / 20
+        k_ms = p.time_kernel_ms(5) / 5
+        flops = 20150 * 24 * 30400.0
+        out["schrodinger"] = {"config": "BASELINE configs[2]: [2,100x4,2], N_f=20000, N_0=N_b=50, Adam lr .05 b1 .99 eps .1",
+                              "ms_per_step": dt * 1e3, "points_per_s": 20000 / dt, "kernel_ms": k_ms,
+                              "roofline_frac_fp64": flops / (k_ms * 1e-3) / 1e12 / fp64_peak()[0]}
+        p.close()
+    except Exception as e:  # pragma: no cover
+        out["schrodinger"] = {"error": str(e)}
+    return out
+
+
 def hbm_peak():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
@@ -171,6 +250,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-f", type=int, default=N_F_PER_GPU, help="collocation points per GPU (default: BASELINE configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -268,7 +348,9 @@ def main():
     achieved = flops / (ms_kernel * 1e-3) / 1e12
     alg_bytes = 16.0 * n_f + 8.0 * 3021 + 8.0 * 3024
     roofline = {"bound": "tensor", "pipe": "fp64 (DMMA.8x8x4 + DFMA share one pipe)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic_bytes(),
+                "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/ncu_burgers_v2_r01_summary.csv)",
+                "algorithmic_bytes": alg_bytes,
                 "kernel": "pinn::burgers::fused_loss_grad", "kernel_ms": ms_kernel,
                 "hbm": {"achieved": alg_bytes / (ms_kernel * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                         "frac": alg_bytes / (ms_kernel * 1e-3) / 1e9 / hbm, "peak_source": hbm_src,
@@ -293,6 +375,9 @@ def main():
     e2e = {"value": n_f_global / e2e_s, "unit": "points/s", "h2d_bytes_per_step": 16 * n_f, "d2h_bytes_per_step": 8,
            "ms_per_step": e2e_s * 1e3, "timing": "wall clock around the API calls, barrier+synchronize both sides"}
 
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = measure_extras(pinn_cabi, n_f)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, cores, _ = time_reference_port(n_f, 12, 3)
@@ -315,6 +400,8 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if extras is not None:
+            line["extras"] = extras
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -1,8 +1,12 @@
 """Data preparation for the continuous-time Burgers problems (restates 1d-burgers/burgersutil.py:27-36, 63-75, 99-131
 of the reference; the discrete-time/IRK branches are out of scope).  Plot helpers degrade to no-ops when
 matplotlib is missing (cosmetic)."""
+import sys
+
 import numpy as np
 import scipy.io
+
+sys.path.append("utils")   # the reference modules do the same (burgersutil.py:24, schrodingerutil.py:18); scripts rely on it
 
 try:
     from pyDOE import lhs

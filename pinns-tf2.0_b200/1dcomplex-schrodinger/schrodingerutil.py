@@ -2,8 +2,12 @@
 import importlib.util
 import os
 
+import sys
+
 import numpy as np
 import scipy.io
+
+sys.path.append("utils")   # the reference modules do the same (burgersutil.py:24, schrodingerutil.py:18); scripts rely on it
 
 _b = importlib.util.spec_from_file_location("_burgersutil_lhs", os.path.join(os.path.dirname(os.path.abspath(__file__)), "..",
                                                                              "1d-burgers", "burgersutil.py"))

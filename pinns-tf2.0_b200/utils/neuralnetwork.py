@@ -271,11 +271,16 @@ def _native_loss(self, u, u_pred=None):
 
 
 def _native_f_model(self, *args):
-    """f_model on the stored residual points (inf_cont_burgers.py:65-90 / ide_cont_burgers.py:56-85 /
-    inf_cont_schrodinger.py:79-105)."""
+    """f_model (inf_cont_burgers.py:65-90 / ide_cont_burgers.py:56-85 / inf_cont_schrodinger.py:79-105): on the stored
+    residual points, or -- identification, where the reference passes the points explicitly -- on the given points."""
     n = self._native()
-    cnt = np.asarray(self._bound_refs[0]).shape[0] if self._pde_id() == pinn_cabi.BURGERS_IDE else np.asarray(self.x_f).shape[0]
-    f = n.residual(cnt)
+    if self._pde_id() == pinn_cabi.BURGERS_IDE:
+        if args:
+            U, Ux, Ut, Uxx = n.derivatives(np.asarray(args[0], dtype=np.float64))
+            w = n.get_weights()
+            return _t(Ut + w[-2] * U * Ux - np.exp(w[-1]) * Uxx)
+        return _t(n.residual(np.asarray(self._bound_refs[0]).shape[0]))
+    f = n.residual(np.asarray(self.x_f).shape[0])
     if f.shape[1] == 2:
         return _t(f[:, 0:1]), _t(f[:, 1:2])
     return _t(f)

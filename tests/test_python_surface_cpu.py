@@ -96,3 +96,36 @@ def test_unmodified_reference_script_runs_up_to_the_gpu_boundary():
     out = r.stdout + r.stderr
     assert "Hyperparameters" in out and "Training started" in out      # data prep, Logger, class creation all worked
     assert "no CUDA device" in out and r.returncode != 0                # and it stops exactly at the GPU boundary
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_indentation_normaliser_repairs_ide_cont_and_leaves_good_scripts_alone():
+    import ast
+    sys.path.insert(0, PKG)
+    import run_reference_script as r
+    src = open(os.path.join(REF, "1d-burgers", "ide_cont_burgers.py"), encoding="utf-8").read()
+    with pytest.raises(SyntaxError):
+        ast.parse(src)                                                   # does not parse as shipped
+    tree = ast.parse(r.normalise_indentation(src))
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef)][0]
+    methods = {m.name: m for m in cls.body if isinstance(m, ast.FunctionDef)}
+    assert list(methods) == ["__init__", "f_model", "loss", "wrap_training_variables", "get_weights", "set_weights",
+                             "get_params", "fit", "predict"]
+    assert len(methods["__init__"].body) == 3                            # super().__init__, lambda_1, lambda_2
+    with_body = [b for b in methods["f_model"].body if isinstance(b, ast.With)][0].body
+    assert len(with_body) == 5                                           # watch, watch, stack, model, u_x (like inf_cont)
+    for f in ("1d-burgers/inf_cont_burgers.py", "1dcomplex-schrodinger/inf_cont_schrodinger.py"):
+        s0 = open(os.path.join(REF, f), encoding="utf-8").read()
+        assert ast.dump(ast.parse(r.normalise_indentation(s0))) == ast.dump(ast.parse(s0))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+@pytest.mark.parametrize("script", ["1d-burgers/ide_cont_burgers.py", "1dcomplex-schrodinger/inf_cont_schrodinger.py"])
+def test_other_reference_scripts_reach_the_gpu_boundary(script):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([sys.executable, os.path.join(PKG, "run_reference_script.py"), os.path.join(REF, script)],
+                       capture_output=True, text=True, timeout=300)
+    out = r.stdout + r.stderr
+    assert "Training started" in out and "no CUDA device" in out and r.returncode != 0
