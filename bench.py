@@ -88,6 +88,7 @@ def measure_extras(pinn_cabi, n_f):
         for _ in range(20):
             p.adam_step(ADAM_LR, sync=False)
         p.sync()
+        p.lbfgs(2, learning_rate=0.8, n_correction=50, tol_fun=float(np.finfo(float).eps))   # allocate history buffers
         t0 = time.perf_counter()
         r = p.lbfgs(60, learning_rate=0.8, n_correction=50, tol_fun=float(np.finfo(float).eps), sync_every=10)
         dt = time.perf_counter() - t0
