@@ -228,14 +228,40 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   {
     const double* H3 = H + (size_t)3 * LSZ;
     const double* W4 = p.w + woff(4);
-    // head outputs out[pt][2s+o] -> OUTV (the adjoint scratch is still unused at this point)
+    // head outputs out[pt][2s+o] -> OUTV (the adjoint scratch is still unused at this point).
+    // One warp per point, lanes over the 100 hidden units (coalesced), 8 partial sums reduced by shuffles.
     double* OUTV = A;
-    for (int i = tid; i < nrounds * RPTS * 8; i += THREADS) {
-      const int pt = i >> 3, so = i & 7, s = so >> 1, o = so & 1;
-      const double* h = H3 + s * SSZ + (size_t)pt * W;
-      double acc = (s == 0) ? __ldg(p.w + boff(4) + o) : 0.0;
-      for (int k = 0; k < W; k++) acc = fma(h[k], __ldg(W4 + 2 * k + o), acc);
-      OUTV[i] = acc;
+    {
+      double w40[4], w41[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int k = lane + 32 * c;
+        w40[c] = k < W ? __ldg(W4 + 2 * k) : 0.0;
+        w41[c] = k < W ? __ldg(W4 + 2 * k + 1) : 0.0;
+      }
+      const double b40 = __ldg(p.w + boff(4)), b41 = __ldg(p.w + boff(4) + 1);
+      for (int pt = warp; pt < nrounds * RPTS; pt += WARPS) {
+        double acc[8];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const int k = lane + 32 * c;
+            const double hv = k < W ? H3[s * SSZ + (size_t)pt * W + k] : 0.0;
+            a0 = fma(hv, w40[c], a0);
+            a1 = fma(hv, w41[c], a1);
+          }
+          acc[2 * s] = a0; acc[2 * s + 1] = a1;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) acc[c] = warp_sum(acc[c]);
+        if (lane == 0) {
+          acc[0] += b40; acc[1] += b41;
+#pragma unroll
+          for (int c = 0; c < 8; c++) OUTV[pt * 8 + c] = acc[c];
+        }
+      }
     }
     __syncthreads();
     double l0 = 0.0, lbd = 0.0, lf = 0.0;
@@ -291,19 +317,35 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       outp[IDX_L0 + tid] = s;
     }
     // head gradient: G4[k][o] = sum_pt sum_s H3[s][pt][k] seed[pt][s][o];  bias: sum_pt seed[pt][0][o]
-    if (tid < 2 * W) {
-      const int k = tid >> 1, o = tid & 1;
-      double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+      const int k = tid & 127, half = tid >> 7;
+      const int npad = nrounds * RPTS;
+      const int p0 = half * (npad / 2), p1 = half ? npad : npad / 2;
+      double g0 = 0.0, g1 = 0.0, gb = 0.0;
+      if (k < W) {
 #pragma unroll 4
-      for (int pt = 0; pt < nrounds * RPTS; pt++)
+        for (int pt = p0; pt < p1; pt++) {
 #pragma unroll
-        for (int s = 0; s < 4; s++) acc4[s] = fma(H3[s * SSZ + (size_t)pt * W + k], SEED[pt * 8 + 2 * s + o], acc4[s]);
-      outp[woff(4) + 2 * k + o] = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
-    } else if (tid < 2 * W + 2) {
-      const int o = tid - 2 * W;
-      double acc = 0.0;
-      for (int pt = 0; pt < nrounds * RPTS; pt++) acc += SEED[pt * 8 + o];
-      outp[boff(4) + o] = acc;
+          for (int s = 0; s < 4; s++) {
+            const double hv = H3[s * SSZ + (size_t)pt * W + k];
+            g0 = fma(hv, SEED[pt * 8 + 2 * s], g0);
+            g1 = fma(hv, SEED[pt * 8 + 2 * s + 1], g1);
+          }
+        }
+      } else if (k < W + 2) {
+        for (int pt = p0; pt < p1; pt++) gb += SEED[pt * 8 + (k - W)];
+      }
+      double* comb = S0;
+      if (half == 1) { comb[k] = g0; comb[128 + k] = g1; comb[256 + k] = gb; }
+      __syncthreads();
+      if (half == 0) {
+        if (k < W) {
+          outp[woff(4) + 2 * k] = g0 + comb[k];
+          outp[woff(4) + 2 * k + 1] = g1 + comb[128 + k];
+        } else if (k < W + 2) {
+          outp[boff(4) + (k - W)] = gb + comb[256 + k];
+        }
+      }
     }
     __syncthreads();
   }
@@ -480,39 +522,51 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   // =============================== B0: layer-0 gradient, direct ===============================
   __syncthreads();
   {
-    const int u = tid & 127, half = tid >> 7;              // 2 point groups x 100 units
-    double gx = 0.0, gt = 0.0, gb = 0.0;
-    if (u < W) {
-      const double* A0 = A + (size_t)1 * 4 * SSZ;          // written by l = 1
-      const int npad = nrounds * RPTS;
-      const int p0 = half * (npad / 2), p1 = half ? npad : npad / 2;
-#pragma unroll 4
-      for (int pt = p0; pt < p1; pt++) {
-        const long long gp = base + (pt < npts ? pt : npts - 1);
-        const double xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;
-        const double th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
-        const size_t o = (size_t)pt * W + u;
-        const double a = H[o], ax = H[SSZ + o], at = H[2 * SSZ + o], axx = H[3 * SSZ + o];
-        const double B0 = A0[o], Bx = A0[SSZ + o], Bt = A0[2 * SSZ + o], Bxx = A0[3 * SSZ + o];
-        const double s = fma(-a, a, 1.0);
-        const double u1 = fma(ax, Bx, at * Bt);
-        const double u2 = fma(a, axx, ax * ax);
-        double z = fma(-2.0 * a, u1, s * B0);
-        z = fma(-2.0 * Bxx, u2, z);
-        const double zbx = fma(-4.0 * a * ax, Bxx, s * Bx);
-        const double zbt = s * Bt;
-        gx = fma(xh, z, fma(sc0, zbx, gx));
-        gt = fma(th, z, fma(sc1, zbt, gt));
-        gb += z;
+    // warp w takes the points pt = w, w+8, ...; lane covers units lane, lane+32, lane+64, lane+96 (coalesced rows);
+    // many independent loads in flight per thread, then a fixed-order combine over the 8 warps.
+    const double* A0 = A + (size_t)1 * 4 * SSZ;            // written by l = 1
+    double gx[4] = {0, 0, 0, 0}, gt[4] = {0, 0, 0, 0}, gb[4] = {0, 0, 0, 0};
+    const int npad = nrounds * RPTS;
+#pragma unroll 2
+    for (int pt = warp; pt < npad; pt += WARPS) {
+      const long long gp = base + (pt < npts ? pt : npts - 1);
+      const double xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;
+      const double th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int u = lane + 32 * c;
+        if (u < W) {
+          const size_t o = (size_t)pt * W + u;
+          const double a = H[o], ax = H[SSZ + o], at = H[2 * SSZ + o], axx = H[3 * SSZ + o];
+          const double B0 = A0[o], Bx = A0[SSZ + o], Bt = A0[2 * SSZ + o], Bxx = A0[3 * SSZ + o];
+          const double s = fma(-a, a, 1.0);
+          const double u1 = fma(ax, Bx, at * Bt);
+          const double u2 = fma(a, axx, ax * ax);
+          double z = fma(-2.0 * a, u1, s * B0);
+          z = fma(-2.0 * Bxx, u2, z);
+          const double zbx = fma(-4.0 * a * ax, Bxx, s * Bx);
+          const double zbt = s * Bt;
+          gx[c] = fma(xh, z, fma(sc0, zbx, gx[c]));
+          gt[c] = fma(th, z, fma(sc1, zbt, gt[c]));
+          gb[c] += z;
+        }
       }
     }
-    double* comb = S0;                                       // staging slab is free now
-    if (half == 1 && u < W) { comb[u] = gx; comb[128 + u] = gt; comb[256 + u] = gb; }
+    double* comb = S0;                                       // [warp][3][128]
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int u = lane + 32 * c;
+      comb[(warp * 3 + 0) * 128 + u] = gx[c];
+      comb[(warp * 3 + 1) * 128 + u] = gt[c];
+      comb[(warp * 3 + 2) * 128 + u] = gb[c];
+    }
     __syncthreads();
-    if (half == 0 && u < W) {
-      outp[woff(0) + u] = gx + comb[u];
-      outp[woff(0) + W + u] = gt + comb[128 + u];
-      outp[boff(0) + u] = gb + comb[256 + u];
+    for (int i = tid; i < 3 * W; i += THREADS) {
+      const int which = i / W, u = i - which * W;
+      double sum = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < WARPS; w8++) sum += comb[(w8 * 3 + which) * 128 + u];
+      outp[(which == 0 ? woff(0) : (which == 1 ? woff(0) + W : boff(0))) + u] = sum;
     }
   }
 }
