@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libpinn_b200.so")
 SOURCES = ["pinn_api.cu"]
-HEADERS = ["pinn_common.cuh", "burgers_fused.cuh", "burgers_fused_v2.cuh", "nls_fused.cuh", "optim_kernels.cuh",
+HEADERS = ["pinn_common.cuh", "burgers_fused.cuh", "burgers_fused_v2.cuh", "nls_fused.cuh", "generic_fused.cuh", "optim_kernels.cuh",
            os.path.join("..", "..", "include", "pinn_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -1,0 +1,311 @@
+// Generic fused PINN loss + gradient kernel: ANY tanh MLP [2, w_1, ..., w_k, out] (widths <= 128, <= 15 Dense layers),
+// all three PDE heads (Burgers inference / identification: out = 1; Schrodinger: out = 2), fp64, sm_100a.
+//
+// Purpose: hp["layers"] is user-configurable in the reference (1d-burgers/inf_cont_burgers.py:23-34); the DMMA kernels
+// (burgers_fused_v2.cuh, nls_fused.cuh) are specialised for the two BASELINE nets.  This kernel keeps the path a drop-in
+// for every other layer list, and doubles as an independent on-GPU cross-check of the specialised kernels
+// (PINN_FORCE_GENERIC=1).  It is a correctness-first fallback: plain DFMA, one launch, persistent CTAs.
+//
+// Structure (same mathematics as the specialised kernels: forward Taylor streams h, h_x, h_t, h_xx and the hand-derived
+// reverse sweep): a CTA owns a contiguous block of points and walks the network layer by layer;
+// activations live in a per-CTA global scratch.
+//   F_l   thread per (point, unit): 4 stream dot products over the previous layer (weights through the read-only path,
+//         activations broadcast within the warp), tanh + Taylor epilogue
+//   HEAD  linear head, PDE residual / data / boundary terms, loss parts, seeds
+//   B_l   Z-bar (division-free backward formula) -> weight gradient (thread per weight entry, loop over the CTA's points;
+//         written once per CTA) -> input adjoint (thread per (point, unit))
+#pragma once
+#include "optim_kernels.cuh"
+
+namespace pinn {
+namespace generic {
+
+constexpr int THREADS = 256;
+constexpr int MAXOUT = 2;
+
+struct Args {
+  const double* w;
+  NetDesc nd;
+  const double* x;
+  const double* t;
+  const double* tgt;          // data targets [n_d][out]
+  long long n_total;
+  int pde;                    // PINN_BURGERS_INF / PINN_BURGERS_IDE / PINN_NLS_INF
+  // Burgers: points [d0, d0+n_d) carry the data term, [c0, c0+n_c) the residual term
+  long long c0, n_c, d0, n_d;
+  double wf, wd, nu;
+  // NLS: [ic n0 | pad to n0p | (lb,ub) pairs 2 nb | collocation]
+  long long n0, n0p, nb;
+  double w0, wb;
+  int p_net;                  // network parameters (identification: lambdas at p_net, p_net+1)
+  double* scrH;               // [grid][sum_l 4*pts*w_l]   outputs of the hidden layers
+  double* scrA;               // [grid][2][4*pts*maxw]     adjoints / Z-bar
+  double* scrS;               // [grid][2][pts*4*out]      head outputs, seeds
+  long long h_per_cta, a_per_cta;
+  int pts, maxw;
+  double* partials;           // [grid][pstride]: [grad p_net | dl1 dl2 - part0 part1 part2]
+  int pstride;
+  const int* run_flag;
+};
+
+__device__ __forceinline__ void block_reduce_store(double v, double* red, double* dst) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < THREADS / 32; i++) s += red[i];
+    *dst = s;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
+  __shared__ double red[THREADS / 32];
+  if (p.run_flag && *p.run_flag != 0) return;
+  const int tid = threadIdx.x;
+  const NetDesc& nd = p.nd;
+  const int L = nd.n_layers;                 // Dense layers; hidden 0..L-2, head L-1
+  const int out = nd.dims[L];
+  const int pts = p.pts;
+  const long long base = (long long)blockIdx.x * pts;
+  const long long navail = p.n_total - base;
+  const int npts = navail <= 0 ? 0 : (navail < pts ? (int)navail : pts);
+  double* Hs = p.scrH + (size_t)blockIdx.x * p.h_per_cta;
+  double* A0 = p.scrA + (size_t)blockIdx.x * 2 * p.a_per_cta;
+  double* A1 = A0 + p.a_per_cta;
+  double* OUTV = p.scrS + (size_t)blockIdx.x * 2 * pts * 4 * MAXOUT;
+  double* SEED = OUTV + (size_t)pts * 4 * MAXOUT;
+  double* outp = p.partials + (size_t)blockIdx.x * p.pstride;
+  const double sc0 = 2.0 / nd.dx0, sc1 = 2.0 / nd.dx1;
+  const bool ide = p.pde == 1;
+  const double l1 = ide ? p.w[p.p_net] : 1.0;
+  const double kap = ide ? exp(p.w[p.p_net + 1]) : p.nu;
+
+  // layer-l output slab: [4][pts][w_l]
+  size_t hoff[MAXL];
+  {
+    size_t o = 0;
+    for (int l = 0; l < L - 1; l++) { hoff[l] = o; o += (size_t)4 * pts * nd.dims[l + 1]; }
+  }
+
+  // ======================================= forward: hidden layers =======================================
+  for (int l = 0; l < L - 1; l++) {
+    const int fi = nd.dims[l], fo = nd.dims[l + 1];
+    const double* Wl = p.w + nd.woff[l];
+    const double* bl = p.w + nd.boff[l];
+    const double* Hp = l > 0 ? Hs + hoff[l - 1] : nullptr;
+    double* Ho = Hs + hoff[l];
+    const size_t sp = (size_t)pts * fi, so = (size_t)pts * fo;
+    for (int idx = tid; idx < npts * fo; idx += THREADS) {
+      const int pt = idx / fo, j = idx - pt * fo;
+      double z = __ldg(bl + j), zx = 0.0, zt = 0.0, zxx = 0.0;
+      if (l == 0) {
+        const double xh = 2.0 * (__ldg(p.x + base + pt) - nd.lb0) / nd.dx0 - 1.0;   // utils/neuralnetwork.py:29-30
+        const double th = 2.0 * (__ldg(p.t + base + pt) - nd.lb1) / nd.dx1 - 1.0;
+        const double w0 = __ldg(Wl + j), w1 = __ldg(Wl + fo + j);
+        z = fma(xh, w0, fma(th, w1, z));
+        zx = sc0 * w0;
+        zt = sc1 * w1;
+      } else {
+        const double* h0 = Hp + (size_t)pt * fi;
+        for (int i = 0; i < fi; i++) {
+          const double wv = __ldg(Wl + (size_t)i * fo + j);
+          z = fma(h0[i], wv, z);
+          zx = fma(h0[sp + i], wv, zx);
+          zt = fma(h0[2 * sp + i], wv, zt);
+          zxx = fma(h0[3 * sp + i], wv, zxx);
+        }
+      }
+      const double a = tanh_fast(z);
+      const double s = fma(-a, a, 1.0);
+      double* o = Ho + (size_t)pt * fo + j;
+      o[0] = a;
+      o[so] = s * zx;
+      o[2 * so] = s * zt;
+      o[3 * so] = s * fma(-2.0 * a * zx, zx, zxx);
+    }
+    __syncthreads();
+  }
+
+  // ======================================= head + PDE terms =======================================
+  const int fl = nd.dims[L - 1];                         // width of the last hidden layer
+  const double* Hl = Hs + hoff[L - 2];
+  const size_t sl = (size_t)pts * fl;
+  const double* Wh = p.w + nd.woff[L - 1];
+  for (int idx = tid; idx < npts * 4 * out; idx += THREADS) {
+    const int pt = idx / (4 * out), so_ = idx - pt * 4 * out, s = so_ / out, o = so_ - s * out;
+    const double* h = Hl + s * sl + (size_t)pt * fl;
+    double acc = s == 0 ? __ldg(p.w + nd.boff[L - 1] + o) : 0.0;
+    for (int i = 0; i < fl; i++) acc = fma(h[i], __ldg(Wh + (size_t)i * out + o), acc);
+    OUTV[idx] = acc;
+  }
+  __syncthreads();
+  double part0 = 0.0, part1 = 0.0, part2 = 0.0, gl1 = 0.0, gl2 = 0.0;
+  for (int pt = tid; pt < npts; pt += THREADS) {
+    const long long gp = base + pt;
+    const double* o = OUTV + (size_t)pt * 4 * out;
+    double sd[4 * MAXOUT];
+#pragma unroll
+    for (int c = 0; c < 4 * MAXOUT; c++) sd[c] = 0.0;
+    if (p.pde != 2) {
+      // Burgers (inf_cont_burgers.py:59-90 / ide_cont_burgers.py:56-91): outputs o = [u, u_x, u_t, u_xx]
+      const double u = o[0], ux = o[1], ut = o[2], uxx = o[3];
+      const double wf = (gp >= p.c0 && gp < p.c0 + p.n_c) ? p.wf : 0.0;
+      const bool has_d = gp >= p.d0 && gp < p.d0 + p.n_d;
+      const double wd = has_d ? p.wd : 0.0;
+      const double r = has_d ? u - __ldg(p.tgt + (gp - p.d0)) : 0.0;
+      const double f = ut + l1 * u * ux - kap * uxx;
+      const double c = 2.0 * wf * f;
+      sd[0] = fma(c * l1, ux, 2.0 * wd * r);
+      sd[1] = c * l1 * u;
+      sd[2] = c;
+      sd[3] = -c * kap;
+      part0 = fma(wd * r, r, part0);
+      part2 = fma(wf * f, f, part2);
+      gl1 = fma(c * u, ux, gl1);
+      gl2 = fma(-c * kap, uxx, gl2);
+    } else {
+      // Schrodinger (inf_cont_schrodinger.py:79-129): o = [u, v, u_x, v_x, u_t, v_t, u_xx, v_xx]
+      if (gp < p.n0) {
+        const double ru = o[0] - __ldg(p.tgt + 2 * gp), rv = o[1] - __ldg(p.tgt + 2 * gp + 1);
+        part0 += p.w0 * (ru * ru + rv * rv);
+        sd[0] = 2.0 * p.w0 * ru; sd[1] = 2.0 * p.w0 * rv;
+      } else if (gp < p.n0p) {
+        // alignment padding: inert
+      } else if (gp < p.n0p + 2 * p.nb) {
+        const bool is_lb = ((gp - p.n0p) & 1) == 0;
+        const double* op = is_lb ? o + 8 : o - 8;
+        const double sgn = is_lb ? 1.0 : -1.0;
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const double d = sgn * (o[c] - op[c]);
+          acc = fma(d, d, acc);
+          sd[c] = sgn * 2.0 * p.wb * d;
+        }
+        if (is_lb) part1 += p.wb * acc;
+      } else {
+        const double u = o[0], v = o[1], ut = o[4], vt = o[5], uxx = o[6], vxx = o[7];
+        const double h2 = u * u + v * v;
+        const double fu = ut + 0.5 * vxx + h2 * v;
+        const double fv = vt - 0.5 * uxx - h2 * u;
+        part2 += p.wf * (fu * fu + fv * fv);
+        const double cu = 2.0 * p.wf * fu, cv = 2.0 * p.wf * fv;
+        sd[0] = cu * 2.0 * u * v - cv * (3.0 * u * u + v * v);
+        sd[1] = cu * (u * u + 3.0 * v * v) - cv * 2.0 * u * v;
+        sd[4] = cu; sd[5] = cv;
+        sd[6] = -0.5 * cv; sd[7] = 0.5 * cu;
+      }
+    }
+    for (int c = 0; c < 4 * out; c++) SEED[(size_t)pt * 4 * out + c] = sd[c];
+  }
+  block_reduce_store(part0, red, outp + p.p_net + 3);
+  block_reduce_store(part1, red, outp + p.p_net + 4);
+  block_reduce_store(part2, red, outp + p.p_net + 5);
+  block_reduce_store(gl1, red, outp + p.p_net + 0);
+  block_reduce_store(gl2, red, outp + p.p_net + 1);
+  __syncthreads();
+
+  // ======================================= head: gradient and input adjoint =======================================
+  for (int e = tid; e < (fl + 1) * out; e += THREADS) {
+    const int i = e / out, o = e - i * out;
+    double acc = 0.0;
+    for (int pt = 0; pt < npts; pt++) {
+      const double* sd = SEED + (size_t)pt * 4 * out;
+      if (i < fl) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) acc = fma(Hl[s * sl + (size_t)pt * fl + i], sd[s * out + o], acc);
+      } else {
+        acc += sd[o];
+      }
+    }
+    if (i < fl) outp[nd.woff[L - 1] + i * out + o] = acc;
+    else outp[nd.boff[L - 1] + o] = acc;
+  }
+  double* Acur = A0;      // adjoint of the current layer's outputs: [4][pts][w]
+  double* Aoth = A1;
+  for (int idx = tid; idx < npts * fl; idx += THREADS) {
+    const int pt = idx / fl, i = idx - pt * fl;
+    const double* sd = SEED + (size_t)pt * 4 * out;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      double acc = 0.0;
+      for (int o = 0; o < out; o++) acc = fma(sd[s * out + o], __ldg(Wh + (size_t)i * out + o), acc);
+      Acur[s * sl + (size_t)pt * fl + i] = acc;
+    }
+  }
+  __syncthreads();
+
+  // ======================================= backward: hidden layers =======================================
+  for (int l = L - 2; l >= 0; l--) {
+    const int fi = nd.dims[l], fo = nd.dims[l + 1];
+    const double* Wl = p.w + nd.woff[l];
+    const double* Ho = Hs + hoff[l];
+    const double* Hp = l > 0 ? Hs + hoff[l - 1] : nullptr;
+    const size_t so = (size_t)pts * fo, sp = (size_t)pts * fi;
+    // (1) Z-bar
+    for (int idx = tid; idx < npts * fo; idx += THREADS) {
+      const size_t q = idx;                               // == pt*fo + j
+      const double a = Ho[q], ax = Ho[so + q], at = Ho[2 * so + q], axx = Ho[3 * so + q];
+      const double B0 = Acur[q], Bx = Acur[so + q], Bt = Acur[2 * so + q], Bxx = Acur[3 * so + q];
+      const double s = fma(-a, a, 1.0);
+      const double u1 = fma(ax, Bx, at * Bt);
+      const double u2 = fma(a, axx, ax * ax);
+      double z = fma(-2.0 * a, u1, s * B0);
+      z = fma(-2.0 * Bxx, u2, z);
+      Aoth[q] = z;
+      Aoth[so + q] = fma(-4.0 * a * ax, Bxx, s * Bx);
+      Aoth[2 * so + q] = s * Bt;
+      Aoth[3 * so + q] = s * Bxx;
+    }
+    __syncthreads();
+    // (2) weight gradient: thread per entry (i, j), i == fi is the bias
+    for (int e = tid; e < (fi + 1) * fo; e += THREADS) {
+      const int i = e / fo, j = e - i * fo;
+      double acc = 0.0;
+      for (int pt = 0; pt < npts; pt++) {
+        const double* z = Aoth + (size_t)pt * fo + j;
+        if (i == fi) {
+          acc += z[0];
+        } else if (l == 0) {
+          const double xh = 2.0 * (__ldg(p.x + base + pt) - nd.lb0) / nd.dx0 - 1.0;
+          const double th = 2.0 * (__ldg(p.t + base + pt) - nd.lb1) / nd.dx1 - 1.0;
+          acc += i == 0 ? fma(xh, z[0], sc0 * z[so]) : fma(th, z[0], sc1 * z[2 * so]);
+        } else {
+          const double* h = Hp + (size_t)pt * fi + i;
+          acc = fma(h[0], z[0], acc);
+          acc = fma(h[sp], z[so], acc);
+          acc = fma(h[2 * sp], z[2 * so], acc);
+          acc = fma(h[3 * sp], z[3 * so], acc);
+        }
+      }
+      if (i < fi) outp[nd.woff[l] + i * fo + j] = acc;
+      else outp[nd.boff[l] + j] = acc;
+    }
+    // (3) input adjoint (overwrites the adjoint of this layer's outputs, which is no longer needed)
+    __syncthreads();
+    if (l > 0) {
+      for (int idx = tid; idx < npts * fi; idx += THREADS) {
+        const int pt = idx / fi, i = idx - pt * fi;
+        const double* z = Aoth + (size_t)pt * fo;
+        double b0 = 0.0, bx = 0.0, bt = 0.0, bxx = 0.0;
+        for (int j = 0; j < fo; j++) {
+          const double wv = __ldg(Wl + (size_t)i * fo + j);
+          b0 = fma(z[j], wv, b0);
+          bx = fma(z[so + j], wv, bx);
+          bt = fma(z[2 * so + j], wv, bt);
+          bxx = fma(z[3 * so + j], wv, bxx);
+        }
+        double* a = Acur + (size_t)pt * fi + i;
+        a[0] = b0; a[sp] = bx; a[2 * sp] = bt; a[3 * sp] = bxx;
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) outp[p.p_net + 2] = 0.0;
+}
+
+}  // namespace generic
+}  // namespace pinn

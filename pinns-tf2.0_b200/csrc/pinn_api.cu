@@ -15,6 +15,7 @@
 #include "burgers_fused_v2.cuh"
 #include "nls_fused.cuh"
 #include "optim_kernels.cuh"
+#include "generic_fused.cuh"
 
 namespace {
 
@@ -76,6 +77,9 @@ struct pinn_handle {
   long long launches = 0;
   pinn::ReduceMap last_map{};       // reduction map / grid / stride of the most recent fused launch
   int last_grid = 0, last_stride = 0;
+  int kernel_kind = 0;              // 0: specialised Burgers DMMA kernel, 1: specialised NLS DMMA kernel, 2: generic
+  double *d_gH = nullptr, *d_gA = nullptr, *d_gS = nullptr;   // generic kernel scratch
+  long long g_pts = 0;
   int burgers_kernel = 2;           // 2: warp-specialised (default); 1: single-role v1 (PINN_BURGERS_KERNEL=v1)
 
   // parameters and optimiser state
@@ -137,6 +141,7 @@ bool is_nls_net(const std::vector<int>& L) {
 
 int nls_upload_points(pinn_t* h);
 int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only);
+int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only);
 
 pinn::NetDesc net_desc(const pinn_t* h) {
   pinn::NetDesc nd{};
@@ -191,7 +196,10 @@ int ensure_points(pinn_t* h, long long need_d, long long need_c) {
 
 int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
   const bool skip_reduce = fused_only;
-  if (h->pde == PINN_BURGERS_INF || h->pde == PINN_BURGERS_IDE) {
+  if (h->kernel_kind == 2) {
+    if (generic_launch_eval(h, run_flag, fused_only)) return -1;
+    if (fused_only) return 0;
+  } else if (h->pde == PINN_BURGERS_INF || h->pde == PINN_BURGERS_IDE) {
     namespace B = pinn::burgers;
     const bool ide = h->pde == PINN_BURGERS_IDE;
     const long long n_total = ide ? h->n_d : h->n_d + h->n_c;
@@ -243,6 +251,66 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
     int rc = g_nccl.AllReduce(h->d_R, h->d_R, (size_t)h->P + 3, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
     if (rc != 0) return fail(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
   }
+  return 0;
+}
+
+int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
+  namespace G = pinn::generic;
+  const bool nls = h->pde == PINN_NLS_INF, ide = h->pde == PINN_BURGERS_IDE;
+  const long long n_total = nls ? h->n_aux + h->n_c : (ide ? h->n_d : h->n_d + h->n_c);
+  if (n_total <= 0) return fail("no points set (pinn_set_collocation / pinn_set_data)");
+  const int grid = h->n_cta;
+  const long long per = (n_total + grid - 1) / grid;
+  const long long pts = (per + 15) / 16 * 16;
+  pinn::NetDesc nd = net_desc(h);
+  int maxw = 0; long long hsum = 0;
+  for (int l = 0; l < nd.n_layers - 1; l++) { hsum += 4 * pts * nd.dims[l + 1]; if (nd.dims[l + 1] > maxw) maxw = nd.dims[l + 1]; }
+  const long long a_per = 4 * pts * maxw;
+  if (pts > h->g_pts) {
+    if (h->d_gH) cudaFree(h->d_gH);
+    if (h->d_gA) cudaFree(h->d_gA);
+    if (h->d_gS) cudaFree(h->d_gS);
+    h->d_gH = h->d_gA = h->d_gS = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&h->d_gH, (size_t)grid * hsum * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_gA, (size_t)grid * 2 * a_per * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_gS, (size_t)grid * 2 * pts * 4 * G::MAXOUT * 8));
+    h->g_pts = pts;
+  }
+  G::Args a{};
+  a.w = h->d_w; a.nd = nd;
+  const long long n_front = nls ? h->n_aux : h->n_d;
+  a.x = h->d_x + (h->dcap - n_front); a.t = h->d_t + (h->dcap - n_front); a.tgt = h->d_u;
+  a.n_total = n_total; a.pde = h->pde;
+  a.c0 = ide ? 0 : h->n_d; a.n_c = ide ? h->n_d : h->n_c; a.d0 = 0; a.n_d = h->n_d;
+  const long long nfg = ide ? h->n_d : h->n_c_global;
+  a.wf = nfg > 0 ? 1.0 / (double)nfg : 0.0;
+  a.wd = h->n_d > 0 ? h->data_weight / (double)h->n_d : 0.0;
+  a.nu = h->nu;
+  a.n0 = h->n_d; a.n0p = (h->n_d + 1) & ~1LL; a.nb = h->n_b;
+  a.w0 = h->n_d > 0 ? h->data_weight / (double)h->n_d : 0.0;
+  a.wb = h->n_b > 0 ? h->data_weight / (double)h->n_b : 0.0;
+  if (nls && h->n_aux != a.n0p + 2 * a.nb) return fail("internal: NLS auxiliary block out of date");
+  a.p_net = h->P_net;
+  a.scrH = h->d_gH; a.scrA = h->d_gA; a.scrS = h->d_gS;
+  a.h_per_cta = hsum; a.a_per_cta = a_per;
+  a.pts = (int)pts; a.maxw = maxw;
+  a.partials = h->d_partials; a.pstride = h->pstride; a.run_flag = run_flag;
+  G::fused_loss_grad<<<grid, G::THREADS, 0, h->stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  pinn::ReduceMap map{};
+  map.p_net = h->P_net;
+  map.n_extra = 0;
+  if (ide) { map.extra_src[map.n_extra++] = h->P_net + 0; map.extra_src[map.n_extra++] = h->P_net + 1; }
+  map.extra_src[map.n_extra++] = h->P_net + 3;
+  map.extra_src[map.n_extra++] = h->P_net + 4;
+  map.extra_src[map.n_extra++] = h->P_net + 5;
+  map.n_out = map.p_net + map.n_extra;
+  h->last_map = map; h->last_grid = grid; h->last_stride = h->pstride;
+  if (fused_only) return 0;
+  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, h->pstride, h->d_R, map, run_flag);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
   return 0;
 }
 
@@ -350,11 +418,18 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
   if (h->layers[0] != 2) { delete h; return fail("pinn_create: input dimension must be 2 (x,t)"); }
   h->lb[0] = lb[0]; h->lb[1] = lb[1]; h->ub[0] = ub[0]; h->ub[1] = ub[1];
   if (!(ub[0] > lb[0]) || !(ub[1] > lb[1])) { delete h; return fail("pinn_create: need ub > lb"); }
-  bool ok_net = (pde_id == PINN_NLS_INF) ? is_nls_net(h->layers) : is_burgers_net(h->layers);
-  if (!ok_net) {
+  const int want_out = pde_id == PINN_NLS_INF ? 2 : 1;
+  if (h->layers.back() != want_out) {
     delete h;
-    return fail(pde_id == PINN_NLS_INF ? "pinn_create: the fused NLS kernel is specialised for layers [2,100,100,100,100,2]"
-                                        : "pinn_create: the fused Burgers kernel is specialised for layers [2,20x8,1]");
+    return fail(pde_id == PINN_NLS_INF ? "pinn_create: the Schrodinger problem needs 2 network outputs (u, v)"
+                                        : "pinn_create: the Burgers problems need 1 network output (u)");
+  }
+  {
+    // specialised DMMA kernels for the two BASELINE nets, generic DFMA kernel for any other layer list
+    const char* fg = getenv("PINN_FORCE_GENERIC");
+    const bool force = fg && fg[0] == '1';
+    const bool special = (pde_id == PINN_NLS_INF) ? is_nls_net(h->layers) : is_burgers_net(h->layers);
+    h->kernel_kind = (special && !force) ? (pde_id == PINN_NLS_INF ? 1 : 0) : 2;
   }
   h->P_net = 0;
   for (int l = 0; l + 1 < n_layers; l++) h->P_net += layers[l] * layers[l + 1] + layers[l + 1];
@@ -398,7 +473,10 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
   CREATE_TRY(cudaMemset(h->d_loss_ring, 0, LOSS_RING * 8));
   CREATE_TRY(cudaMalloc((void**)&h->d_lb, sizeof(pinn::LbfgsState)));
   CREATE_TRY(cudaMemset(h->d_lb, 0, sizeof(pinn::LbfgsState)));
-  if (pde_id == PINN_NLS_INF) {
+  if (h->kernel_kind == 2) {
+    h->n_cta = 2 * h->n_sm;
+    h->pstride = ((h->P_net + 8 + 15) / 16) * 16;
+  } else if (pde_id == PINN_NLS_INF) {
     h->n_cta = pinn::nls::grid_size(h->n_sm);
     h->pstride = pinn::nls::PSTRIDE;
     CREATE_TRY(cudaFuncSetAttribute(pinn::nls::fused_loss_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, pinn::nls::SMEM_BYTES));
@@ -430,7 +508,7 @@ int pinn_destroy(pinn_t* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  double* bufs[] = {h->d_w, h->d_R, h->d_partials, h->d_m, h->d_v, h->d_loss_ring, h->d_x, h->d_t, h->d_u, h->d_scrH, h->d_scrA, h->d_scrS, h->d_gold,
+  double* bufs[] = {h->d_w, h->d_R, h->d_partials, h->d_m, h->d_v, h->d_loss_ring, h->d_x, h->d_t, h->d_u, h->d_scrH, h->d_scrA, h->d_scrS, h->d_gH, h->d_gA, h->d_gS, h->d_gold,
                     h->d_d, h->d_S, h->d_Y, h->d_xfinal, h->d_fhist, h->d_px, h->d_pout};
   for (double* b : bufs) if (b) cudaFree(b);
   if (h->d_step) cudaFree(h->d_step);
@@ -846,7 +924,10 @@ int pinn_kernel_info(pinn_t* h, char* buf, int buflen) {
   if (!h || !buf || buflen < 1) return fail("bad arguments");
   cudaFuncAttributes fa{};
   int smem = 0, threads = 0;
-  if (h->pde == PINN_NLS_INF) {
+  if (h->kernel_kind == 2) {
+    CUDA_TRY(cudaFuncGetAttributes(&fa, pinn::generic::fused_loss_grad));
+    smem = 0; threads = pinn::generic::THREADS;
+  } else if (h->pde == PINN_NLS_INF) {
     CUDA_TRY(cudaFuncGetAttributes(&fa, pinn::nls::fused_loss_grad));
     smem = pinn::nls::SMEM_BYTES; threads = pinn::nls::THREADS;
   } else {

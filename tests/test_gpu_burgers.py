@@ -160,8 +160,12 @@ def test_full_size_properties(cabi):
 
 
 def test_errors_are_reported_not_thrown(cabi):
-    with pytest.raises(cabi.PinnError, match="specialised"):
-        cabi.Pinn(cabi.BURGERS_INF, [2, 10, 1], [-1, 0], [1, 1])
+    with pytest.raises(cabi.PinnError, match="1 network output"):
+        cabi.Pinn(cabi.BURGERS_INF, [2, 10, 2], [-1, 0], [1, 1])
+    with pytest.raises(cabi.PinnError, match="width out of range"):
+        cabi.Pinn(cabi.BURGERS_INF, [2, 300, 1], [-1, 0], [1, 1])
+    with pytest.raises(cabi.PinnError, match="input dimension"):
+        cabi.Pinn(cabi.BURGERS_INF, [3, 10, 1], [-1, 0], [1, 1])
     p = cabi.Pinn(cabi.BURGERS_INF, LAYERS, [-1, 0], [1, 1])
     with pytest.raises(cabi.PinnError, match="expected 3021"):
         p.set_weights(np.zeros(5))
