@@ -71,6 +71,11 @@ int pinn_set_pde_params(pinn_t* h, const double* p, int n);
  * n_global = N_f over all ranks (the MSE_f denominator); pass n when world == 1. */
 int pinn_set_collocation(pinn_t* h, const double* x, const double* t, int64_t n, int64_t n_global);
 
+/* Zero-copy variant for per-step resampling (the e2e path of bench.py): x, t must be PINNED host memory
+ * (pinn_host_alloc); nothing is copied -- the fused kernel reads the batch straight over PCIe (prefetched one tile ahead).
+ * The buffers must stay valid and unchanged until the next synchronising call.  Burgers inference kernel only. */
+int pinn_set_collocation_mapped(pinn_t* h, const double* x_pinned, const double* t_pinned, int64_t n, int64_t n_global);
+
 /* Data term: X_u,u of fit(X_u,u) (utils/neuralnetwork.py:138-146).  X is (n,in_dim) row-major; in_dim==1
  * reproduces the Lambda's broadcast of a (N,1) input to (x, t:=x) (quirk Q1, inf_cont_schrodinger.py:164).
  * u is (n,out_dim).  For BURGERS_IDE these are also the residual points (ide_cont_burgers.py:88-91,116-118).

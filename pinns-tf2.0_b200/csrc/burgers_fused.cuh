@@ -57,6 +57,8 @@ struct Args {
   const double* x;        // n_total
   const double* t;        // n_total
   const double* utgt;     // n_d targets (point d0+i <-> utgt[i])
+  const double* xc;       // optional: collocation block read from here (xc[pt-c0]) instead of x[pt] -- e.g. pinned
+  const double* tc;       //           host memory mapped into the device address space (zero-copy e2e path); v2 only
   long long n_total;      // points in the set
   long long c0, n_c;      // points [c0, c0+n_c) carry the residual term with weight wf
   long long d0, n_d;      // points [d0, d0+n_d) carry the data term with weight wd

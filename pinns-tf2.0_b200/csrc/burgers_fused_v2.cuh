@@ -51,6 +51,9 @@ constexpr int ROUND = CHAINS * TILE;      // 32 points per CTA round
 #ifndef PINN_PHASE_OFFSET
 #define PINN_PHASE_OFFSET 0
 #endif
+#ifndef PINN_XT_PREFETCH
+#define PINN_XT_PREFETCH 1
+#endif
 #ifndef PINN_WG_ROLLED
 #define PINN_WG_ROLLED 0
 #endif
@@ -343,14 +346,29 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     for (int nt = 0; nt < 3; nt++) g8[nt][0] = g8[nt][1] = 0.0;
     const int pg = prow(g);
     if (PINN_PHASE_OFFSET && c >= 2) mbar_wait(bars + 1 + 2 * CHAINS * RING, 0);   // start half a tile behind half A
+    // coordinates of this lane's point in tile `it`; the next tile's pair is prefetched one tile ahead so that neither
+    // the L2/HBM latency nor (zero-copy mode: p.xc in pinned host memory) the PCIe latency is exposed
+    auto load_xt = [&](int it, double& xo, double& to) {
+      const long long rnd = blockIdx.x + (long long)it * gridDim.x;
+      long long pt = rnd * ROUND + c * TILE + g;
+      if (pt >= p.n_total) pt = p.n_total - 1;
+      if (p.xc && pt >= p.c0 && pt < p.c0 + p.n_c) {
+        xo = __ldg(p.xc + (pt - p.c0)); to = __ldg(p.tc + (pt - p.c0));
+      } else {
+        xo = __ldg(p.x + pt); to = __ldg(p.t + pt);
+      }
+    };
+    double xr_next = 0.0, tr_next = 0.0;
+    if (PINN_XT_PREFETCH && my_rounds > 0) load_xt(0, xr_next, tr_next);
 
 #pragma unroll 1
     for (int it = 0; it < my_rounds; it++) {
       const long long rnd = blockIdx.x + (long long)it * gridDim.x;
       const long long pt = rnd * ROUND + c * TILE + g;
       const bool in_set = pt < p.n_total;
-      const long long pc = in_set ? pt : p.n_total - 1;
-      const double xr = __ldg(p.x + pc), tr = __ldg(p.t + pc);
+      if (!PINN_XT_PREFETCH) load_xt(it, xr_next, tr_next);
+      const double xr = xr_next, tr = tr_next;
+      if (PINN_XT_PREFETCH && it + 1 < my_rounds) load_xt(it + 1, xr_next, tr_next);
       const double wf = (in_set && pt >= p.c0 && pt < p.c0 + p.n_c) ? p.wf : 0.0;
       const bool has_d = in_set && pt >= p.d0 && pt < p.d0 + p.n_d;
       const double wd = has_d ? p.wd : 0.0;

@@ -103,6 +103,7 @@ struct pinn_handle {
   double data_weight = 1.0;
   std::vector<double> h_tb;                 // NLS boundary times
   std::vector<double> h_icx, h_ict;         // NLS initial-condition points (host copy for re-assembly)
+  const double *map_x = nullptr, *map_t = nullptr;   // zero-copy collocation block (device aliases of pinned host memory)
   long long n_aux = 0;                      // points stored in the data region (Burgers: n_d; NLS: n0p + 2 n_b)
   double *d_scrH = nullptr, *d_scrA = nullptr, *d_scrS = nullptr;   // NLS activation / adjoint / seed scratch
   int scr_pts = 0;
@@ -207,6 +208,8 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
     B::Args a{};
     a.w = h->d_w;
     a.x = h->d_x + (h->dcap - h->n_d); a.t = h->d_t + (h->dcap - h->n_d); a.utgt = h->d_u;
+    a.xc = h->map_x; a.tc = h->map_t;
+    if (h->map_x && h->burgers_kernel != 2) return fail("zero-copy collocation needs the v2 Burgers kernel");
     a.n_total = n_total;
     a.c0 = ide ? 0 : h->n_d;
     a.n_c = ide ? h->n_d : h->n_c;
@@ -550,6 +553,26 @@ int pinn_set_collocation(pinn_t* h, const double* x, const double* t, int64_t n,
     CUDA_TRY(cudaStreamSynchronize(h->stream));   // the buffers are only borrowed for the call
   }
   h->n_c = n; h->n_c_global = n_global;
+  h->map_x = h->map_t = nullptr;
+  return 0;
+}
+
+int pinn_set_collocation_mapped(pinn_t* h, const double* x_pinned, const double* t_pinned, int64_t n, int64_t n_global) {
+  if (!h) return fail("null handle");
+  if (h->kernel_kind != 0 || h->pde != PINN_BURGERS_INF)
+    return fail("pinn_set_collocation_mapped: zero-copy collocation is implemented for the fused Burgers inference kernel only");
+  if (n <= 0 || !x_pinned || !t_pinned || n_global < n) return fail("pinn_set_collocation_mapped: bad arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  void *dx = nullptr, *dt = nullptr;
+  if (cudaHostGetDevicePointer(&dx, (void*)x_pinned, 0) != cudaSuccess || cudaHostGetDevicePointer(&dt, (void*)t_pinned, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return fail("pinn_set_collocation_mapped: the buffers must be pinned host memory (pinn_host_alloc / cudaHostAlloc)");
+  }
+  if (ensure_points(h, h->n_aux, 0)) return -1;
+  // the kernel that is about to be enqueued reads the caller's buffers: they must stay valid and unchanged until the
+  // next synchronising call (pinn_adam_step with a loss pointer, pinn_loss_grad, pinn_sync)
+  h->map_x = (const double*)dx; h->map_t = (const double*)dt;
+  h->n_c = n; h->n_c_global = n_global;
   return 0;
 }
 
@@ -817,7 +840,9 @@ int pinn_residual(pinn_t* h, double* f_out) {
   if (n == 0) return 0;
   const long long off = ide ? h->dcap - h->n_d : h->dcap;
   std::vector<double> D(n * 4 * h->layers.back());
-  if (forward_generic(h, nullptr, h->d_x + off, h->d_t + off, n, 2, D.data(), 4)) return -1;
+  const double* rx = (!ide && h->map_x) ? h->map_x : h->d_x + off;
+  const double* rt = (!ide && h->map_t) ? h->map_t : h->d_t + off;
+  if (forward_generic(h, nullptr, rx, rt, n, 2, D.data(), 4)) return -1;
   if (h->pde == PINN_NLS_INF) {
     for (int64_t i = 0; i < n; i++) {
       const double* d = &D[i * 8];

@@ -30,6 +30,7 @@ SIGNATURES = {
     "pinn_num_params": (C.c_int64, [C.c_void_p]),
     "pinn_set_pde_params": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "pinn_set_collocation": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64]),
+    "pinn_set_collocation_mapped": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64]),
     "pinn_set_data": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int, _dp, C.c_int, C.c_double]),
     "pinn_set_boundary": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "pinn_set_weights": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
@@ -136,6 +137,10 @@ class Pinn(object):
     def set_collocation_ptr(self, x_ptr, t_ptr, n, n_global=None):
         """Raw-pointer variant (pinned host buffers from host_alloc)."""
         self._ck(self.lib.pinn_set_collocation(self.h, x_ptr, t_ptr, int(n), int(n_global or n)))
+
+    def set_collocation_mapped(self, x_ptr, t_ptr, n, n_global=None):
+        """Zero-copy: the fused kernel reads the (pinned) host buffers directly; keep them alive and unchanged."""
+        self._ck(self.lib.pinn_set_collocation_mapped(self.h, x_ptr, t_ptr, int(n), int(n_global or n)))
 
     def set_data(self, X, u, weight=1.0):
         X, u = _arr(X), _arr(u)

@@ -183,3 +183,34 @@ def test_device_tanh_accuracy(cabi):
     assert ulp.max() <= 4.0
     assert got[-3] == 1.0 and got[-2] == -1.0 and got[-4] == 0.0
     assert np.array_equal(cabi.device_tanh(-xs), -got)
+
+
+def test_zero_copy_collocation_matches_copied_and_sees_host_updates(cabi):
+    """pinn_set_collocation_mapped: the fused kernel reads the pinned batch over PCIe.  Same loss/gradient as the copied
+    path, and a batch rewritten in place by the host is what the next launch sees (no stale device-side caching)."""
+    import ctypes as C
+    g = load_golden("burgers_inf")
+    n = g["X_f"].shape[0]
+    hx, hx_ptr = cabi.host_alloc(n); ht, ht_ptr = cabi.host_alloc(n)
+    dp = C.POINTER(C.c_double)
+    hx[:] = g["X_f"][:, 0]; ht[:] = g["X_f"][:, 1]
+    p = make_inf(cabi, g)
+    l_copy, g_copy, _ = p.loss_grad()
+    p.set_collocation_mapped(C.cast(hx_ptr, dp), C.cast(ht_ptr, dp), n)
+    l_map, g_map, _ = p.loss_grad()
+    assert l_map == l_copy and np.array_equal(g_map, g_copy)
+    assert rel(p.residual(n), g["residual"]) < 1e-10
+    # new batch written in place
+    rng = np.random.default_rng(3)
+    Xn = g["lb"] + (g["ub"] - g["lb"]) * rng.random((n, 2))
+    hx[:] = Xn[:, 0]; ht[:] = Xn[:, 1]
+    p.set_collocation_mapped(C.cast(hx_ptr, dp), C.cast(ht_ptr, dp), n)
+    l_new, g_new, _ = p.loss_grad()
+    q = make_inf(cabi, g)
+    q.set_collocation(Xn[:, 0], Xn[:, 1])
+    l_ref, g_ref, _ = q.loss_grad()
+    assert l_new == l_ref and np.array_equal(g_new, g_ref) and l_new != l_copy
+    # switching back to the copied path drops the mapping
+    p.set_collocation(g["X_f"][:, 0], g["X_f"][:, 1])
+    assert p.loss_grad()[0] == l_copy
+    p.close(); q.close()
