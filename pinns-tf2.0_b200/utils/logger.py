@@ -1,60 +1,110 @@
-"""Progress logger with the reference's surface (utils/logger.py:7-60), TensorFlow-free.
+"""Progress reporting for the B200 PINN core.
 
-Same constructor (``Logger(hp)`` reading hp["log_frequency"]) and methods; the TF banner (logger.py:13-15) is
-replaced by the native library's version line.  The loss handed to ``log_train_epoch`` may be a lazy device
-scalar: it is only fetched (one 8-byte D2H) when a line is actually printed, i.e. every ``frequency`` epochs.
+Keeps the call surface the reference scripts use (``Logger(hp)``; ``log_train_start/opt/epoch/end``,
+``set_error_fn``, ``get_error_u``, ``get_elapsed``, ``get_epoch_duration`` -- utils/logger.py:7-60 of the reference) and
+the layout of the lines it prints, but is written for an asynchronous device-resident trainer:
+
+* the loss handed to ``log_train_epoch`` may be a lazy device scalar; it is converted to a float (one 8-byte read-back,
+  one host sync) only for the epochs that are actually printed, i.e. every ``hp["log_frequency"]`` steps;
+* under a multi-process launch (RANK/WORLD_SIZE in the environment) only rank 0 prints;
+* there is no TensorFlow banner -- the native library reports its own version instead.
 """
 import json
+import os
+import sys
 import time
-from datetime import datetime
+
+
+class _Stopwatch(object):
+    """Wall-clock bookkeeping: total time since construction and time since the previous lap."""
+
+    def __init__(self):
+        self.t0 = self.lap_t = time.time()
+
+    def total(self):
+        return time.time() - self.t0
+
+    def lap(self):
+        now = time.time()
+        dt, self.lap_t = now - self.lap_t, now
+        return dt
+
+
+def _mm_ss(seconds):
+    s = int(seconds)
+    return "%02d:%02d" % ((s // 60) % 60, s % 60)          # the reference wraps at one hour too (quirk Q5)
+
+
+def _ss_t(seconds):
+    return "%04.1f" % (seconds % 60.0)
 
 
 class Logger(object):
-    def __init__(self, hp):
-        print("Hyperparameters:")
-        print(json.dumps(hp, indent=2))
-        print()
+    def __init__(self, hp, stream=None):
+        self.frequency = hp["log_frequency"]
+        self.out = stream or sys.stdout
+        self.quiet = int(os.environ.get("RANK", "0")) != 0
+        self.watch = _Stopwatch()
+        self.error_fn = None
+        self.model = None
+        self._say("Hyperparameters:")
+        self._say(json.dumps(hp, indent=2))
+        self._say("")
+        self._say("PINN core: " + self._core_version())
+
+    # ------------------------------------------------------------------ helpers
+    def _say(self, text):
+        if not self.quiet:
+            print(text, file=self.out)
+
+    @staticmethod
+    def _core_version():
         try:
             import pinn_cabi
-            print("PINN core: {}".format(pinn_cabi.load().pinn_version().decode()))
-        except Exception as e:  # the banner must not hide the real error, which surfaces at first use
-            print("PINN core: unavailable ({})".format(e))
-        self.start_time = time.time()
-        self.prev_time = self.start_time
-        self.frequency = hp["log_frequency"]
+            return pinn_cabi.load().pinn_version().decode()
+        except Exception as exc:      # the banner must never hide the real error, which surfaces at first use
+            return "unavailable (%s)" % exc
+
+    # compatibility attributes of the reference class
+    @property
+    def start_time(self):
+        return self.watch.t0
+
+    @property
+    def prev_time(self):
+        return self.watch.lap_t
+
+    # ------------------------------------------------------------------ reference surface
+    def get_elapsed(self):
+        return _mm_ss(self.watch.total())
 
     def get_epoch_duration(self):
-        now = time.time()
-        edur = datetime.fromtimestamp(now - self.prev_time).strftime("%S.%f")[:-5]
-        self.prev_time = now
-        return edur
-
-    def get_elapsed(self):
-        return datetime.fromtimestamp(time.time() - self.start_time).strftime("%M:%S")
-
-    def get_error_u(self):
-        return self.error_fn()
+        return _ss_t(self.watch.lap())
 
     def set_error_fn(self, error_fn):
         self.error_fn = error_fn
 
-    def log_train_start(self, model, model_description=False):
-        print("\nTraining started")
-        print("================")
-        self.model = model
-        if model_description:
-            print(model.summary())
+    def get_error_u(self):
+        return self.error_fn()
 
-    def log_train_epoch(self, epoch, loss, custom="", is_iter=False):
-        if epoch % self.frequency == 0:
-            name = "nt_epoch" if is_iter else "tf_epoch"
-            print(f"{name} = {epoch:6d}  elapsed = {self.get_elapsed()} (+{self.get_epoch_duration()})  "
-                  f"loss = {float(loss):.4e}  " + custom)
+    def log_train_start(self, model, model_description=False):
+        self.model = model
+        self._say("\nTraining started")
+        self._say("================")
+        if model_description:
+            self._say(model.summary())
 
     def log_train_opt(self, name):
-        print(f"-- Starting {name} optimization --")
+        self._say("-- Starting %s optimization --" % name)
+
+    def log_train_epoch(self, epoch, loss, custom="", is_iter=False):
+        if epoch % self.frequency:
+            return                                          # nothing printed: the (possibly lazy) loss is never fetched
+        tag = "nt_epoch" if is_iter else "tf_epoch"
+        self._say("%s = %6d  elapsed = %s (+%s)  loss = %.4e  %s"
+                  % (tag, epoch, self.get_elapsed(), self.get_epoch_duration(), float(loss), custom))
 
     def log_train_end(self, epoch, custom=""):
-        print("==================")
-        print(f"Training finished (epoch {epoch}): duration = {self.get_elapsed()}  "
-              f"error = {self.get_error_u():.4e}  " + custom)
+        self._say("==================")
+        self._say("Training finished (epoch %s): duration = %s  error = %.4e  %s"
+                  % (epoch, self.get_elapsed(), self.get_error_u(), custom))
