@@ -35,7 +35,9 @@ typedef struct pinn_handle pinn_t;
 enum {
   PINN_BURGERS_INF = 0, /* 1d-burgers/inf_cont_burgers.py:48-98   f = u_t + u u_x - nu u_xx              */
   PINN_BURGERS_IDE = 1, /* 1d-burgers/ide_cont_burgers.py:47-118  f = u_t + l1 u u_x - exp(l2) u_xx      */
-  PINN_NLS_INF = 2      /* 1dcomplex-schrodinger/inf_cont_schrodinger.py:46-135                          */
+  PINN_NLS_INF = 2,     /* 1dcomplex-schrodinger/inf_cont_schrodinger.py:46-135                          */
+  PINN_BURGERS_DISC = 3 /* 1d-burgers/inf_disc_burgers.py:49-127  discrete time, q-stage implicit Runge-Kutta:
+                           net [1, ..., q+1] on x only; U_0 = U_1 + dt (U U_x - nu U_xx) IRK^T; SSE losses          */
 };
 
 /* L-BFGS stop reasons (utils/custom_lbfgs.py:73-76,154-156,192-215). */
@@ -64,8 +66,12 @@ int pinn_nccl_unique_id(void* out128);
 /* Number of entries of the flat parameter vector (net params [+2 for identification]). */
 int64_t pinn_num_params(const pinn_t* h);
 
-/* PDE constants.  BURGERS_INF: p[0] = nu (inf_cont_burgers.py:52,111).  Others take none. */
+/* PDE constants.  BURGERS_INF: p[0] = nu (inf_cont_burgers.py:52,111).  BURGERS_DISC: p = [nu, dt]
+ * (inf_disc_burgers.py:53-54).  Others take none. */
 int pinn_set_pde_params(pinn_t* h, const double* p, int n);
+/* BURGERS_DISC: the implicit Runge-Kutta stage matrix IRK_weights, (q+1) x q row-major (inf_disc_burgers.py:56,86);
+ * q+1 must equal the network's output width. */
+int pinn_set_irk(pinn_t* h, const double* irk, int q);
 
 /* Collocation points of THIS rank: x_f, t_f (inf_cont_burgers.py:55-56; inf_cont_schrodinger.py:56-57).
  * n_global = N_f over all ranks (the MSE_f denominator); pass n when world == 1. */
@@ -82,7 +88,8 @@ int pinn_set_collocation_mapped(pinn_t* h, const double* x_pinned, const double*
  * weight: 1 on the rank that owns the (replicated) data term, 0 elsewhere. */
 int pinn_set_data(pinn_t* h, const double* X, int64_t n, int in_dim, const double* u, int out_dim, double weight);
 
-/* NLS periodic-boundary times tb (N_b,1): X_lb=(lb0,tb), X_ub=(ub0,tb) (inf_cont_schrodinger.py:50-53). */
+/* NLS periodic-boundary times tb (N_b,1): X_lb=(lb0,tb), X_ub=(ub0,tb) (inf_cont_schrodinger.py:50-53).
+ * BURGERS_DISC: the boundary positions x_1 on which sum(net(x_1)^2) is imposed (inf_disc_burgers.py:57,99). */
 int pinn_set_boundary(pinn_t* h, const double* tb, int64_t n_b);
 
 /* get_weights / set_weights (utils/neuralnetwork.py:68-89; ide_cont_burgers.py:98-107). */

@@ -242,6 +242,51 @@ class SchrodingerInference:
         return a + b + c
 
 
+@dataclass
+class BurgersDiscreteInference:
+    """1d-burgers/inf_disc_burgers.py:49-127.  Net [1, ..., q+1] on x only; the x-derivatives of the q stage outputs are
+    obtained with the reference's two-step "dummy gradient" trick (:61-88): g = vjp(U, x; dummy), U_x = d g / d dummy --
+    a reverse-over-reverse evaluation of the forward-mode derivative -- applied twice for U_xx."""
+    layers: Sequence[int]
+    lb: np.ndarray
+    ub: np.ndarray
+    nu: float
+    dt: float
+    x_0: np.ndarray            # (N, 1)
+    u_0: np.ndarray            # (N, 1)
+    x_1: np.ndarray            # (2, 1) boundary positions
+    IRK_weights: np.ndarray    # (q+1, q)
+
+    def __post_init__(self):
+        t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+        self._lb, self._ub = t(self.lb).reshape(-1), t(self.ub).reshape(-1)
+        self._x0, self._u0, self._x1 = t(self.x_0), t(self.u_0), t(self.x_1)
+        self._irk = t(self.IRK_weights)
+        self.q = int(self.IRK_weights.shape[1])
+        self.P = num_params(self.layers)
+
+    def U_0_model(self, w: torch.Tensor):
+        x = self._x0.clone().requires_grad_(True)
+        dummy = torch.ones(x.shape[0], self.q, dtype=DT, requires_grad=True)          # :119
+        U_1 = mlp(w, x, self.layers, self._lb, self._ub)                              # :68
+        U = U_1[:, :-1]                                                               # :69
+        g_U = torch.autograd.grad(U, x, grad_outputs=dummy, create_graph=True)[0]     # :72
+        U_x = torch.autograd.grad(g_U, dummy, grad_outputs=torch.ones_like(g_U), create_graph=True)[0]      # :73
+        g_U_x = torch.autograd.grad(U_x, x, grad_outputs=dummy, create_graph=True)[0]                       # :74
+        U_xx = torch.autograd.grad(g_U_x, dummy, grad_outputs=torch.ones_like(g_U_x), create_graph=True)[0]  # :78
+        N = U * U_x - self.nu * U_xx                                                  # :85
+        return U_1 + self.dt * (N @ self._irk.T), (U_1, U_x, U_xx)                    # :86
+
+    def loss_parts(self, w: torch.Tensor):
+        U0, _ = self.U_0_model(w)
+        u1 = mlp(w, self._x1, self.layers, self._lb, self._ub)                        # :99
+        return torch.sum(torch.square(U0 - self._u0)), torch.sum(torch.square(u1))    # :100-101
+
+    def loss(self, w: torch.Tensor) -> torch.Tensor:
+        a, b = self.loss_parts(w)
+        return a + b
+
+
 def loss_and_flat_grad(problem, w) -> Tuple[float, np.ndarray]:
     """get_loss_and_flat_grad closure (neuralnetwork.py:91-103): loss value + flat gradient in the
     trainable_variables order (== flat weight layout; identification appends d/dl1, d/dl2)."""

@@ -36,16 +36,21 @@ def _unpack(w, layers):
 def forward(w, layers, lb, ub, X):
     """X: (N,2) -> outputs (u, u_x, u_t, u_xx), each (N, n_out), and the per-layer stash."""
     X = np.asarray(X, dtype=np.float64)
-    if X.shape[1] == 1:            # quirk Q1: (N,1) input broadcast by the Lambda to (x, t:=x)
-        X = np.concatenate([X, X], axis=1)
-    lb, ub = np.asarray(lb, float), np.asarray(ub, float)
+    lb, ub = np.asarray(lb, float).reshape(-1), np.asarray(ub, float).reshape(-1)
     Ws, bs = _unpack(np.asarray(w, dtype=np.float64), layers)
     N = X.shape[0]
-    sc = 2.0 / (ub - lb)
-    h = sc * (X - lb) - 1.0
-    hx = np.zeros((N, 2)); hx[:, 0] = sc[0]
-    ht = np.zeros((N, 2)); ht[:, 1] = sc[1]
-    hxx = np.zeros((N, 2))
+    if int(layers[0]) == 1:        # discrete-time models: 1-D input x (1d-burgers/inf_disc_burgers.py:34), no t stream
+        sc = 2.0 / (ub[:1] - lb[:1])
+        h = sc * (X[:, :1] - lb[:1]) - 1.0
+        hx = np.full((N, 1), sc[0]); ht = np.zeros((N, 1)); hxx = np.zeros((N, 1))
+    else:
+        if X.shape[1] == 1:        # quirk Q1: (N,1) input broadcast by the Lambda to (x, t:=x)
+            X = np.concatenate([X, X], axis=1)
+        sc = 2.0 / (ub - lb)
+        h = sc * (X - lb) - 1.0
+        hx = np.zeros((N, 2)); hx[:, 0] = sc[0]
+        ht = np.zeros((N, 2)); ht[:, 1] = sc[1]
+        hxx = np.zeros((N, 2))
     stash = []
     L = len(Ws)
     for l in range(L - 1):
@@ -153,3 +158,28 @@ def schrodinger_loss_grad(w, layers, lb, ub, X_f, tb, X0, uv0, n_f_global=None, 
     g = g + backward(w, layers, stl, (k * d, k * dx, zb, zb)) + backward(w, layers, stu, (-k * d, -k * dx, zb, zb))
     mse_b = aux_weight * float((np.sum(d * d) + np.sum(dx * dx)) / nb)
     return mse_0 + mse_b + mse_f, g, (mse_0, mse_b, mse_f)
+
+
+def burgers_disc_loss_grad(w, layers, lb, ub, x_0, u_0, x_1, nu, dt, IRK_weights):
+    """Discrete-time (implicit Runge-Kutta, q stages) Burgers inference, 1d-burgers/inf_disc_burgers.py:49-127:
+    net [1, ..., q+1]; U_1 = net(x) (N, q+1); U = U_1[:, :q]; N = U U_x - nu U_xx;
+    U_0 = U_1 + dt N IRK^T  (IRK: (q+1, q));  loss = sum((U_0 - u_0)^2) + sum(net(x_1)^2)   (sums, not means, :98-101)."""
+    w = np.asarray(w, dtype=np.float64)
+    IRK = np.asarray(IRK_weights, dtype=np.float64)
+    q = IRK.shape[1]
+    (U1, U1x, _, U1xx), st = forward(w, layers, lb, ub, x_0)
+    U, Ux, Uxx = U1[:, :q], U1x[:, :q], U1xx[:, :q]
+    Nn = U * Ux - nu * Uxx
+    U0 = U1 + dt * Nn @ IRK.T
+    R = 2.0 * (U0 - u_0)                                  # u_0 (N,1) broadcasts over the q+1 stages
+    Nbar = dt * R @ IRK                                   # (N, q)
+    S = R.copy(); S[:, :q] += Nbar * Ux
+    Sx = np.zeros_like(R); Sx[:, :q] = Nbar * U
+    Sxx = np.zeros_like(R); Sxx[:, :q] = -nu * Nbar
+    g = backward(w, layers, st, (S, Sx, np.zeros_like(R), Sxx))
+    loss0 = float(np.sum((U0 - u_0) ** 2))
+    (B1, _, _, _), stb = forward(w, layers, lb, ub, x_1)
+    zb = np.zeros_like(B1)
+    g = g + backward(w, layers, stb, (2.0 * B1, zb, zb, zb))
+    loss1 = float(np.sum(B1 ** 2))
+    return loss0 + loss1, g, (loss0, loss1)

@@ -28,12 +28,24 @@ def _lhs(d, n):
 
 def prep_data(path, N_u=None, N_f=None, N_n=None, q=None, ub=None, lb=None, noise=0.0, idx_t_0=None, idx_t_1=None,
               N_0=None, N_1=None):
-    if N_n is not None or N_0 is not None:
-        raise NotImplementedError("discrete-time (IRK) data preparation is out of scope of the hot path (SURVEY 8(f)2)")
+    if N_0 is not None:
+        raise NotImplementedError("discrete-time IDENTIFICATION data preparation is not provided (ide_disc_burgers.py is "
+                                  "broken as shipped, SURVEY section 2 #11)")
     data = scipy.io.loadmat(path)
     t = data["t"].flatten()[:, None]
     x = data["x"].flatten()[:, None]
     Exact_u = np.real(data["usol"]).T
+    if N_n is not None:
+        # discrete-time inference (reference burgersutil.py:38-60): N_n points of the snapshot idx_t_0, the two boundary
+        # positions, the target snapshot idx_t_1 and the q-stage implicit Runge-Kutta table of the upstream repository
+        dt_ = t[idx_t_1] - t[idx_t_0]
+        idx_x = np.random.choice(Exact_u.shape[1], N_n, replace=False)
+        x_0 = x[idx_x, :]
+        u_0 = Exact_u[idx_t_0:idx_t_0 + 1, idx_x].T
+        u_0 = u_0 + noise * np.std(u_0) * np.random.randn(u_0.shape[0], u_0.shape[1])
+        x_1 = np.vstack((lb, ub))
+        irk_w, irk_t = load_irk(q)
+        return x, t, dt_, Exact_u, x_0, u_0, x_1, x, Exact_u[idx_t_1, :], irk_w, irk_t
     X, T = np.meshgrid(x, t)
     X_star = np.hstack((X.flatten()[:, None], T.flatten()[:, None]))
     u_star = Exact_u.flatten()[:, None]
@@ -52,6 +64,15 @@ def prep_data(path, N_u=None, N_f=None, N_n=None, q=None, ub=None, lb=None, nois
     X_f_train = lb + (ub - lb) * _lhs(2, N_f)
     idx = np.random.choice(X_u_train.shape[0], N_u, replace=False)
     return x, t, X, T, Exact_u, X_star, u_star, X_u_train[idx, :], u_train[idx, :], X_f_train, ub, lb
+
+
+def load_irk(q, utils_path=None):
+    """Butcher table of the q-stage Gauss-Legendre IRK scheme as shipped by the upstream PINNs repository
+    (PINNs/Utilities/IRK_weights/Butcher_IRK<q>.txt), rounded to float32 like the reference does."""
+    import os
+    utils_path = utils_path or os.path.join(".", "PINNs", "Utilities")
+    tmp = np.float32(np.loadtxt(os.path.join(utils_path, "IRK_weights", "Butcher_IRK%d.txt" % q), ndmin=2))
+    return np.reshape(tmp[0:q ** 2 + q], (q + 1, q)), tmp[q ** 2 + q:]
 
 
 def _no_plot(*a, **k):

@@ -1,5 +1,6 @@
 // Generic fused PINN loss + gradient kernel: ANY tanh MLP [2, w_1, ..., w_k, out] (widths <= 128, <= 15 Dense layers),
-// all three PDE heads (Burgers inference / identification: out = 1; Schrodinger: out = 2), fp64, sm_100a.
+// PDE heads: Burgers inference / identification (out = 1), Schrodinger (out = 2), and the discrete-time (implicit
+// Runge-Kutta) Burgers model [1, ..., q+1] of 1d-burgers/inf_disc_burgers.py (1-D input, q+1 <= 512 outputs); fp64, sm_100a.
 //
 // Purpose: hp["layers"] is user-configurable in the reference (1d-burgers/inf_cont_burgers.py:23-34); the DMMA kernels
 // (burgers_fused_v2.cuh, nls_fused.cuh) are specialised for the two BASELINE nets.  This kernel keeps the path a drop-in
@@ -30,7 +31,10 @@ struct Args {
   const double* t;
   const double* tgt;          // data targets [n_d][out]
   long long n_total;
-  int pde;                    // PINN_BURGERS_INF / PINN_BURGERS_IDE / PINN_NLS_INF
+  int pde;                    // PINN_BURGERS_INF / PINN_BURGERS_IDE / PINN_NLS_INF / PINN_BURGERS_DISC (3)
+  int in_dim;                 // 2 (x,t), or 1 (x only: discrete-time models)
+  double dt;                  // DISC: time step;  irk: (q+1) x q stage matrix, q = out - 1
+  const double* irk;
   // Burgers: points [d0, d0+n_d) carry the data term, [c0, c0+n_c) the residual term
   long long c0, n_c, d0, n_d;
   double wf, wd, nu;
@@ -75,8 +79,8 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
   double* Hs = p.scrH + (size_t)blockIdx.x * p.h_per_cta;
   double* A0 = p.scrA + (size_t)blockIdx.x * 2 * p.a_per_cta;
   double* A1 = A0 + p.a_per_cta;
-  double* OUTV = p.scrS + (size_t)blockIdx.x * 2 * pts * 4 * MAXOUT;
-  double* SEED = OUTV + (size_t)pts * 4 * MAXOUT;
+  double* OUTV = p.scrS + (size_t)blockIdx.x * 2 * pts * 4 * out;
+  double* SEED = OUTV + (size_t)pts * 4 * out;
   double* outp = p.partials + (size_t)blockIdx.x * p.pstride;
   const double sc0 = 2.0 / nd.dx0, sc1 = 2.0 / nd.dx1;
   const bool ide = p.pde == 1;
@@ -103,8 +107,8 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
       double z = __ldg(bl + j), zx = 0.0, zt = 0.0, zxx = 0.0;
       if (l == 0) {
         const double xh = 2.0 * (__ldg(p.x + base + pt) - nd.lb0) / nd.dx0 - 1.0;   // utils/neuralnetwork.py:29-30
-        const double th = 2.0 * (__ldg(p.t + base + pt) - nd.lb1) / nd.dx1 - 1.0;
-        const double w0 = __ldg(Wl + j), w1 = __ldg(Wl + fo + j);
+        const double th = p.in_dim == 2 ? 2.0 * (__ldg(p.t + base + pt) - nd.lb1) / nd.dx1 - 1.0 : 0.0;
+        const double w0 = __ldg(Wl + j), w1 = p.in_dim == 2 ? __ldg(Wl + fo + j) : 0.0;
         z = fma(xh, w0, fma(th, w1, z));
         zx = sc0 * w0;
         zt = sc1 * w1;
@@ -143,6 +147,60 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
   }
   __syncthreads();
   double part0 = 0.0, part1 = 0.0, part2 = 0.0, gl1 = 0.0, gl2 = 0.0;
+  if (p.pde == 3) {
+    // Discrete-time IRK head (1d-burgers/inf_disc_burgers.py:61-101).  OUTV[pt] = [U_1 (q+1) | U_x | (t: 0) | U_xx]
+    //   N_j = U_j U_x,j - nu U_xx,j (j < q);  U_0,k = U_1,k + dt sum_j N_j IRK[k][j];  loss = sum (U_0 - u_0)^2 on the
+    //   data points + sum U_1^2 on the boundary points.  Scratch: NB[pt][q] (N, then N-bar), RB[pt][q+1] (2 (U_0 - u_0)).
+    const int q = out - 1;
+    double* NB = A0;
+    double* RB = A1;
+    for (int idx = tid; idx < npts * q; idx += THREADS) {
+      const int pt = idx / q, j = idx - pt * q;
+      const double* o = OUTV + (size_t)pt * 4 * out;
+      NB[idx] = o[j] * o[out + j] - p.nu * o[3 * out + j];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < npts * out; idx += THREADS) {
+      const int pt = idx / out, k = idx - pt * out;
+      const long long gp = base + pt;
+      const double u1k = OUTV[(size_t)pt * 4 * out + k];
+      if (gp < p.n_d) {
+        const double* nrow = NB + (size_t)pt * q;
+        const double* irow = p.irk + (size_t)k * q;
+        double acc = 0.0;
+        for (int j = 0; j < q; j++) acc = fma(nrow[j], __ldg(irow + j), acc);
+        const double r = fma(p.dt, acc, u1k) - __ldg(p.tgt + gp);
+        part0 = fma(r, r, part0);
+        RB[idx] = 2.0 * r;
+      } else {
+        part1 = fma(u1k, u1k, part1);
+        RB[idx] = 2.0 * u1k;                 // boundary point: d/dU_1 of sum U_1^2
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < npts * q; idx += THREADS) {
+      const int pt = idx / q, j = idx - pt * q;
+      double acc = 0.0;
+      if (base + pt < p.n_d) {
+        const double* rrow = RB + (size_t)pt * out;
+        for (int k = 0; k < out; k++) acc = fma(rrow[k], __ldg(p.irk + (size_t)k * q + j), acc);
+        acc *= p.dt;
+      }
+      NB[idx] = acc;                          // N-bar (0 on boundary points)
+    }
+    __syncthreads();
+    for (int idx = tid; idx < npts * out; idx += THREADS) {
+      const int pt = idx / out, k = idx - pt * out;
+      const double* o = OUTV + (size_t)pt * 4 * out;
+      const double nb_ = k < q ? NB[(size_t)pt * q + k] : 0.0;
+      double* sdp = SEED + (size_t)pt * 4 * out;
+      sdp[k] = fma(nb_, o[out + k], RB[idx]);
+      sdp[out + k] = nb_ * o[k];
+      sdp[2 * out + k] = 0.0;
+      sdp[3 * out + k] = -p.nu * nb_;
+    }
+    __syncthreads();
+  } else
   for (int pt = tid; pt < npts; pt += THREADS) {
     const long long gp = base + pt;
     const double* o = OUTV + (size_t)pt * 4 * out;
@@ -271,7 +329,7 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
           acc += z[0];
         } else if (l == 0) {
           const double xh = 2.0 * (__ldg(p.x + base + pt) - nd.lb0) / nd.dx0 - 1.0;
-          const double th = 2.0 * (__ldg(p.t + base + pt) - nd.lb1) / nd.dx1 - 1.0;
+          const double th = p.in_dim == 2 ? 2.0 * (__ldg(p.t + base + pt) - nd.lb1) / nd.dx1 - 1.0 : 0.0;
           acc += i == 0 ? fma(xh, z[0], sc0 * z[so]) : fma(th, z[0], sc1 * z[2 * so]);
         } else {
           const double* h = Hp + (size_t)pt * fi + i;

@@ -384,7 +384,7 @@ __global__ void mlp_forward_generic(const double* __restrict__ w, NetDesc nd, co
   const double x = Tsoa ? X[p] : X[p * in_dim];
   const double t = Tsoa ? Tsoa[p] : (in_dim == 1 ? x : X[p * in_dim + 1]);
   h[0][0] = 2.0 * (x - nd.lb0) / nd.dx0 - 1.0;
-  h[0][1] = 2.0 * (t - nd.lb1) / nd.dx1 - 1.0;
+  h[0][1] = nd.dims[0] == 2 ? 2.0 * (t - nd.lb1) / nd.dx1 - 1.0 : 0.0;   // 1-D nets (discrete-time models) ignore t
   if (NS == 4) {
     h[1][0] = 2.0 / nd.dx0; h[1][1] = 0.0;
     h[2][0] = 0.0;          h[2][1] = 2.0 / nd.dx1;
@@ -394,6 +394,23 @@ __global__ void mlp_forward_generic(const double* __restrict__ w, NetDesc nd, co
     const int fi = nd.dims[l], fo = nd.dims[l + 1];
     const double* Wl = w + nd.woff[l];
     const double* bl = w + nd.boff[l];
+    if (l == nd.n_layers - 1) {
+      // linear head: written straight to the output (it may be wider than MAXW, e.g. q+1 = 501 IRK stages)
+      for (int j = 0; j < fo; j++) {
+        double acc[NS];
+        acc[0] = __ldg(bl + j);
+#pragma unroll
+        for (int s = 1; s < NS; s++) acc[s] = 0.0;
+        for (int i = 0; i < fi; i++) {
+          const double wv = __ldg(Wl + i * fo + j);
+#pragma unroll
+          for (int s = 0; s < NS; s++) acc[s] = fma(h[s][i], wv, acc[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) out[p * (NS * fo) + s * fo + j] = acc[s];
+      }
+      return;
+    }
     for (int j = 0; j < fo; j++) {
       double acc[NS];
       acc[0] = __ldg(bl + j);

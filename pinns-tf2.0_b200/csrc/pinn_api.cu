@@ -70,7 +70,10 @@ struct pinn_handle {
   std::vector<int> layers;
   double lb[2] = {0, 0}, ub[2] = {1, 1};
   int P_net = 0, P = 0;             // net parameters; P = P_net (+2 identification)
-  double nu = 0.0;
+  double nu = 0.0, dt = 0.0;
+  double* d_irk = nullptr;          // DISC: (q+1) x q stage matrix
+  int irk_q = 0;
+  std::vector<double> h_x0;         // DISC: data x positions (host copy for re-assembly)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_sm = 0;
@@ -143,6 +146,7 @@ bool is_nls_net(const std::vector<int>& L) {
 int nls_upload_points(pinn_t* h);
 int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only);
 int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only);
+int disc_upload_points(pinn_t* h);
 
 pinn::NetDesc net_desc(const pinn_t* h) {
   pinn::NetDesc nd{};
@@ -257,10 +261,28 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
   return 0;
 }
 
+// DISC: data region = [x_0 data points | x_1 boundary points], right-aligned like every data block (t is unused)
+int disc_upload_points(pinn_t* h) {
+  const long long n_aux = h->n_d + h->n_b;
+  if (ensure_points(h, n_aux > h->n_aux ? n_aux : h->n_aux, 0)) return -1;
+  h->stage_x.assign(n_aux, 0.0); h->stage_t.assign(n_aux, 0.0);
+  for (long long i = 0; i < h->n_d; i++) h->stage_x[i] = h->h_x0[i];
+  for (long long i = 0; i < h->n_b; i++) h->stage_x[h->n_d + i] = h->h_tb[i];
+  if (n_aux) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_x + h->dcap - n_aux, h->stage_x.data(), n_aux * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_t + h->dcap - n_aux, h->stage_t.data(), n_aux * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  h->n_aux = n_aux;
+  return 0;
+}
+
 int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
   namespace G = pinn::generic;
+  const bool disc = h->pde == PINN_BURGERS_DISC;
+  if (disc && (!h->d_irk || h->irk_q + 1 != h->layers.back())) return fail("discrete-time model: call pinn_set_irk first");
   const bool nls = h->pde == PINN_NLS_INF, ide = h->pde == PINN_BURGERS_IDE;
-  const long long n_total = nls ? h->n_aux + h->n_c : (ide ? h->n_d : h->n_d + h->n_c);
+  const long long n_total = disc ? h->n_aux : (nls ? h->n_aux + h->n_c : (ide ? h->n_d : h->n_d + h->n_c));
   if (n_total <= 0) return fail("no points set (pinn_set_collocation / pinn_set_data)");
   const int grid = h->n_cta;
   const long long per = (n_total + grid - 1) / grid;
@@ -268,6 +290,8 @@ int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
   pinn::NetDesc nd = net_desc(h);
   int maxw = 0; long long hsum = 0;
   for (int l = 0; l < nd.n_layers - 1; l++) { hsum += 4 * pts * nd.dims[l + 1]; if (nd.dims[l + 1] > maxw) maxw = nd.dims[l + 1]; }
+  const int out_w = nd.dims[nd.n_layers];
+  if (out_w > maxw) maxw = out_w;                 // the IRK head reuses the adjoint scratch for N, N-bar and 2(U_0 - u_0)
   const long long a_per = 4 * pts * maxw;
   if (pts > h->g_pts) {
     if (h->d_gH) cudaFree(h->d_gH);
@@ -276,14 +300,15 @@ int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
     h->d_gH = h->d_gA = h->d_gS = nullptr;
     CUDA_TRY(cudaMalloc((void**)&h->d_gH, (size_t)grid * hsum * 8));
     CUDA_TRY(cudaMalloc((void**)&h->d_gA, (size_t)grid * 2 * a_per * 8));
-    CUDA_TRY(cudaMalloc((void**)&h->d_gS, (size_t)grid * 2 * pts * 4 * G::MAXOUT * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_gS, (size_t)grid * 2 * pts * 4 * out_w * 8));
     h->g_pts = pts;
   }
   G::Args a{};
   a.w = h->d_w; a.nd = nd;
-  const long long n_front = nls ? h->n_aux : h->n_d;
+  const long long n_front = (nls || disc) ? h->n_aux : h->n_d;
   a.x = h->d_x + (h->dcap - n_front); a.t = h->d_t + (h->dcap - n_front); a.tgt = h->d_u;
   a.n_total = n_total; a.pde = h->pde;
+  a.in_dim = disc ? 1 : 2; a.dt = h->dt; a.irk = h->d_irk;
   a.c0 = ide ? 0 : h->n_d; a.n_c = ide ? h->n_d : h->n_c; a.d0 = 0; a.n_d = h->n_d;
   const long long nfg = ide ? h->n_d : h->n_c_global;
   a.wf = nfg > 0 ? 1.0 / (double)nfg : 0.0;
@@ -409,7 +434,7 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
                 int device, int rank, int world, const void* nccl_uid) {
   if (!out || !layers || !lb || !ub) return fail("pinn_create: null argument");
   if (n_layers < 3 || n_layers > pinn::MAXL) return fail("pinn_create: need 3..16 layer sizes");
-  if (pde_id < 0 || pde_id > 2) return fail("pinn_create: unknown pde_id");
+  if (pde_id < 0 || pde_id > 3) return fail("pinn_create: unknown pde_id");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("pinn_create: no CUDA device -- this library has no CPU fallback");
@@ -417,12 +442,23 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
   pinn_t* h = new pinn_t();
   h->pde = pde_id; h->device = device; h->rank = rank; h->world = world < 1 ? 1 : world;
   h->layers.assign(layers, layers + n_layers);
-  for (int v : h->layers) if (v < 1 || v > pinn::MAXW) { delete h; return fail("pinn_create: layer width out of range (1..128)"); }
-  if (h->layers[0] != 2) { delete h; return fail("pinn_create: input dimension must be 2 (x,t)"); }
-  h->lb[0] = lb[0]; h->lb[1] = lb[1]; h->ub[0] = ub[0]; h->ub[1] = ub[1];
-  if (!(ub[0] > lb[0]) || !(ub[1] > lb[1])) { delete h; return fail("pinn_create: need ub > lb"); }
+  const bool disc = pde_id == PINN_BURGERS_DISC;
+  for (int i = 0; i < n_layers; i++) {
+    const int v = h->layers[i];
+    const int cap = (disc && i == n_layers - 1) ? 512 : pinn::MAXW;     // the IRK head may be q+1 = 501 wide
+    if (v < 1 || v > cap) { delete h; return fail("pinn_create: layer width out of range (1..128; IRK head <= 512)"); }
+  }
+  if (h->layers[0] != (disc ? 1 : 2)) {
+    delete h;
+    return fail(disc ? "pinn_create: the discrete-time model takes a 1-D input (x)" : "pinn_create: input dimension must be 2 (x,t)");
+  }
+  h->lb[0] = lb[0]; h->ub[0] = ub[0];
+  h->lb[1] = disc ? 0.0 : lb[1]; h->ub[1] = disc ? 1.0 : ub[1];            // the t axis does not exist for 1-D nets
+  if (!(h->ub[0] > h->lb[0]) || !(h->ub[1] > h->lb[1])) { delete h; return fail("pinn_create: need ub > lb"); }
   const int want_out = pde_id == PINN_NLS_INF ? 2 : 1;
-  if (h->layers.back() != want_out) {
+  if (disc) {
+    if (h->layers.back() < 2) { delete h; return fail("pinn_create: the discrete-time model needs q+1 >= 2 outputs"); }
+  } else if (h->layers.back() != want_out) {
     delete h;
     return fail(pde_id == PINN_NLS_INF ? "pinn_create: the Schrodinger problem needs 2 network outputs (u, v)"
                                         : "pinn_create: the Burgers problems need 1 network output (u)");
@@ -431,7 +467,7 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
     // specialised DMMA kernels for the two BASELINE nets, generic DFMA kernel for any other layer list
     const char* fg = getenv("PINN_FORCE_GENERIC");
     const bool force = fg && fg[0] == '1';
-    const bool special = (pde_id == PINN_NLS_INF) ? is_nls_net(h->layers) : is_burgers_net(h->layers);
+    const bool special = disc ? false : ((pde_id == PINN_NLS_INF) ? is_nls_net(h->layers) : is_burgers_net(h->layers));
     h->kernel_kind = (special && !force) ? (pde_id == PINN_NLS_INF ? 1 : 0) : 2;
   }
   h->P_net = 0;
@@ -511,7 +547,7 @@ int pinn_destroy(pinn_t* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  double* bufs[] = {h->d_w, h->d_R, h->d_partials, h->d_m, h->d_v, h->d_loss_ring, h->d_x, h->d_t, h->d_u, h->d_scrH, h->d_scrA, h->d_scrS, h->d_gH, h->d_gA, h->d_gS, h->d_gold,
+  double* bufs[] = {h->d_w, h->d_R, h->d_partials, h->d_m, h->d_v, h->d_loss_ring, h->d_x, h->d_t, h->d_u, h->d_scrH, h->d_scrA, h->d_scrS, h->d_gH, h->d_gA, h->d_gS, h->d_irk, h->d_gold,
                     h->d_d, h->d_S, h->d_Y, h->d_xfinal, h->d_fhist, h->d_px, h->d_pout};
   for (double* b : bufs) if (b) cudaFree(b);
   if (h->d_step) cudaFree(h->d_step);
@@ -535,13 +571,32 @@ int pinn_set_pde_params(pinn_t* h, const double* p, int n) {
     h->nu = p[0];
     return 0;
   }
+  if (h->pde == PINN_BURGERS_DISC) {
+    if (n != 2 || !p) return fail("pinn_set_pde_params: BURGERS_DISC takes [nu, dt]");
+    h->nu = p[0]; h->dt = p[1];
+    return 0;
+  }
   if (n != 0) return fail("pinn_set_pde_params: this PDE takes no constants");
+  return 0;
+}
+
+int pinn_set_irk(pinn_t* h, const double* irk, int q) {
+  if (!h || !irk) return fail("pinn_set_irk: null argument");
+  if (h->pde != PINN_BURGERS_DISC) return fail("pinn_set_irk: only the discrete-time model has a stage matrix");
+  if (q + 1 != h->layers.back()) return fail("pinn_set_irk: q+1 must equal the network's output width");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->d_irk) cudaFree(h->d_irk);
+  h->d_irk = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&h->d_irk, (size_t)(q + 1) * q * 8));
+  CUDA_TRY(cudaMemcpy(h->d_irk, irk, (size_t)(q + 1) * q * 8, cudaMemcpyHostToDevice));
+  h->irk_q = q;
   return 0;
 }
 
 int pinn_set_collocation(pinn_t* h, const double* x, const double* t, int64_t n, int64_t n_global) {
   if (!h) return fail("null handle");
   if (h->pde == PINN_BURGERS_IDE) return fail("pinn_set_collocation: identification uses the data points as residual points");
+  if (h->pde == PINN_BURGERS_DISC) return fail("pinn_set_collocation: the discrete-time model has no collocation set (x_0 data + x_1 boundary)");
   if (n < 0 || (n > 0 && (!x || !t))) return fail("pinn_set_collocation: bad arguments");
   if (n_global < n) return fail("pinn_set_collocation: n_global < n");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -580,6 +635,19 @@ int pinn_set_data(pinn_t* h, const double* X, int64_t n, int in_dim, const doubl
   if (!h) return fail("null handle");
   if (n < 0 || (n > 0 && (!X || !u))) return fail("pinn_set_data: bad arguments");
   if (in_dim != 1 && in_dim != 2) return fail("pinn_set_data: in_dim must be 1 (broadcast quirk) or 2");
+  if (h->pde == PINN_BURGERS_DISC) {
+    // x_0 (n,1) and u_0 (n,1): the snapshot the q stages are fitted to (inf_disc_burgers.py:98-101; u_0 broadcasts)
+    if (in_dim != 1 || out_dim != 1) return fail("pinn_set_data: the discrete-time model takes x_0 (n,1) and u_0 (n,1)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->h_x0.assign(X, X + n);
+    if (n) {
+      if (ensure(&h->d_u, &h->u_cap, n)) return -1;
+      CUDA_TRY(cudaMemcpyAsync(h->d_u, u, n * 8, cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->n_d = n; h->d_out_dim = 1; h->data_weight = weight;
+    return disc_upload_points(h);
+  }
   if (out_dim != h->layers.back()) return fail("pinn_set_data: out_dim does not match the network head");
   CUDA_TRY(cudaSetDevice(h->device));
   if (h->pde == PINN_NLS_INF) {
@@ -616,7 +684,14 @@ int pinn_set_data(pinn_t* h, const double* X, int64_t n, int in_dim, const doubl
 
 int pinn_set_boundary(pinn_t* h, const double* tb, int64_t n_b) {
   if (!h) return fail("null handle");
-  if (h->pde != PINN_NLS_INF) return fail("pinn_set_boundary: only the NLS problem has a boundary term");
+  if (h->pde == PINN_BURGERS_DISC) {
+    if (n_b < 0 || (n_b > 0 && !tb)) return fail("pinn_set_boundary: bad arguments");
+    h->h_tb.assign(tb, tb + n_b);
+    h->n_b = n_b;
+    CUDA_TRY(cudaSetDevice(h->device));
+    return disc_upload_points(h);
+  }
+  if (h->pde != PINN_NLS_INF) return fail("pinn_set_boundary: only the NLS and discrete-time problems have a boundary term");
   if (n_b < 0 || (n_b > 0 && !tb)) return fail("pinn_set_boundary: bad arguments");
   h->h_tb.assign(tb, tb + n_b);
   h->n_b = n_b;
@@ -830,11 +905,12 @@ int pinn_predict(pinn_t* h, const double* X, int64_t n, int in_dim, double* out)
 }
 
 int pinn_derivatives(pinn_t* h, const double* X, int64_t n, double* out) {
-  return forward_generic(h, X, nullptr, nullptr, n, 2, out, 4);
+  return forward_generic(h, X, nullptr, nullptr, n, h ? h->layers[0] : 2, out, 4);
 }
 
 int pinn_residual(pinn_t* h, double* f_out) {
   if (!h || !f_out) return fail("null argument");
+  if (h->pde == PINN_BURGERS_DISC) return fail("pinn_residual: not defined for the discrete-time model");
   const bool ide = h->pde == PINN_BURGERS_IDE;
   const int64_t n = ide ? h->n_d : h->n_c;
   if (n == 0) return 0;

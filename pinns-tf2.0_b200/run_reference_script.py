@@ -22,6 +22,8 @@ def prepare_workdir(script):
     ref_root = os.path.dirname(os.path.dirname(os.path.abspath(script)))
     wd = tempfile.mkdtemp(prefix="pinn_b200_run_")
     os.symlink(os.path.join(HERE, "utils"), os.path.join(wd, "utils"))
+    if os.path.isdir(os.path.join(ref_root, "PINNs")):        # IRK tables of the upstream repository (discrete-time models)
+        os.symlink(os.path.join(ref_root, "PINNs"), os.path.join(wd, "PINNs"))
     for eqn in ("1d-burgers", "1dcomplex-schrodinger"):
         d = os.path.join(wd, eqn)
         os.makedirs(d)

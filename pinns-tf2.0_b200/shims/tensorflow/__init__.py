@@ -29,6 +29,10 @@ def stack(values, axis=0):
     return _t(np.stack([np.asarray(v) for v in values], axis=axis))
 
 
+def ones(shape, dtype=None):
+    return _t(np.ones([int(v) for v in shape]))
+
+
 def exp(a):
     return _t(np.exp(np.asarray(a)))
 

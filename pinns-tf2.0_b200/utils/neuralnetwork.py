@@ -89,7 +89,8 @@ class NeuralNetwork(object):
     def __init_subclass__(cls, **kw):
         super().__init_subclass__(**kw)
         # TensorFlow tape bodies in the reference subclasses are replaced by the fused-kernel equivalents
-        for name in ("loss", "f_model", "uvx_model", "get_params", "wrap_training_variables", "get_weights", "set_weights"):
+        for name in ("loss", "f_model", "uvx_model", "U_0_model", "grad", "get_loss_and_flat_grad", "get_params",
+                     "wrap_training_variables", "get_weights", "set_weights"):
             if name in cls.__dict__ and name in _NATIVE_OVERRIDES and not getattr(cls.__dict__[name], "_keep", False):
                 setattr(cls, "_script_" + name, cls.__dict__[name])
                 setattr(cls, name, _NATIVE_OVERRIDES[name])
@@ -130,7 +131,9 @@ class NeuralNetwork(object):
     def _pde_id(self):
         tag = self.pde
         if tag is None:
-            if hasattr(self, "lambda_1"):
+            if hasattr(self, "IRK_weights"):
+                tag = "burgers_disc"
+            elif hasattr(self, "lambda_1"):
                 tag = "burgers_ide"
             elif hasattr(self, "X_lb"):
                 tag = "nls_inf"
@@ -138,7 +141,8 @@ class NeuralNetwork(object):
                 tag = "burgers_inf"
             else:
                 raise pinn_cabi.PinnError("cannot recognise the PDE of %s: set the class attribute `pde`" % type(self).__name__)
-        return {"burgers_inf": pinn_cabi.BURGERS_INF, "burgers_ide": pinn_cabi.BURGERS_IDE, "nls_inf": pinn_cabi.NLS_INF}[tag]
+        return {"burgers_inf": pinn_cabi.BURGERS_INF, "burgers_ide": pinn_cabi.BURGERS_IDE, "nls_inf": pinn_cabi.NLS_INF,
+                "burgers_disc": pinn_cabi.BURGERS_DISC}[tag]
 
     def _native(self):
         if self._h is None:
@@ -150,6 +154,10 @@ class NeuralNetwork(object):
             if pde == pinn_cabi.BURGERS_INF:
                 h.set_pde_params([float(self.nu)])
                 h.set_collocation(np.asarray(self.x_f)[:, 0], np.asarray(self.t_f)[:, 0], getattr(self, "n_f_global", None))
+            elif pde == pinn_cabi.BURGERS_DISC:                      # inf_disc_burgers.py:50-59
+                h.set_pde_params([float(self.nu), float(np.asarray(self.dt).reshape(-1)[0])])
+                h.set_irk(np.asarray(self.IRK_weights, dtype=np.float64))
+                h.set_boundary(np.asarray(self.x_1, dtype=np.float64).reshape(-1))
             elif pde == pinn_cabi.BURGERS_IDE:
                 l1 = float(np.asarray(self.lambda_1.numpy() if hasattr(self.lambda_1, "numpy") else self.lambda_1).reshape(-1)[0])
                 l2 = float(np.asarray(self.lambda_2.numpy() if hasattr(self.lambda_2, "numpy") else self.lambda_2).reshape(-1)[0])
@@ -286,6 +294,18 @@ def _native_f_model(self, *args):
     return _t(f)
 
 
+def _native_U_0_model(self, x):
+    raise pinn_cabi.PinnError("U_0_model is evaluated inside the fused kernel; use grad()/fit()/predict()")
+
+
+def _native_grad(self, X, u):
+    return NeuralNetwork.grad(self, X, u)
+
+
+def _native_get_loss_and_flat_grad(self, X, u):
+    return NeuralNetwork.get_loss_and_flat_grad(self, X, u)
+
+
 def _native_uvx_model(self, X):
     U, Ux, _, _ = self._native().derivatives(np.asarray(X, dtype=np.float64))
     return _t(U[:, 0:1]), _t(U[:, 1:2]), _t(Ux[:, 0:1]), _t(Ux[:, 1:2])
@@ -314,6 +334,7 @@ def _native_set_weights(self, w):
     return NeuralNetwork.set_weights(self, w)
 
 
+_NATIVE_OVERRIDES.update(U_0_model=_native_U_0_model, grad=_native_grad, get_loss_and_flat_grad=_native_get_loss_and_flat_grad)
 _NATIVE_OVERRIDES.update(loss=_native_loss, f_model=_native_f_model, uvx_model=_native_uvx_model,
                          get_params=_native_get_params, wrap_training_variables=_native_wrap_training_variables,
                          get_weights=_native_get_weights, set_weights=_native_set_weights)

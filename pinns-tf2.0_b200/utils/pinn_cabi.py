@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.realpath(__file__))
 LIB_PATH = os.path.join(_HERE, "..", "lib", "libpinn_b200.so")
 
-BURGERS_INF, BURGERS_IDE, NLS_INF = 0, 1, 2
+BURGERS_INF, BURGERS_IDE, NLS_INF, BURGERS_DISC = 0, 1, 2, 3
 LBFGS_REASONS = {0: "running", 1: "max iterations", 2: "max evaluations", 3: "optimality", 4: "step below tolX",
                  5: "f change below tolX", 6: "no progress along direction", 7: "initial optimality"}
 
@@ -29,6 +29,7 @@ SIGNATURES = {
     "pinn_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "pinn_num_params": (C.c_int64, [C.c_void_p]),
     "pinn_set_pde_params": (C.c_int, [C.c_void_p, _dp, C.c_int]),
+    "pinn_set_irk": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "pinn_set_collocation": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64]),
     "pinn_set_collocation_mapped": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64]),
     "pinn_set_data": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int, _dp, C.c_int, C.c_double]),
@@ -96,7 +97,9 @@ class Pinn(object):
         self.lib = load()
         self.h = C.c_void_p()
         L = (C.c_int * len(layers))(*[int(v) for v in layers])
-        self._lb, self._ub = _arr(lb), _arr(ub)
+        self._lb, self._ub = _arr(lb).reshape(-1), _arr(ub).reshape(-1)
+        if self._lb.size == 1:               # 1-D models (discrete time): the ABI takes lb[2], ub[2]
+            self._lb, self._ub = np.array([self._lb[0], 0.0]), np.array([self._ub[0], 1.0])
         uid = None
         if nccl_uid is not None:
             self._uid = C.create_string_buffer(bytes(nccl_uid), 128)
@@ -128,6 +131,11 @@ class Pinn(object):
     def set_pde_params(self, params):
         a = _arr(params).reshape(-1)
         self._ck(self.lib.pinn_set_pde_params(self.h, _p(a), a.size))
+
+    def set_irk(self, irk):
+        irk = _arr(irk)
+        assert irk.ndim == 2 and irk.shape[0] == irk.shape[1] + 1
+        self._ck(self.lib.pinn_set_irk(self.h, _p(irk), irk.shape[1]))
 
     def set_collocation(self, x, t, n_global=None):
         x, t = _arr(x).reshape(-1), _arr(t).reshape(-1)

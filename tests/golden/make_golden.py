@@ -148,10 +148,41 @@ def make_nls():
     np.savez_compressed(os.path.join(OUT, "nls_inf.npz"), **out)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--disc" not in sys.argv:
     make_burgers_inf()
     make_burgers_ide()
     make_nls()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+def make_burgers_disc():
+    """Discrete-time (q-stage IRK) Burgers inference, 1d-burgers/inf_disc_burgers.py, with the upstream q=100 table."""
+    sys.path.insert(0, os.path.join(ROOT, "pinns-tf2.0_b200", "1d-burgers"))
+    import burgersutil
+    rng = np.random.default_rng(2024)
+    np.random.seed(1234)
+    q = 100
+    lb, ub = np.array([-1.0]), np.array([1.0])
+    cwd = os.getcwd(); os.chdir(REF)
+    try:
+        x, t, dt, Exact_u, x_0, u_0, x_1, x_star, u_star, IRK_w, IRK_t = burgersutil.prep_data(
+            os.path.join(REF, "1d-burgers", "data", "burgers_shock.mat"), N_n=250, q=q, lb=lb, ub=ub, noise=0.0, idx_t_0=10, idx_t_1=90)
+    finally:
+        os.chdir(cwd)
+    layers = [1, 50, 50, 50, q + 1]
+    w = rp.glorot_normal_flat(layers, rng) + 0.02 * rng.standard_normal(rp.num_params(layers))
+    nu, dtv = 0.01 / np.pi, float(np.asarray(dt).reshape(-1)[0])
+    pb = rp.BurgersDiscreteInference(layers, lb, ub, nu, dtv, x_0, u_0, x_1, IRK_w)
+    f, g = rp.loss_and_flat_grad(pb, w)
+    f2, g2, parts = ty.burgers_disc_loss_grad(w, layers, lb, ub, x_0, u_0, x_1, nu, dtv, IRK_w)
+    check("burgers_disc", f, g, f2, g2)
+    wa, la, _ = rp.adam_train(pb, w, 3, lr=1e-3, eps=1e-8)                 # inf_disc_burgers.py:38-41
+    np.savez_compressed(os.path.join(OUT, "burgers_disc.npz"), layers=layers, lb=lb, ub=ub, nu=nu, dt=dtv, q=q, x_0=x_0, u_0=u_0,
+                        x_1=x_1, IRK=IRK_w.astype(np.float32), w=w, loss=f, parts=np.array(parts), grad=g, adam_losses=la,
+                        adam_w=wa, x_star=x_star, predict=rp.predict(pb, w, x_star)[:, -1])
+
+
+if __name__ == "__main__" and "--disc" in sys.argv:
+    make_burgers_disc()

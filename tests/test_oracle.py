@@ -128,3 +128,19 @@ def test_lua_struct_defaults_to_zero():
     s = rp.LuaStruct()
     s.maxIter = 3
     assert s.maxIter == 3 and s.lineSearch == 0 and (s.tolX or 1e-19) == 1e-19    # custom_lbfgs.py:242-246
+
+
+def test_burgers_disc_golden_both_oracles():
+    """Discrete-time IRK model (1d-burgers/inf_disc_burgers.py:61-101): nested autograd with the reference's dummy-gradient
+    trick and the closed-form Taylor oracle against the committed vector (upstream q=100 Butcher table)."""
+    g = load_golden("burgers_disc")
+    layers = [int(v) for v in g["layers"]]
+    IRK = g["IRK"].astype(np.float64)
+    pb = rp.BurgersDiscreteInference(layers, g["lb"], g["ub"], float(g["nu"]), float(g["dt"]), g["x_0"], g["u_0"], g["x_1"], IRK)
+    f, gr = rp.loss_and_flat_grad(pb, g["w"])
+    f2, g2, parts = ty.burgers_disc_loss_grad(g["w"], layers, g["lb"], g["ub"], g["x_0"], g["u_0"], g["x_1"], float(g["nu"]),
+                                              float(g["dt"]), IRK)
+    for fv, gv in ((f, gr), (f2, g2)):
+        assert abs(fv - g["loss"]) <= 1e-13 * abs(g["loss"]) and rel(gv, g["grad"]) < 1e-12
+    assert np.allclose(parts, g["parts"], rtol=1e-12)
+    assert IRK.shape == (101, 100) and abs(IRK[-1].sum() - 1.0) < 1e-5        # last row: the quadrature weights b_j

@@ -120,7 +120,8 @@ def test_indentation_normaliser_repairs_ide_cont_and_leaves_good_scripts_alone()
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
-@pytest.mark.parametrize("script", ["1d-burgers/ide_cont_burgers.py", "1dcomplex-schrodinger/inf_cont_schrodinger.py"])
+@pytest.mark.parametrize("script", ["1d-burgers/ide_cont_burgers.py", "1dcomplex-schrodinger/inf_cont_schrodinger.py",
+                                    "1d-burgers/inf_disc_burgers.py"])
 def test_other_reference_scripts_reach_the_gpu_boundary(script):
     import torch
     if torch.cuda.is_available():
