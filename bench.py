@@ -314,6 +314,8 @@ def main():
     _, X_u, u = synthetic_problem(1234, 1)     # data term identical on all ranks
     p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, LAYERS, LB, UB, device=local_rank, rank=rank, world=world, nccl_uid=uid)
     handle.append(p)
+    import sharding
+    used_p2p = sharding.connect_p2p(dist, p, world) if dist is not None else False
     p.set_pde_params([NU])
     p.set_data(X_u, u, weight=1.0 if rank == 0 else 0.0)
     # pinned host copies of this rank's collocation batch (e2e leg uploads them every step)
@@ -427,7 +429,7 @@ def main():
             "config": {"workload": "1d-burgers inf_cont [2,20x8,1] tanh, N_f=%d per GPU (%d global), N_u=100, Adam lr 1e-3 "
                                    "(BASELINE configs[1])" % (n_f, n_f_global),
                        "l2": "flushed (256 MB memset) between timed iterations; inputs are 1.6 MB, the path is compute-bound",
-                       "parallelism": "dp%d (collocation shards, one ncclAllReduce of 3024 doubles per step)" % world},
+                       "parallelism": "dp%d (collocation shards; per step one exchange of 3024 doubles: %s)" % (world, "fused NVLink P2P gather-reduce-Adam kernel" if used_p2p else ("ncclAllReduce" if world > 1 else "none"))},
             "clocks": clocks.summary(),
             "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches_per_step,
             "roofline": roofline, "kernel_info": p.kernel_info(), "final_loss": loss,

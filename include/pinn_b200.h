@@ -63,6 +63,14 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
 int pinn_destroy(pinn_t* h);
 int pinn_nccl_unique_id(void* out128);
 
+/* Fused NVLink P2P exchange (optional, world > 1): instead of reduce -> ncclAllReduce -> Adam, every rank publishes its
+ * reduced [gradient | loss] vector in a small IPC-exported buffer and ONE kernel per rank gathers all peers' vectors with
+ * P2P loads over NVLink, sums them in rank order (bitwise identical on all ranks) and applies Adam.  Usage: each rank calls
+ * pinn_p2p_export (64-byte cudaIpcMemHandle), the handles are all-gathered by the caller's control plane, then each rank
+ * calls pinn_p2p_connect(handles[world][64]).  Without it the NCCL communicator of pinn_create is used. */
+int pinn_p2p_export(pinn_t* h, void* out64);
+int pinn_p2p_connect(pinn_t* h, const void* handles, int world);
+
 /* Number of entries of the flat parameter vector (net params [+2 for identification]). */
 int64_t pinn_num_params(const pinn_t* h);
 

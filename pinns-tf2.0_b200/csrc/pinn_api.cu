@@ -128,6 +128,15 @@ struct pinn_handle {
   long long px_cap = 0, pout_cap = 0;
 
   ncclComm_t comm = nullptr;
+  // fused NVLink P2P exchange (optim_kernels.cuh: p2p_gather_reduce)
+  double* d_xchg = nullptr;            // [2][xchg_len] doubles + 2 flags (IPC-exported)
+  int xchg_len = 0;
+  bool p2p_ready = false;
+  pinn::P2PPeers peers{};
+  void* peer_base[pinn::P2P_MAX] = {nullptr};
+  unsigned long long p2p_seq = 0;
+  double* reduce_dst = nullptr;        // where reduce_partials writes: d_R, or this evaluation's exchange slot
+  int* d_p2p_err = nullptr;
 };
 
 namespace {
@@ -147,6 +156,7 @@ int nls_upload_points(pinn_t* h);
 int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only);
 int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only);
 int disc_upload_points(pinn_t* h);
+int p2p_exchange(pinn_t* h, bool adam, double lr, double b1, double b2, double eps);
 
 pinn::NetDesc net_desc(const pinn_t* h) {
   pinn::NetDesc nd{};
@@ -199,8 +209,15 @@ int ensure_points(pinn_t* h, long long need_d, long long need_c) {
   return 0;
 }
 
-int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
+int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false, bool defer_exchange = false) {
   const bool skip_reduce = fused_only;
+  const bool p2p = h->world > 1 && h->p2p_ready && !fused_only;
+  if (p2p) {
+    ++h->p2p_seq;                                               // this evaluation's sequence number / slot
+    h->reduce_dst = h->d_xchg + (size_t)(h->p2p_seq & 1) * h->xchg_len;
+  } else {
+    h->reduce_dst = h->d_R;
+  }
   if (h->kernel_kind == 2) {
     if (generic_launch_eval(h, run_flag, fused_only)) return -1;
     if (fused_only) return 0;
@@ -245,7 +262,7 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
     map.n_out = map.p_net + map.n_extra;
     h->last_map = map; h->last_grid = grid; h->last_stride = B::PSTRIDE;
     if (skip_reduce) return 0;
-    pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, B::PSTRIDE, h->d_R, map, run_flag);
+    pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, B::PSTRIDE, h->reduce_dst, map, run_flag);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   } else {
@@ -253,11 +270,32 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false) {
     if (fused_only) return 0;
   }
   if (h->world > 1) {
-    // one allreduce over [gradient | loss parts].  A skipped evaluation (L-BFGS stopped) still
-    // joins the collective with stale but rank-identical participation so that ranks never diverge.
-    int rc = g_nccl.AllReduce(h->d_R, h->d_R, (size_t)h->P + 3, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
-    if (rc != 0) return fail(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    // one exchange over [gradient | loss parts].  A skipped evaluation (L-BFGS stopped) still takes part
+    // with stale but rank-identical participation so that ranks never diverge.
+    if (h->p2p_ready) {
+      if (!defer_exchange && p2p_exchange(h, false, 0, 0, 0, 0)) return -1;
+    } else {
+      int rc = g_nccl.AllReduce(h->d_R, h->d_R, (size_t)h->P + 3, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+      if (rc != 0) return fail(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    }
   }
+  return 0;
+}
+
+// The local reduction of this evaluation has been enqueued into the exchange slot: publish it and run the fused
+// gather-reduce(-Adam) kernel over peer memory.
+int p2p_exchange(pinn_t* h, bool adam, double lr, double b1, double b2, double eps) {
+  const int n = h->P + 3;
+  const unsigned long long seq = h->p2p_seq;
+  const int slot = (int)(seq & 1);
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(h->d_xchg + 2 * (size_t)h->xchg_len);
+  pinn::p2p_publish<<<1, 1, 0, h->stream>>>(flags + slot, seq);
+  CUDA_TRY(cudaGetLastError());
+  pinn::p2p_gather_reduce<<<(n + 255) / 256, 256, 0, h->stream>>>(h->peers, slot, h->xchg_len, seq, n, h->d_R, h->d_p2p_err,
+                                                                  adam ? 1 : 0, h->d_w, h->d_m, h->d_v, h->P, h->d_step, lr, b1,
+                                                                  b2, eps, h->d_loss_ring, LOSS_RING);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 2;
   return 0;
 }
 
@@ -336,7 +374,7 @@ int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
   map.n_out = map.p_net + map.n_extra;
   h->last_map = map; h->last_grid = grid; h->last_stride = h->pstride;
   if (fused_only) return 0;
-  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, h->pstride, h->d_R, map, run_flag);
+  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, h->pstride, h->reduce_dst, map, run_flag);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return 0;
@@ -407,7 +445,7 @@ int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
   map.n_out = map.p_net + map.n_extra;
   h->last_map = map; h->last_grid = grid; h->last_stride = N::PSTRIDE;
   if (fused_only) return 0;
-  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, N::PSTRIDE, h->d_R, map, run_flag);
+  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, N::PSTRIDE, h->reduce_dst, map, run_flag);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return 0;
@@ -419,6 +457,49 @@ extern "C" {
 
 const char* pinn_last_error(void) { return g_err.c_str(); }
 const char* pinn_version(void) { return "pinn_b200 0.1 (sm_100a, fp64 DMMA)"; }
+
+int pinn_p2p_export(pinn_t* h, void* out64) {
+  if (!h || !out64) return fail("pinn_p2p_export: null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->d_xchg) {
+    h->xchg_len = ((h->P + 3 + 15) / 16) * 16;
+    const size_t bytes = (size_t)2 * h->xchg_len * 8 + 64;
+    CUDA_TRY(cudaMalloc((void**)&h->d_xchg, bytes));
+    CUDA_TRY(cudaMemset(h->d_xchg, 0, bytes));
+    CUDA_TRY(cudaMalloc((void**)&h->d_p2p_err, 4));
+    CUDA_TRY(cudaMemset(h->d_p2p_err, 0, 4));
+  }
+  cudaIpcMemHandle_t hd;
+  CUDA_TRY(cudaIpcGetMemHandle(&hd, h->d_xchg));
+  static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(out64, &hd, 64);
+  return 0;
+}
+
+int pinn_p2p_connect(pinn_t* h, const void* handles, int world) {
+  if (!h || !handles) return fail("pinn_p2p_connect: null argument");
+  if (world != h->world || world < 2 || world > pinn::P2P_MAX) return fail("pinn_p2p_connect: world must match pinn_create (2..8)");
+  if (!h->d_xchg) return fail("pinn_p2p_connect: call pinn_p2p_export first");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->peers.world = world; h->peers.rank = h->rank;
+  for (int r = 0; r < world; r++) {
+    void* base = nullptr;
+    if (r == h->rank) {
+      base = h->d_xchg;
+    } else {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, (const char*)handles + (size_t)r * 64, 64);
+      cudaError_t e = cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e)); }
+      h->peer_base[r] = base;
+    }
+    h->peers.buf[r] = (const double*)base;
+    h->peers.flag[r] = reinterpret_cast<const unsigned long long*>((const double*)base + 2 * (size_t)h->xchg_len);
+  }
+  h->p2p_ready = true;
+  h->p2p_seq = 0;
+  return 0;
+}
 
 int pinn_nccl_unique_id(void* out128) {
   std::string why;
@@ -546,6 +627,9 @@ int pinn_destroy(pinn_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int r = 0; r < pinn::P2P_MAX; r++) if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+  if (h->d_xchg) cudaFree(h->d_xchg);
+  if (h->d_p2p_err) cudaFree(h->d_p2p_err);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   double* bufs[] = {h->d_w, h->d_R, h->d_partials, h->d_m, h->d_v, h->d_loss_ring, h->d_x, h->d_t, h->d_u, h->d_scrH, h->d_scrA, h->d_scrS, h->d_gH, h->d_gA, h->d_gS, h->d_irk, h->d_gold,
                     h->d_d, h->d_S, h->d_Y, h->d_xfinal, h->d_fhist, h->d_px, h->d_pout};
@@ -744,6 +828,10 @@ int pinn_adam_step(pinn_t* h, double lr, double b1, double b2, double eps, doubl
                                                                     h->d_loss_ring, LOSS_RING);
     CUDA_TRY(cudaGetLastError());
     h->launches += 1;
+  } else if (h->p2p_ready) {
+    // fused kernel + local reduction, then ONE kernel: wait for the peers, P2P gather-reduce over NVLink, Adam
+    if (launch_eval(h, nullptr, false, true)) return -1;
+    if (p2p_exchange(h, true, lr, b1, b2, eps)) return -1;
   } else {
     if (launch_eval(h, nullptr)) return -1;      // fused + reduce + allreduce
     pinn::adam_update<<<(h->P + 127) / 128, 128, 0, h->stream>>>(h->d_w, h->d_m, h->d_v, h->d_R, h->P, h->d_step, lr, b1, b2,
@@ -946,6 +1034,11 @@ int pinn_sync(pinn_t* h) {
   if (!h) return fail("null handle");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->p2p_ready) {
+    int e = 0;
+    CUDA_TRY(cudaMemcpy(&e, h->d_p2p_err, 4, cudaMemcpyDeviceToHost));
+    if (e) return fail("P2P exchange timed out waiting for a peer rank (a rank died or the evaluation counts diverged)");
+  }
   return 0;
 }
 

@@ -27,6 +27,8 @@ SIGNATURES = {
                               C.c_int, C.c_void_p]),
     "pinn_destroy": (C.c_int, [C.c_void_p]),
     "pinn_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "pinn_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pinn_p2p_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pinn_num_params": (C.c_int64, [C.c_void_p]),
     "pinn_set_pde_params": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "pinn_set_irk": (C.c_int, [C.c_void_p, _dp, C.c_int]),
@@ -126,6 +128,17 @@ class Pinn(object):
             self.close()
         except Exception:
             pass
+
+    # ---- fused NVLink P2P exchange (multi-GPU)
+    def p2p_export(self):
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.pinn_p2p_export(self.h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def p2p_connect(self, handles):
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        self._ck(self.lib.pinn_p2p_connect(self.h, C.cast(buf, C.c_void_p), len(handles)))
 
     # ---- problem definition
     def set_pde_params(self, params):

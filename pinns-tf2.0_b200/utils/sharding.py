@@ -28,3 +28,15 @@ def exchange_nccl_uid(dist, rank, make_uid):
     box = [make_uid() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     return box[0]
+
+
+def connect_p2p(dist, pinn, world):
+    """All-gather the ranks' IPC handles through the control plane and map the peers' exchange buffers (fused NVLink P2P
+    gather-reduce-Adam instead of ncclAllReduce).  Set PINN_COLLECTIVE=nccl to keep the NCCL path."""
+    if world < 2 or os.environ.get("PINN_COLLECTIVE", "p2p") == "nccl":
+        return False
+    handles = [None] * world
+    dist.all_gather_object(handles, pinn.p2p_export())
+    pinn.p2p_connect(handles)
+    dist.barrier()
+    return True

@@ -33,6 +33,7 @@ def main():
     w = np.load(os.path.join(ROOT, "tests", "golden", "burgers_inf.npz"))["w"]
     lo, hi = sharding.shard_rows(n_f, rank, world)
     p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, layers, lb, ub, device=local_rank, rank=rank, world=world, nccl_uid=uid)
+    used_p2p = sharding.connect_p2p(dist, p, world)
     p.set_pde_params([0.01 / np.pi])
     p.set_collocation(X_f[lo:hi, 0], X_f[lo:hi, 1], n_global=n_f)
     p.set_data(X_u, u, weight=sharding.data_weight(rank))
@@ -57,7 +58,7 @@ def main():
     dist.all_gather(ws, wt)
     assert all(torch.equal(ws[0], x) for x in ws)
     if rank == 0:
-        print(f"mgpu_check ok: world={world} loss={lN:.12e} rel_grad={rel(gN, g1):.1e} lbfgs_iters={rN['n_iter']}")
+        print(f"mgpu_check ok: p2p={used_p2p} world={world} loss={lN:.12e} rel_grad={rel(gN, g1):.1e} lbfgs_iters={rN['n_iter']}")
     dist.barrier()
     p.close(); s.close()
     dist.destroy_process_group()
