@@ -343,11 +343,18 @@ def main():
         barrier()
         launches = p.launch_count() - l0          # kernels of this library launched inside the timed region
         wall = time.perf_counter() - t_wall0
-        # keep the sampler alive for at least ~1.5 s of load so that it sees clocks under load
-        t_end = time.perf_counter() + max(0.0, 1.5 - wall)
-        while time.perf_counter() < t_end:
+        # keep the sampler alive for at least ~1.5 s of load so that it sees clocks under load.  The number of extra steps
+        # is decided by rank 0 and broadcast: every rank MUST execute the same number of exchanges (a time-based loop per
+        # rank deadlocks the collective as soon as the counts differ).
+        extra = int(max(0.0, 1.5 - wall) / max(wall / args.steps, 1e-5)) + 1
+        if dist is not None:
+            te = torch.tensor([extra], dtype=torch.int64)
+            dist.broadcast(te, src=0)
+            extra = int(te.item())
+        for _ in range(extra):
             p.adam_step(ADAM_LR, sync=False)
-            p.sync()
+        p.sync()
+        barrier()
     ms_steps = [p.event_elapsed_ms(2 * i, 2 * i + 1) for i in range(args.steps)]
     ms_step = float(np.mean(ms_steps))
     # launches inside the timed region: world == 1: fused + reduce_adam; world > 1: fused + reduce (+ NCCL) + adam
@@ -440,9 +447,12 @@ def main():
             line["extras"] = extras
         print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.barrier()
+        barrier()
         p.close()
+        dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)          # no lingering helper threads: the next launch on this box must find the GPUs and ports free
 
 
 if __name__ == "__main__":

@@ -37,20 +37,41 @@ struct ReduceMap {
 
 // 8 lanes per output entry: coalesced 64-byte... each lane sums every 8th CTA partial, then a 3-step shuffle
 // tree in fixed order (deterministic).  blockDim = 256 -> 32 entries per block.
+// Optional publication for the P2P exchange: the LAST block to finish makes the reduced vector visible system-wide and
+// raises this rank's flag (saves a separate one-thread launch).  pub_counter must be zero on entry and is reset.
+struct Publish {
+  unsigned long long* flag;     // nullptr: no publication
+  unsigned long long seq;
+  int* counter;
+};
+
 __global__ void reduce_partials(const double* __restrict__ partials, int n_cta, int stride, double* __restrict__ R,
-                                ReduceMap map, const int* __restrict__ run_flag) {
-  if (run_flag && *run_flag != 0) return;
+                                ReduceMap map, const int* __restrict__ run_flag, Publish pub) {
+  const bool skip = run_flag && *run_flag != 0;      // a skipped evaluation still publishes (ranks must not diverge)
   const int sub = threadIdx.x & 7;
   const int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
   const bool ok = i < map.n_out;
   const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
   double s = 0.0;
-  if (ok)
+  if (ok && !skip)
     for (int b = sub; b < n_cta; b += 8) s += partials[(size_t)b * stride + src];
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (ok && sub == 0) R[i] = s;
+  if (ok && sub == 0 && !skip) R[i] = s;
+  if (pub.flag) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int done = atomicAdd(pub.counter, 1);
+      if (done == (int)gridDim.x - 1) {
+        *pub.counter = 0;
+        __threadfence_system();
+        *(volatile unsigned long long*)pub.flag = pub.seq;
+        __threadfence_system();
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

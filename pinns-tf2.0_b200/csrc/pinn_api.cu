@@ -135,6 +135,8 @@ struct pinn_handle {
   pinn::P2PPeers peers{};
   void* peer_base[pinn::P2P_MAX] = {nullptr};
   unsigned long long p2p_seq = 0;
+  pinn::Publish pub{};                 // publication request for the reduction that is about to be enqueued
+  int* d_pub_counter = nullptr;
   double* reduce_dst = nullptr;        // where reduce_partials writes: d_R, or this evaluation's exchange slot
   int* d_p2p_err = nullptr;
 };
@@ -212,9 +214,14 @@ int ensure_points(pinn_t* h, long long need_d, long long need_c) {
 int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false, bool defer_exchange = false) {
   const bool skip_reduce = fused_only;
   const bool p2p = h->world > 1 && h->p2p_ready && !fused_only;
+  h->pub = pinn::Publish{};
   if (p2p) {
     ++h->p2p_seq;                                               // this evaluation's sequence number / slot
-    h->reduce_dst = h->d_xchg + (size_t)(h->p2p_seq & 1) * h->xchg_len;
+    const int slot = (int)(h->p2p_seq & 1);
+    h->reduce_dst = h->d_xchg + (size_t)slot * h->xchg_len;
+    h->pub.flag = reinterpret_cast<unsigned long long*>(h->d_xchg + 2 * (size_t)h->xchg_len) + slot;
+    h->pub.seq = h->p2p_seq;
+    h->pub.counter = h->d_pub_counter;
   } else {
     h->reduce_dst = h->d_R;
   }
@@ -262,7 +269,7 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false, bool de
     map.n_out = map.p_net + map.n_extra;
     h->last_map = map; h->last_grid = grid; h->last_stride = B::PSTRIDE;
     if (skip_reduce) return 0;
-    pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, B::PSTRIDE, h->reduce_dst, map, run_flag);
+    pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, B::PSTRIDE, h->reduce_dst, map, run_flag, h->pub);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
   } else {
@@ -288,14 +295,11 @@ int p2p_exchange(pinn_t* h, bool adam, double lr, double b1, double b2, double e
   const int n = h->P + 3;
   const unsigned long long seq = h->p2p_seq;
   const int slot = (int)(seq & 1);
-  unsigned long long* flags = reinterpret_cast<unsigned long long*>(h->d_xchg + 2 * (size_t)h->xchg_len);
-  pinn::p2p_publish<<<1, 1, 0, h->stream>>>(flags + slot, seq);
-  CUDA_TRY(cudaGetLastError());
   pinn::p2p_gather_reduce<<<(n + 255) / 256, 256, 0, h->stream>>>(h->peers, slot, h->xchg_len, seq, n, h->d_R, h->d_p2p_err,
                                                                   adam ? 1 : 0, h->d_w, h->d_m, h->d_v, h->P, h->d_step, lr, b1,
                                                                   b2, eps, h->d_loss_ring, LOSS_RING);
   CUDA_TRY(cudaGetLastError());
-  h->launches += 2;
+  h->launches += 1;
   return 0;
 }
 
@@ -374,7 +378,7 @@ int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
   map.n_out = map.p_net + map.n_extra;
   h->last_map = map; h->last_grid = grid; h->last_stride = h->pstride;
   if (fused_only) return 0;
-  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, h->pstride, h->reduce_dst, map, run_flag);
+  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, h->pstride, h->reduce_dst, map, run_flag, h->pub);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return 0;
@@ -445,7 +449,7 @@ int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
   map.n_out = map.p_net + map.n_extra;
   h->last_map = map; h->last_grid = grid; h->last_stride = N::PSTRIDE;
   if (fused_only) return 0;
-  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, N::PSTRIDE, h->reduce_dst, map, run_flag);
+  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, N::PSTRIDE, h->reduce_dst, map, run_flag, h->pub);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return 0;
@@ -468,6 +472,8 @@ int pinn_p2p_export(pinn_t* h, void* out64) {
     CUDA_TRY(cudaMemset(h->d_xchg, 0, bytes));
     CUDA_TRY(cudaMalloc((void**)&h->d_p2p_err, 4));
     CUDA_TRY(cudaMemset(h->d_p2p_err, 0, 4));
+    CUDA_TRY(cudaMalloc((void**)&h->d_pub_counter, 4));
+    CUDA_TRY(cudaMemset(h->d_pub_counter, 0, 4));
   }
   cudaIpcMemHandle_t hd;
   CUDA_TRY(cudaIpcGetMemHandle(&hd, h->d_xchg));
@@ -630,6 +636,7 @@ int pinn_destroy(pinn_t* h) {
   for (int r = 0; r < pinn::P2P_MAX; r++) if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
   if (h->d_xchg) cudaFree(h->d_xchg);
   if (h->d_p2p_err) cudaFree(h->d_p2p_err);
+  if (h->d_pub_counter) cudaFree(h->d_pub_counter);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   double* bufs[] = {h->d_w, h->d_R, h->d_partials, h->d_m, h->d_v, h->d_loss_ring, h->d_x, h->d_t, h->d_u, h->d_scrH, h->d_scrA, h->d_scrS, h->d_gH, h->d_gA, h->d_gS, h->d_irk, h->d_gold,
                     h->d_d, h->d_S, h->d_Y, h->d_xfinal, h->d_fhist, h->d_px, h->d_pout};
