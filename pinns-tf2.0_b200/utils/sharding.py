@@ -32,8 +32,10 @@ def exchange_nccl_uid(dist, rank, make_uid):
 
 def connect_p2p(dist, pinn, world):
     """All-gather the ranks' IPC handles through the control plane and map the peers' exchange buffers (fused NVLink P2P
-    gather-reduce-Adam instead of ncclAllReduce).  Set PINN_COLLECTIVE=nccl to keep the NCCL path."""
-    if world < 2 or os.environ.get("PINN_COLLECTIVE", "p2p") == "nccl":
+    gather-reduce-Adam instead of ncclAllReduce).  Opt-in with PINN_COLLECTIVE=p2p: measured on 2xB200 it is correct
+    (tests/mgpu_check.py) but not faster than NCCL's low-latency allreduce for this 24 KB message (0.488-0.536 ms vs
+    0.484-0.486 ms per step), so NCCL is the default."""
+    if world < 2 or os.environ.get("PINN_COLLECTIVE", "nccl") != "p2p":
         return False
     handles = [None] * world
     dist.all_gather_object(handles, pinn.p2p_export())
