@@ -138,6 +138,27 @@ def measure_extras(pinn_cabi, n_f):
         p.close()
     except Exception as e:  # pragma: no cover
         out["schrodinger"] = {"error": str(e)}
+    try:
+        q = 500
+        L = [1, 50, 50, 50, q + 1]
+        rng = np.random.default_rng(11)
+        from neuralnetwork import _glorot_normal
+        x0 = rng.uniform(-1, 1, (250, 1)); u0 = -np.sin(np.pi * x0)
+        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_DISC, L, [-1.0], [1.0])
+        p.set_pde_params([NU, 0.8]); p.set_irk(rng.standard_normal((q + 1, q)) / q); p.set_boundary(np.array([-1.0, 1.0]))
+        p.set_data(x0, u0); p.set_weights(_glorot_normal(L, np.random.default_rng(1234)))
+        for _ in range(5):
+            p.adam_step(1e-3, eps=1e-8, sync=False)
+        p.sync(); t0 = time.perf_counter()
+        for _ in range(50):
+            p.adam_step(1e-3, eps=1e-8, sync=False)
+        p.sync(); dt = (time.perf_counter() - t0) / 50
+        out["burgers_discrete_time"] = {"config": "1d-burgers/inf_disc_burgers.py: [1,50,50,50,501], N=250 + 2 boundary points, q=500 "
+                                                  "(synthetic stage matrix), generic fused kernel", "ms_per_step": dt * 1e3,
+                                        "points_per_s": 250 / dt}
+        p.close()
+    except Exception as e:  # pragma: no cover
+        out["burgers_discrete_time"] = {"error": str(e)}
     return out
 
 

@@ -233,7 +233,7 @@ template <int EPT, int LB_THREADS>
 __global__ void __launch_bounds__(LB_THREADS, 1)
 lbfgs_iterate(LbfgsState* __restrict__ st, double* __restrict__ w, const double* __restrict__ R, int P,
               double* __restrict__ g_old, double* __restrict__ d, double* __restrict__ S, double* __restrict__ Y,
-              double* __restrict__ x_final, double* __restrict__ f_hist, int* __restrict__ logged, int finalize_only) {
+              double* __restrict__ x_final, double* __restrict__ f_hist, int* __restrict__ logged) {
   __shared__ double red[64];
   __shared__ double ro[128], al[128];
   int red_phase = 0;
@@ -287,7 +287,6 @@ lbfgs_iterate(LbfgsState* __restrict__ st, double* __restrict__ w, const double*
     __syncthreads();
     if (status != 0) return;
   }
-  if (finalize_only) return;
 
   // ---- (b) direction
   const int n_iter = st->n_iter + 1;

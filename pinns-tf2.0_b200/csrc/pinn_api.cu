@@ -928,10 +928,10 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
   std::vector<double> fh(max_iter + 2);
   std::vector<int> lg(max_iter + 2);
   int reported = 0;
-  auto iterate = [&](int fin) -> int {
+  auto iterate = [&]() -> int {
 #define LB_LAUNCH(E, NT)                                                                                       \
   pinn::lbfgs_iterate<E, NT><<<1, NT, 0, h->stream>>>(h->d_lb, h->d_w, h->d_R, P, h->d_gold, h->d_d, h->d_S, h->d_Y, \
-                                                      h->d_xfinal, h->d_fhist, h->d_logged, fin)
+                                                      h->d_xfinal, h->d_fhist, h->d_logged)
     if (P <= 12 * 256) LB_LAUNCH(12, 256);        // Burgers-size vectors: 8 warps, 12 entries per thread
     else if (P <= 8 * 1024) LB_LAUNCH(8, 1024);
     else LB_LAUNCH(32, 1024);
@@ -942,7 +942,7 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
   };
   while (true) {
     for (int b = 0; b < sync_every; b++) {
-      if (iterate(0)) return -1;
+      if (iterate()) return -1;
       if (launch_eval(h, run_flag)) return -1;
     }
     CUDA_TRY(cudaMemcpyAsync(&st, h->d_lb, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
