@@ -231,7 +231,7 @@ def time_reference_port(n_f, steps, warmup, seed=1234):
         ncpu = len(os.sched_getaffinity(0))
     except Exception:
         ncpu = os.cpu_count() or 1
-    Xc, Xuc, uc = synthetic_problem(seed + 1, 4000)
+    Xc, Xuc, uc = synthetic_problem(seed + 1, max(2000, n_f // 4))
     pbc = rp.BurgersInference(LAYERS, LB, UB, NU, Xc, Xuc, uc)
     wc = init_weights()
     best_t, best_n = None, 1
@@ -240,12 +240,14 @@ def time_reference_port(n_f, steps, warmup, seed=1234):
             break
         torch.set_num_threads(cand)
         rp.loss_and_flat_grad(pbc, wc)
-        t0 = time.perf_counter()
-        rp.loss_and_flat_grad(pbc, wc)
-        dt = time.perf_counter() - t0
+        dt = 1e30
+        for _ in range(3):                       # best of three: a single timing is too noisy to rank thread counts
+            t0 = time.perf_counter()
+            rp.loss_and_flat_grad(pbc, wc)
+            dt = min(dt, time.perf_counter() - t0)
         if best_t is None or dt < best_t:
             best_t, best_n = dt, cand
-        elif dt > 1.5 * best_t:
+        elif dt > 2.0 * best_t:
             break
     torch.set_num_threads(best_n)
     X_f, X_u, u = synthetic_problem(seed, n_f)
