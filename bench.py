@@ -250,6 +250,12 @@ def time_reference_port(n_f, steps, warmup, seed=1234):
         elif dt > 2.0 * best_t:
             break
     torch.set_num_threads(best_n)
+    # bounded sample: keep the whole (warmup + steps) run within ~2.5 minutes whatever --steps the caller passes; throughput
+    # in points/s is nearly size-independent at these sizes (1.5e5 - 3e5 pts/s from N_f = 1e4 to 1e5)
+    est_step = best_t * n_f / max(1, Xc.shape[0])
+    budget_s = 110.0
+    if est_step * (steps + warmup) > budget_s:
+        n_f = max(2000, int(n_f * budget_s / (est_step * (steps + warmup))))
     X_f, X_u, u = synthetic_problem(seed, n_f)
     pb = rp.BurgersInference(LAYERS, LB, UB, NU, X_f, X_u, u)
     w = init_weights()
@@ -261,23 +267,23 @@ def time_reference_port(n_f, steps, warmup, seed=1234):
         w = rp.adam_update(w, g, st, ADAM_LR)
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
-    return float(np.mean(ts)), torch.get_num_threads(), f
+    return float(np.mean(ts)), torch.get_num_threads(), f, n_f
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     n_f = N_F_PER_GPU
-    sec, cores, _ = time_reference_port(n_f, args.steps, args.warmup)
-    val = n_f / sec
+    sec, cores, _, n_used = time_reference_port(n_f, args.steps, args.warmup)
+    val = n_used / sec
     line = {
         "impl": "reference", "metric": "collocation-points/sec per training step (1D Burgers 8x20 tanh, Adam step)",
         "value": val, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "1d-burgers inf_cont [2,20x8,1] tanh, N_f=100000 per step sample, N_u=100, Adam lr 1e-3 (BASELINE configs[1])"},
+        "config": {"workload": "1d-burgers inf_cont [2,20x8,1] tanh, N_f=%d per step sample, N_u=100, Adam lr 1e-3 (BASELINE configs[1])" % n_used},
         "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} Adam steps of N_f={n_f} after {args.warmup} warm-up, oracle/reference_port.py "
+                         "sample": f"{args.steps} Adam steps of N_f={n_used} after {args.warmup} warm-up, oracle/reference_port.py "
                                    "(TF-free restatement; TensorFlow 2.0 is not installable here)"},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -446,9 +452,9 @@ def main():
         extras = measure_extras(pinn_cabi, n_f)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, cores, _ = time_reference_port(n_f, 12, 3)
-        cpu = {"value": n_f / sec, "unit": "points/s", "cores": cores, "kind": "port",
-               "sample": f"12 Adam steps of N_f={n_f} after 3 warm-up, oracle/reference_port.py (nested reverse-mode, torch CPU fp64)"}
+        sec, cores, _, n_used = time_reference_port(n_f, 12, 3)
+        cpu = {"value": n_used / sec, "unit": "points/s", "cores": cores, "kind": "port",
+               "sample": f"12 Adam steps of N_f={n_used} after 3 warm-up, oracle/reference_port.py (nested reverse-mode, torch CPU fp64)"}
 
     if rank == 0:
         line = {
