@@ -318,6 +318,9 @@ def main():
     dist = None
     uid = None
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner off it unless debug output was asked for
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         # Control plane (uid exchange, barriers, max over ranks) on gloo: the ONLY NCCL communicator in this process is
