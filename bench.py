@@ -463,8 +463,8 @@ def main():
         line = {
             "metric": "collocation-points/sec per training step (1D Burgers 8x20 tanh, Adam step)",
             "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
+            "ms_per_step": ms_step, "ms_per_step_median": float(np.median(ms_steps)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "1d-burgers inf_cont [2,20x8,1] tanh, N_f=%d per GPU (%d global), N_u=100, Adam lr 1e-3 "
                                    "(BASELINE configs[1])" % (n_f, n_f_global),
                        "l2": "flushed (256 MB memset) between timed iterations; inputs are 1.6 MB, the path is compute-bound",

@@ -77,6 +77,9 @@ int64_t pinn_num_params(const pinn_t* h);
 /* PDE constants.  BURGERS_INF: p[0] = nu (inf_cont_burgers.py:52,111).  BURGERS_DISC: p = [nu, dt]
  * (inf_disc_burgers.py:53-54).  Others take none. */
 int pinn_set_pde_params(pinn_t* h, const double* p, int n);
+/* get_params(numpy=True): BURGERS_INF -> [nu] (inf_cont_burgers.py:92-93); BURGERS_IDE -> [lambda_1, exp(lambda_2)]
+ * read from the trained flat vector (ide_cont_burgers.py:109-114); BURGERS_DISC -> [nu, dt]. */
+int pinn_get_params(pinn_t* h, double* p, int n);
 /* BURGERS_DISC: the implicit Runge-Kutta stage matrix IRK_weights, (q+1) x q row-major (inf_disc_burgers.py:56,86);
  * q+1 must equal the network's output width. */
 int pinn_set_irk(pinn_t* h, const double* irk, int q);

@@ -671,6 +671,31 @@ int pinn_set_pde_params(pinn_t* h, const double* p, int n) {
   return 0;
 }
 
+int pinn_get_params(pinn_t* h, double* p, int n) {
+  if (!h || !p) return fail("pinn_get_params: null argument");
+  if (h->pde == PINN_BURGERS_INF) {
+    if (n != 1) return fail("pinn_get_params: BURGERS_INF has one parameter (nu)");
+    p[0] = h->nu;                                   // inf_cont_burgers.py:92-93
+    return 0;
+  }
+  if (h->pde == PINN_BURGERS_IDE) {
+    if (n != 2) return fail("pinn_get_params: BURGERS_IDE has two parameters (lambda_1, exp(lambda_2))");
+    CUDA_TRY(cudaSetDevice(h->device));
+    double lam[2];
+    CUDA_TRY(cudaMemcpyAsync(lam, h->d_w + h->P_net, 16, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    p[0] = lam[0]; p[1] = std::exp(lam[1]);         // ide_cont_burgers.py:109-114
+    return 0;
+  }
+  if (h->pde == PINN_BURGERS_DISC) {
+    if (n != 2) return fail("pinn_get_params: BURGERS_DISC has two constants (nu, dt)");
+    p[0] = h->nu; p[1] = h->dt;
+    return 0;
+  }
+  if (n != 0) return fail("pinn_get_params: this PDE has no parameters");
+  return 0;
+}
+
 int pinn_set_irk(pinn_t* h, const double* irk, int q) {
   if (!h || !irk) return fail("pinn_set_irk: null argument");
   if (h->pde != PINN_BURGERS_DISC) return fail("pinn_set_irk: only the discrete-time model has a stage matrix");

@@ -31,6 +31,7 @@ SIGNATURES = {
     "pinn_p2p_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pinn_num_params": (C.c_int64, [C.c_void_p]),
     "pinn_set_pde_params": (C.c_int, [C.c_void_p, _dp, C.c_int]),
+    "pinn_get_params": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "pinn_set_irk": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "pinn_set_collocation": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64]),
     "pinn_set_collocation_mapped": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64]),
@@ -144,6 +145,12 @@ class Pinn(object):
     def set_pde_params(self, params):
         a = _arr(params).reshape(-1)
         self._ck(self.lib.pinn_set_pde_params(self.h, _p(a), a.size))
+
+    def get_params(self):
+        n = {BURGERS_INF: 1, BURGERS_IDE: 2, NLS_INF: 0, BURGERS_DISC: 2}[self.pde]
+        out = np.zeros(max(n, 1))
+        self._ck(self.lib.pinn_get_params(self.h, _p(out), n))
+        return out[:n]
 
     def set_irk(self, irk):
         irk = _arr(irk)

@@ -101,6 +101,7 @@ def test_identification_matches_golden(cabi):
         assert abs(loss - g[fk]) <= 1e-10 * abs(g[fk])
         assert rel(grad, g[gk]) < 1e-10
         assert rel(grad[-2:], g[gk][-2:]) < 1e-9
+        assert np.allclose(p.get_params(), [g[wk][-2], np.exp(g[wk][-1])], rtol=1e-15)      # (lambda_1, exp(lambda_2))
     p.set_weights(g["w"])
     losses = [p.adam_step(1e-3) for _ in range(5)]
     assert rel(losses, g["adam_losses"]) < 1e-8 and rel(p.get_weights(), g["adam_w"]) < 1e-8
