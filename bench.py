@@ -318,9 +318,9 @@ def main():
     dist = None
     uid = None
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner off it unless debug output was asked for
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: NCCL's version banner (printed at VERSION and WARN level) and any other
+        # NCCL debug output go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         # Control plane (uid exchange, barriers, max over ranks) on gloo: the ONLY NCCL communicator in this process is
