@@ -1,0 +1,85 @@
+"""CPU: bench.py's host logic end to end against a FAKE backend (no GPU, no oracle timing): argument handling, the timed
+loops, the e2e modes, extras and the JSON contract (one line, required keys).  The fake only counts calls and returns
+plausible numbers; nothing here measures anything."""
+import ctypes as C
+import io
+import json
+import os
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+
+from conftest import ROOT
+
+
+class FakePinn(object):
+    instances = []
+
+    def __init__(self, pde, layers, lb, ub, device=0, rank=0, world=1, nccl_uid=None):
+        self.pde, self.layers, self.launches, self.events = pde, list(layers), 0, {}
+        self.P = sum(a * b + b for a, b in zip(layers[:-1], layers[1:])) + (2 if pde == 1 else 0)
+        FakePinn.instances.append(self)
+
+    def _noop(self, *a, **k):
+        return None
+
+    set_pde_params = set_data = set_collocation = set_collocation_ptr = set_collocation_mapped = _noop
+    set_weights = set_boundary = set_irk = sync = flush_l2 = close = _noop
+
+    def adam_step(self, lr, b1=0.9, b2=0.999, eps=1e-7, sync=True):
+        self.launches += 2
+        return 0.5 if sync else None
+
+    def event_record(self, idx):
+        self.events[idx] = True
+
+    def event_elapsed_ms(self, i, j):
+        assert i in self.events and j in self.events
+        return 0.46
+
+    def launch_count(self):
+        return self.launches
+
+    def time_kernel_ms(self, iters):
+        return 0.445 * iters
+
+    def kernel_info(self):
+        return {"grid": 148, "block": 256, "dyn_smem": 196376, "regs": 252, "local_bytes": 0, "sms": 148}
+
+    def lbfgs(self, max_iter, **k):
+        return {"n_iter": max_iter, "n_eval": max_iter, "reason": 1, "reason_str": "max iterations", "x_final": None}
+
+
+def test_bench_gpu_arm_control_flow_with_fake_backend(monkeypatch):
+    sys.path.insert(0, ROOT)
+    import torch
+    import pinn_cabi
+    import bench
+    monkeypatch.setattr(pinn_cabi, "Pinn", FakePinn)
+    monkeypatch.setattr(pinn_cabi, "host_alloc", lambda n: (np.zeros(n), C.c_void_p(0)))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(bench, "time_reference_port", lambda n_f, steps, warmup, seed=1234: (0.4, 8, 0.1, n_f))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "4", "--warmup", "1"])
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.main()
+    lines = [l for l in buf.getvalue().strip().split("\n") if l]
+    assert len(lines) == 1                                   # exactly one JSON line on stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "extras"):
+        assert key in d, key
+    assert d["warmup"] == 3 and d["steps"] == 4              # warm-up is raised to the minimum of 3
+    assert d["dtype"] == "f64" and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["gpu_launches"] == 2 * 4 and abs(d["ms_per_step"] - 0.46) < 1e-9
+    assert abs(d["value"] - 100000 / 0.46e-3) / d["value"] < 1e-9
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "copy_mode", "mapped_mode"}
+    assert d["e2e"]["h2d_bytes_per_step"] == 1600000 and d["e2e"]["d2h_bytes_per_step"] == 8
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"] > 1e6
+    assert set(d["extras"]) == {"burgers_lbfgs", "burgers_identification", "schrodinger", "burgers_discrete_time"}
+    assert all("error" not in v for v in d["extras"].values())
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 8
