@@ -83,3 +83,44 @@ def test_bench_gpu_arm_control_flow_with_fake_backend(monkeypatch):
     assert set(d["extras"]) == {"burgers_lbfgs", "burgers_identification", "schrodinger", "burgers_discrete_time"}
     assert all("error" not in v for v in d["extras"].values())
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 8
+
+
+def _launch_two(extra_args, tmp_path):
+    import subprocess
+    port = 29600 + os.getpid() % 300
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "bench_fake_worker.py")] + extra_args,
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        try:
+            o, e = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        assert p.returncode == 0, e[-2000:]
+        outs.append(o)
+    return outs
+
+
+def test_bench_two_ranks_gloo(tmp_path):
+    """Both ranks run the same number of steps (the keep-alive count is broadcast), exit 0, and only rank 0 prints."""
+    outs = _launch_two([], tmp_path)
+    assert outs[1].strip() == ""
+    lines = [l for l in outs[0].strip().split("\n") if l]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and "cpu_baseline" not in d and "extras" not in d
+    assert abs(d["value"] - 200000 / 0.46e-3) / d["value"] < 1e-9          # whole-job aggregate over both shards
+    assert "ncclAllReduce" in d["config"]["parallelism"]
+
+
+def test_reference_arm_under_two_ranks_only_rank0_works(tmp_path, monkeypatch):
+    """--impl reference under a 2-rank launch: rank 0 alone runs and prints, the other rank exits 0 without work."""
+    outs = _launch_two(["--impl", "reference", "--steps", "1", "--warmup", "1", "--n-f", "2000"], tmp_path)
+    assert outs[1].strip() == ""
+    d = json.loads(outs[0].strip().split("\n")[-1])
+    assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["value"] == d["value"]
