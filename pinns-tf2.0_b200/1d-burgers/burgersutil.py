@@ -1,6 +1,6 @@
 """Data preparation for the continuous-time Burgers problems (restates 1d-burgers/burgersutil.py:27-36, 63-75, 99-131
-of the reference; the discrete-time/IRK branches are out of scope).  Plot helpers degrade to no-ops when
-matplotlib is missing (cosmetic)."""
+and, for discrete-time inference, :38-60 of the reference).  The plot_* helpers write the run's artefact directory
+(hp.json + fields.npz, figure only when matplotlib exists) through utils/plotting.py."""
 import sys
 
 import numpy as np
@@ -75,8 +75,73 @@ def load_irk(q, utils_path=None):
     return np.reshape(tmp[0:q ** 2 + q], (q + 1, q)), tmp[q ** 2 + q:]
 
 
-def _no_plot(*a, **k):
-    print("(plotting skipped: matplotlib/LaTeX are not part of the training hot path)")
+def _grid(X_star, values, X, T):
+    """Prediction on the (t, x) grid the figure shows: X_star is that grid flattened (prep_data), so a reshape; scattered
+    inputs go through scipy's cubic griddata like the reference (burgersutil.py:136)."""
+    values = np.asarray(values).reshape(-1)
+    if values.size == X.size:
+        return values.reshape(X.shape)
+    from scipy.interpolate import griddata
+    return griddata(X_star, values, (X, T), method="cubic")
 
 
-plot_inf_cont_results = plot_ide_cont_results = plot_inf_disc_results = plot_ide_disc_results = _no_plot
+def _finish(save_path, save_hp, draw, **fields):
+    """Common tail of the plot_* helpers: stage the arrays, draw if matplotlib exists, write the artefact directory."""
+    import plotting
+    plotting.stage_fields(**fields)
+    if plotting.have_matplotlib():
+        try:
+            draw(plotting)
+        except Exception as exc:            # a cosmetic failure must not lose the run's numbers
+            print("(figure skipped: %s)" % exc)
+    if save_path is not None and save_hp is not None:
+        return plotting.saveResultDir(save_path, save_hp)
+    print("(no save_path/save_hp given and no interactive display: nothing written)")
+    return None
+
+
+def _slices(pl, x, exact_rows, pred_rows, titles):
+    fig, _ = pl.newfig(1.0, 1.1)
+    for k, (e, p_, ttl) in enumerate(zip(exact_rows, pred_rows, titles)):
+        ax = fig.add_subplot(1, len(titles), k + 1)
+        ax.plot(x, e, "b-", linewidth=2, label="Exact")
+        if p_ is not None:
+            ax.plot(x, p_, "r--", linewidth=2, label="Prediction")
+        ax.set_xlabel("x"); ax.set_title(ttl, fontsize=10)
+    return fig
+
+
+def plot_inf_cont_results(X_star, u_pred, X_u_train, u_train, Exact_u, X, T, x, t, save_path=None, save_hp=None):
+    U_pred = _grid(X_star, u_pred, X, T)
+    rows = (25, 50, 75)                                   # the three time slices of the reference figure (burgersutil.py:166-196)
+    return _finish(save_path, save_hp,
+                   lambda pl: _slices(pl, x, [Exact_u[r] for r in rows], [U_pred[r] for r in rows], ["t = %.2f" % t[r, 0] for r in rows]),
+                   U_pred=U_pred, Exact_u=Exact_u, x=x, t=t, X_u_train=X_u_train, u_train=u_train, slice_rows=np.array(rows),
+                   rel_l2_error=np.linalg.norm(Exact_u - U_pred) / np.linalg.norm(Exact_u))
+
+
+def plot_ide_cont_results(X_star, u_pred, X_u_train, u_train, Exact_u, X, T, x, t, lambda_1_value, lambda_1_value_noisy,
+                          lambda_2_value, lambda_2_value_noisy, save_path=None, save_hp=None):
+    U_pred = _grid(X_star, u_pred, X, T)
+    rows = (25, 50, 75)
+    return _finish(save_path, save_hp,
+                   lambda pl: _slices(pl, x, [Exact_u[r] for r in rows], [U_pred[r] for r in rows], ["t = %.2f" % t[r, 0] for r in rows]),
+                   U_pred=U_pred, Exact_u=Exact_u, x=x, t=t, X_u_train=X_u_train, u_train=u_train, slice_rows=np.array(rows),
+                   lambdas=np.array([lambda_1_value, lambda_2_value], dtype=float),
+                   lambdas_noisy=np.array([lambda_1_value_noisy, lambda_2_value_noisy], dtype=float),
+                   lambdas_exact=np.array([1.0, 0.01 / np.pi]))
+
+
+def plot_inf_disc_results(x_star, idx_t_0, idx_t_1, x_0, u_0, ub, lb, u_1_pred, Exact_u, x, t, save_path=None, save_hp=None):
+    u_1_pred = np.asarray(u_1_pred).reshape(-1)
+    return _finish(save_path, save_hp,
+                   lambda pl: _slices(pl, x, [Exact_u[idx_t_0], Exact_u[idx_t_1]], [None, u_1_pred],
+                                      ["t = %.2f" % t[idx_t_0, 0], "t = %.2f" % t[idx_t_1, 0]]),
+                   u_1_pred=u_1_pred, Exact_u=Exact_u, x=x, t=t, x_star=x_star, x_0=x_0, u_0=u_0, lb=lb, ub=ub,
+                   idx_t=np.array([idx_t_0, idx_t_1]),
+                   rel_l2_error=np.linalg.norm(Exact_u[idx_t_1] - u_1_pred) / np.linalg.norm(Exact_u[idx_t_1]))
+
+
+def plot_ide_disc_results(*a, **k):
+    raise NotImplementedError("discrete-time identification (ide_disc_burgers.py) is not provided; it is broken as shipped "
+                              "(SURVEY section 2 #11)")

@@ -1,4 +1,5 @@
-"""Data preparation for the NLS problem (restates 1dcomplex-schrodinger/schrodingerutil.py:21-61 of the reference)."""
+"""Data preparation for the NLS problem (restates 1dcomplex-schrodinger/schrodingerutil.py:21-61 of the reference) and the
+run's artefact writer (shares the helpers of 1d-burgers/burgersutil.py)."""
 import importlib.util
 import os
 
@@ -40,5 +41,14 @@ def prep_data(path, N_0, N_b, N_f, noise):
     return x, t, X, T, Exact_u, Exact_v, Exact_h, X_star, u_star, v_star, h_star, X_f, ub, lb, tb, x0, u0, v0, X0, H0
 
 
-def plot_inf_cont_results(*a, **k):
-    print("(plotting skipped: matplotlib/LaTeX are not part of the training hot path)")
+def plot_inf_cont_results(X_star, u_pred, v_pred, h_pred, Exact_h, X, T, x, t, ub, lb, x0, tb, save_path=None, save_hp=None):
+    """Artefacts of the Schrodinger run (reference figure: schrodingerutil.py:63-140): |h| on the (t, x) grid, the three time
+    slices t[75], t[100], t[125], the training point locations; drawn only when matplotlib exists."""
+    U, V, H = (_m._grid(X_star, a, X, T) for a in (u_pred, v_pred, h_pred))
+    rows = (75, 100, 125)
+    X_train = np.vstack([np.concatenate((x0, 0 * x0), 1), np.concatenate((0 * tb + lb[0], tb), 1),
+                         np.concatenate((0 * tb + ub[0], tb), 1)])
+    return _m._finish(save_path, save_hp,
+                      lambda pl: _m._slices(pl, x, [Exact_h[:, r] for r in rows], [H[r] for r in rows], ["t = %.2f" % t[r, 0] for r in rows]),
+                      U_pred=U, V_pred=V, H_pred=H, Exact_h=Exact_h, x=x, t=t, X_train=X_train, slice_rows=np.array(rows),
+                      rel_l2_error_h=np.linalg.norm(Exact_h.T - H) / np.linalg.norm(Exact_h))

@@ -107,6 +107,8 @@ def main(argv):
     wd = prepare_workdir(script)
     for pth in (os.path.join(HERE, "shims"), os.path.join(wd, os.path.basename(os.path.dirname(script)))):
         sys.path.insert(0, pth)
+    # result artefacts (hp.json, fields.npz, figure) land under <launch directory>/<eqn>/results/, not in the scratch directory
+    os.environ.setdefault("PINN_RESULTS_ROOT", os.getcwd())
     os.chdir(wd)
     sys.argv = [script] + argv[2:]
     src = open(script, encoding="utf-8").read()

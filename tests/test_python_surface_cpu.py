@@ -130,3 +130,33 @@ def test_other_reference_scripts_reach_the_gpu_boundary(script):
                        capture_output=True, text=True, timeout=300)
     out = r.stdout + r.stderr
     assert "Training started" in out and "no CUDA device" in out and r.returncode != 0
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_result_artefacts_hp_json_and_fields(tmp_path, monkeypatch):
+    """the plot_* helpers leave <save_path>/results/<timestamp>-<script>/{hp.json, fields.npz} behind, with or
+    without matplotlib (reference: utils/plotting.py:8-16, burgersutil.py:132-203)."""
+    import json
+    import importlib
+    monkeypatch.setenv("PINN_RESULTS_ROOT", str(tmp_path))
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.setattr(sys, "argv", ["inf_cont_burgers.py"])
+    sys.path.insert(0, os.path.join(PKG, "utils"))
+    sys.path.insert(0, os.path.join(PKG, "1d-burgers"))
+    burgersutil = importlib.import_module("burgersutil")
+    np.random.seed(0)
+    x, t, X, T, Exact_u, X_star, u_star, X_u, u_tr, X_f, ub, lb = burgersutil.prep_data(
+        os.path.join(REF, "1d-burgers", "data", "burgers_shock.mat"), 50, 500)
+    hp = {"N_u": 50, "layers": [2, 20, 1], "tf_eps": None, "np_value": np.float64(0.5)}
+    out = burgersutil.plot_inf_cont_results(X_star, u_star.flatten() * 1.01, X_u, u_tr, Exact_u, X, T, x, t,
+                                            save_path="1d-burgers", save_hp=hp)
+    assert out.startswith(os.path.join(str(tmp_path), "1d-burgers", "results")) and out.endswith("-inf_cont_burgers")
+    assert json.load(open(os.path.join(out, "hp.json"))) == {"N_u": 50, "layers": [2, 20, 1], "tf_eps": None, "np_value": 0.5}
+    f = np.load(os.path.join(out, "fields.npz"))
+    assert f["U_pred"].shape == Exact_u.shape == (100, 256)
+    assert abs(float(f["rel_l2_error"]) - 0.01) < 1e-12
+    assert burgersutil.plot_ide_cont_results(X_star, u_star, X_u, u_tr, Exact_u, X, T, x, t, 1.0, 1.0, 0.003, 0.003) is None
+    # non-zero ranks of a multi-process job write nothing
+    monkeypatch.setenv("RANK", "1")
+    assert burgersutil.plot_inf_cont_results(X_star, u_star.flatten(), X_u, u_tr, Exact_u, X, T, x, t,
+                                             save_path="1d-burgers", save_hp=hp) is None
