@@ -1,6 +1,7 @@
 """Restated reference: TF-free fp64 port of the PINNs-TF2.0 training hot path (torch CPU autograd).
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED by the reference itself (no tests).
+TEST INFRASTRUCTURE (see oracle/__init__.py).  The reference has no tests of its own (parity against TensorFlow's kernels is
+UNPINNED); this port is pinned to the reference's own Python executed on an emulated TensorFlow (tests/test_reference_pin.py).
 
 The reference computes u_x, u_t, u_xx with nested ``tf.GradientTape``s and d(loss)/d(params) with an
 outer tape.  This port keeps that *algorithmic structure* -- nested reverse-mode sweeps with

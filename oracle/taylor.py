@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  numpy only; shares no code or derivation with
 ``oracle.reference_port`` (nested autograd).  The two must agree to ~1e-13 -- that agreement is what
-stands in for the golden vectors the reference does not have (PARITY UNPINNED).
+is the independent check of the mathematics; the pin to the reference's own code is tests/golden/reference_run.npz
+(parity against TensorFlow's kernels themselves remains UNPINNED: TF cannot be installed).
 
 Maths.  Input layer (utils/neuralnetwork.py:29-30):
     h = 2(X-lb)/(ub-lb)-1,  h_x = [2/(ub0-lb0), 0],  h_t = [0, 2/(ub1-lb1)],  h_xx = 0

@@ -3,9 +3,10 @@
 Run in the build container (reads the reference's data files; /root/reference does not exist on the GPU box):
     PYTHONPATH=/root/repo python tests/golden/make_golden.py
 
-The reference ships no golden vectors and TensorFlow 2.0 cannot be installed here (PARITY UNPINNED), so the
+The reference ships no golden vectors and TensorFlow 2.0 cannot be installed here (parity against TF's kernels UNPINNED), so the
 vectors come from ``oracle.reference_port`` (nested reverse-mode restatement of the reference) and every
-loss/gradient is cross-checked against the independent ``oracle.taylor`` before it is written.
+loss/gradient is cross-checked against the independent ``oracle.taylor`` before it is written.  make_reference_fixtures.py then
+runs the reference's own Python (on an emulated TensorFlow) over the same inputs and must reproduce these values.
 """
 import os
 import sys
