@@ -258,8 +258,42 @@ def run_burgers_disc(out, dev):
         out["burgers_disc_lbfgs_runs"] = np.array(0)
 
 
+def run_burgers_default_schedule(out, dev):
+    """The reference's default training run (1d-burgers/inf_cont_burgers.py:27-43: N_u=100, N_f=10000, 100 Adam epochs at 0.03,
+    200 fixed-step L-BFGS iterations at 0.8, 50 corrections) through ITS fit(), from the initial weights and data of
+    tests/golden/burgers_accuracy.npz; compared with the oracle's loss curves, final weights and rel. L2 error stored there."""
+    g = np.load(os.path.join(HERE, "burgers_accuracy.npz"))
+    cls = reference_class("1d-burgers/inf_cont_burgers.py", "BurgersInformedNN")
+    hp = hp_for([2] + [20] * 8 + [1], tf_epochs=100, tf_lr=0.03, nt_epochs=200)
+    m = cls(hp, RecordingLogger(hp), g["X_f"], g["ub"], g["lb"], 0.01 / np.pi)
+    m.set_weights(tf.convert_to_tensor(g["w0"], dtype="float64"))
+    quiet_fit(m, g["X_u"], g["u"])
+    adam = np.array([v for _, v in m.logger.tf_losses])
+    lb_log = np.array([v for _, v in m.logger.nt_losses])               # f after iterations 1..199 (the last one is not logged)
+    w = np.asarray(m.get_weights())
+    u_pred, _ = m.predict(g["X_star"].astype(np.float64))
+    err = float(np.linalg.norm(g["u_star"].astype(np.float64) - u_pred) / np.linalg.norm(g["u_star"].astype(np.float64)))
+    out["schedule_adam_losses"], out["schedule_lbfgs_logged_f"], out["schedule_w"], out["schedule_error"] = adam, lb_log, w, err
+    # The fixed-step L-BFGS iteration is chaotic: rounding-level differences between two fp64 implementations of the SAME
+    # algorithm grow about tenfold every ten iterations (1e-16 at iteration 1, 1e-11 at 40, 1e-7 at 80, 1e-3 at 100), so only a
+    # prefix can agree tightly; the end point agrees in magnitude.  The same holds between the CUDA path and the oracle.
+    f_dev = np.abs(lb_log - g["oracle_lbfgs_f"][1:]) / g["oracle_lbfgs_f"][1:]
+    out["schedule_lbfgs_f_deviation"] = f_dev
+    dev["default schedule: 100 Adam losses"] = (rel(adam, g["oracle_adam_losses"]), 1e-13)
+    dev["default schedule: L-BFGS f, iterations 1..40"] = (float(f_dev[:40].max()), 1e-9)
+    dev["default schedule: L-BFGS f, iteration 199 (chaotic tail)"] = (float(f_dev[-1]), 0.25)
+    dev["default schedule: final model weights (chaotic tail)"] = (rel(w, g["oracle_w"]), 0.05)
+    dev["default schedule: rel. L2 error of u %.4f vs %.4f" % (err, float(g["oracle_error"]))] = \
+        (abs(err - float(g["oracle_error"])) / float(g["oracle_error"]), 0.25)
+    return dev
+
+
 def main():
     out, dev = {}, {}
+    sched = run_burgers_default_schedule(out, {})
+    for k, (v, tol) in sched.items():
+        print("%-70s rel. deviation from the oracle's value: %.2e (bound %.0e)" % (k, v, tol))
+        assert v <= tol, k
     for fn in (run_burgers_inf, run_burgers_ide, run_nls, run_burgers_disc):
         fn(out, dev)
     width = max(len(k) for k in dev)
@@ -273,7 +307,8 @@ def main():
         old = np.load(path)
         assert sorted(old.files) == sorted(out), "fixture keys changed"
         for k in out:
-            assert rel(out[k], old[k]) < 1e-12 or np.array_equal(out[k], old[k]), k
+            if k in ("schedule_adam_losses",) or not k.startswith("schedule_"):      # the chaotic tail may differ between machines
+                assert rel(out[k], old[k]) < 1e-12 or np.array_equal(out[k], old[k]), k
         print("committed fixture reproduced")
     else:
         np.savez_compressed(path, **{k: np.asarray(v) for k, v in out.items()})
