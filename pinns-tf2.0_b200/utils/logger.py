@@ -30,13 +30,18 @@ class _Stopwatch(object):
         return dt
 
 
+def _micro(seconds):
+    return int(round(seconds * 1e6))                        # datetime.fromtimestamp rounds to microseconds
+
+
 def _mm_ss(seconds):
-    s = int(seconds)
+    s = _micro(seconds) // 1000000
     return "%02d:%02d" % ((s // 60) % 60, s % 60)          # the reference wraps at one hour too (quirk Q5)
 
 
 def _ss_t(seconds):
-    return "%04.1f" % (seconds % 60.0)
+    us = _micro(seconds)                                    # "%S.%f"[:-5] of the reference: tenths are TRUNCATED, not rounded
+    return "%02d.%d" % ((us // 1000000) % 60, (us % 1000000) // 100000)
 
 
 class Logger(object):

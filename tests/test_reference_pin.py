@@ -211,3 +211,21 @@ def test_reference_default_schedule_run():
     assert dev[-1] > 1e-6                                              # the tail really does diverge
     assert abs(float(r["schedule_error"]) - float(a["oracle_error"])) <= 0.25 * float(a["oracle_error"])
     assert _rel(r["schedule_w"], a["oracle_w"]) <= 0.05
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_logger_prints_what_the_reference_logger_prints():
+    """with the same clock, the mirror's Logger emits the reference Logger's lines character for character
+    (hyper-parameter dump, epoch lines with truncated tenths, `:.4e` losses, end line); only the version banner differs."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "logger_compare_worker.py"), ROOT],
+                       capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert r.returncode == 0 and "logger output identical" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_mirror_host_attributes_equal_the_reference():
+    """sizes_w / sizes_b (incl. the uniform-width assumption, quirk Q7), nt_config, tf_epochs, dtype, get_params and the
+    custom_lbfgs module surface of the mirror equal those of the reference classes built from the same hp."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "surface_compare_worker.py"), ROOT],
+                       capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert r.returncode == 0 and "host attributes identical" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
