@@ -229,3 +229,12 @@ def test_mirror_host_attributes_equal_the_reference():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "surface_compare_worker.py"), ROOT],
                        capture_output=True, text=True, timeout=300, cwd="/tmp")
     assert r.returncode == 0 and "host attributes identical" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_prep_data_equals_the_reference():
+    """every array returned by the package's prep_data restatements (Burgers inference / identification /
+    discrete-time inference, Schrodinger) is bit-identical to what the reference's own prep_data returns from the same seed."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "prep_data_compare_worker.py"), ROOT],
+                       capture_output=True, text=True, timeout=600, cwd="/tmp")
+    assert r.returncode == 0 and "prep_data identical" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
