@@ -288,6 +288,74 @@ class BurgersDiscreteInference:
         return a + b
 
 
+@dataclass
+class BurgersDiscreteIdentification:
+    """1d-burgers/ide_disc_burgers.py:48-203 (discrete-time identification; SURVEY section 2 #11 -- the SCRIPT is broken as
+    shipped (`Logger(frequency=10)` :225, `np.asscalar` in its prep_data branch) but the class is well defined).
+    Net [1, ..., q] on x only, two snapshots: (x_0, u_0) at t_0 and (x_1, u_1) at t_1 = t_0 + dt.  Flat parameters
+    w = [net, lambda_1, lambda_2].  U, U_x, U_xx of ALL q outputs by the dummy-gradient trick (:57-79);
+        N    = l1 U U_x - e^{l2} U_xx                       U_0 = U + dt N alpha^T                 (:81-92)
+        N'   = -l1 U U_x + e^{l2} U_xx                      U_1 = U + dt N' (beta - alpha)^T        (:94-108)
+        loss = sum((U_0 - u_0)^2) + sum((U_1 - u_1)^2)      (sums over points AND stages, :111-115)."""
+    layers: Sequence[int]
+    lb: np.ndarray
+    ub: np.ndarray
+    dt: float
+    x_0: np.ndarray            # (N_0, 1)
+    u_0: np.ndarray            # (N_0, 1)
+    x_1: np.ndarray            # (N_1, 1)
+    u_1: np.ndarray            # (N_1, 1)
+    IRK_alpha: np.ndarray      # (q, q)
+    IRK_beta: np.ndarray       # (1, q)
+
+    def __post_init__(self):
+        t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+        self._lb, self._ub = t(self.lb).reshape(-1), t(self.ub).reshape(-1)
+        self._x0, self._u0, self._x1, self._u1 = t(self.x_0), t(self.u_0), t(self.x_1), t(self.u_1)
+        self._alpha = t(self.IRK_alpha)
+        # (self.IRK_beta - self.IRK_alpha) is NUMPY arithmetic in the reference (:107), i.e. it is rounded in the tables' own
+        # dtype -- float32, burgersutil.py:92 -- before TensorFlow ever sees it
+        self._beta_minus_alpha = t(np.asarray(self.IRK_beta) - np.asarray(self.IRK_alpha))
+        self.q = int(self.IRK_alpha.shape[1])
+        self.P = num_params(self.layers) + 2
+
+    def autograd(self, wn: torch.Tensor, x0: torch.Tensor):
+        x = x0.clone().requires_grad_(True)
+        dummy = torch.ones(x.shape[0], self.q, dtype=DT, requires_grad=True)          # createDummy, :143-144
+        U = mlp(wn, x, self.layers, self._lb, self._ub)                               # :66
+        g_U = torch.autograd.grad(U, x, grad_outputs=dummy, create_graph=True)[0]     # :69
+        U_x = torch.autograd.grad(g_U, dummy, grad_outputs=torch.ones_like(g_U), create_graph=True)[0]       # :70
+        g_U_x = torch.autograd.grad(U_x, x, grad_outputs=dummy, create_graph=True)[0]                        # :71
+        U_xx = torch.autograd.grad(g_U_x, dummy, grad_outputs=torch.ones_like(g_U_x), create_graph=True)[0]  # :75
+        return U, U_x, U_xx
+
+    def U_0_model(self, w: torch.Tensor, x=None):
+        U, U_x, U_xx = self.autograd(w[:-2], self._x0 if x is None else x)
+        l1, l2 = w[-2], torch.exp(w[-1])                                              # :88-89
+        N = l1 * U * U_x - l2 * U_xx                                                  # :90
+        return U + self.dt * (N @ self._alpha.T)                                      # :91
+
+    def U_1_model(self, w: torch.Tensor, x=None):
+        U, U_x, U_xx = self.autograd(w[:-2], self._x1 if x is None else x)
+        l1, l2 = w[-2], torch.exp(w[-1])                                              # :104-105
+        N = -l1 * U * U_x + l2 * U_xx                                                 # :106
+        return U + self.dt * (N @ self._beta_minus_alpha.T)                           # :107
+
+    def loss_parts(self, w: torch.Tensor):
+        return (torch.sum(torch.square(self.U_0_model(w) - self._u0)),                # :111-115
+                torch.sum(torch.square(self.U_1_model(w) - self._u1)))
+
+    def loss(self, w: torch.Tensor) -> torch.Tensor:
+        a, b = self.loss_parts(w)
+        return a + b
+
+    def predict(self, w, x_star):
+        """predict (:197-202): both models on x_star with a fresh dummy."""
+        wt = torch.as_tensor(np.asarray(w, dtype=np.float64))
+        xs = torch.as_tensor(np.asarray(x_star, dtype=np.float64))
+        return self.U_0_model(wt, xs).detach().numpy(), self.U_1_model(wt, xs).detach().numpy()
+
+
 def loss_and_flat_grad(problem, w) -> Tuple[float, np.ndarray]:
     """get_loss_and_flat_grad closure (neuralnetwork.py:91-103): loss value + flat gradient in the
     trainable_variables order (== flat weight layout; identification appends d/dl1, d/dl2)."""

@@ -184,3 +184,28 @@ def burgers_disc_loss_grad(w, layers, lb, ub, x_0, u_0, x_1, nu, dt, IRK_weights
     g = g + backward(w, layers, stb, (2.0 * B1, zb, zb, zb))
     loss1 = float(np.sum(B1 ** 2))
     return loss0 + loss1, g, (loss0, loss1)
+
+
+def burgers_ide_disc_loss_grad(w, layers, lb, ub, x_0, u_0, x_1, u_1, dt, IRK_alpha, IRK_beta):
+    """Discrete-time Burgers identification, 1d-burgers/ide_disc_burgers.py:81-115: w = [net, l1, l2], net [1, ..., q];
+    U_0 = U + dt N alpha^T on x_0, U_1 = U - dt N (beta - alpha)^T on x_1 with N = l1 U U_x - e^{l2} U_xx;
+    loss = sum((U_0 - u_0)^2) + sum((U_1 - u_1)^2).  Both snapshots are the same computation with stage matrices
+    M_0 = alpha and M_1 = -(beta - alpha) (beta broadcast over rows): pred = U + dt N M^T."""
+    w = np.asarray(w, dtype=np.float64)
+    wn, l1, kappa = w[:-2], w[-2], np.exp(w[-1])
+    A = np.asarray(IRK_alpha, dtype=np.float64)
+    # beta - alpha is formed by numpy in the tables' own dtype (float32 in the reference, ide_disc_burgers.py:107) and only then promoted
+    M1 = -np.asarray(np.asarray(IRK_beta).reshape(1, -1) - np.asarray(IRK_alpha), dtype=np.float64)
+    g = np.zeros(wn.size)
+    dl1 = dl2 = 0.0
+    parts = []
+    for x, u, M in ((x_0, u_0, A), (x_1, u_1, M1)):
+        (U, Ux, _, Uxx), st = forward(wn, layers, lb, ub, x)
+        Nn = l1 * U * Ux - kappa * Uxx
+        R = 2.0 * (U + dt * Nn @ M.T - u)                   # u (N,1) broadcasts over the q stages
+        Nbar = dt * R @ M
+        g = g + backward(wn, layers, st, (R + Nbar * l1 * Ux, Nbar * l1 * U, np.zeros_like(R), -kappa * Nbar))
+        dl1 += float(np.sum(Nbar * U * Ux))
+        dl2 += float(np.sum(Nbar * (-kappa) * Uxx))
+        parts.append(float(np.sum((0.5 * R) ** 2)))
+    return parts[0] + parts[1], np.concatenate([g, [dl1, dl2]]), tuple(parts)

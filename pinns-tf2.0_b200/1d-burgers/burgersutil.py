@@ -28,9 +28,6 @@ def _lhs(d, n):
 
 def prep_data(path, N_u=None, N_f=None, N_n=None, q=None, ub=None, lb=None, noise=0.0, idx_t_0=None, idx_t_1=None,
               N_0=None, N_1=None):
-    if N_0 is not None:
-        raise NotImplementedError("discrete-time IDENTIFICATION data preparation is not provided (ide_disc_burgers.py is "
-                                  "broken as shipped, SURVEY section 2 #11)")
     data = scipy.io.loadmat(path)
     t = data["t"].flatten()[:, None]
     x = data["x"].flatten()[:, None]
@@ -53,6 +50,23 @@ def prep_data(path, N_u=None, N_f=None, N_n=None, q=None, ub=None, lb=None, nois
     idx = np.random.choice(X_star.shape[0], N_u, replace=False)
     X_u_train, u_train = X_star[idx, :], u_star[idx, :]
     lb, ub = X_star.min(axis=0), X_star.max(axis=0)
+    if N_0 is not None and N_1 is not None:
+        # discrete-time identification (reference burgersutil.py:76-97; its np.asscalar no longer exists in numpy, .item() is
+        # the same value): N_0 / N_1 points of the snapshots idx_t_0 / idx_t_1, q from the time step, IRK table split in
+        # alpha (q x q) and beta (1 x q)
+        Exact_xt = Exact_u.T
+        idx_x = np.random.choice(Exact_xt.shape[0], N_0, replace=False)
+        x_0 = x[idx_x, :]
+        u_0 = Exact_xt[idx_x, idx_t_0][:, None]
+        u_0 = u_0 + noise * np.std(u_0) * np.random.randn(u_0.shape[0], u_0.shape[1])
+        idx_x = np.random.choice(Exact_xt.shape[0], N_1, replace=False)
+        x_1 = x[idx_x, :]
+        u_1 = Exact_xt[idx_x, idx_t_1][:, None]
+        u_1 = u_1 + noise * np.std(u_1) * np.random.randn(u_1.shape[0], u_1.shape[1])
+        dt_ = (t[idx_t_1] - t[idx_t_0]).item()
+        q = int(np.ceil(0.5 * np.log(np.finfo(float).eps) / np.log(dt_)))
+        weights, _ = load_irk(q)
+        return x_0, u_0, x_1, u_1, x, t, dt_, q, Exact_xt, weights[0:-1, :], weights[-1:, :]
     if N_f is None:
         return x, t, X, T, Exact_u, X_star, u_star, X_u_train, u_train, ub, lb
     # inference: initial + boundary points, then a Latin hypercube of collocation points (burgersutil.py:104-129)
@@ -142,6 +156,14 @@ def plot_inf_disc_results(x_star, idx_t_0, idx_t_1, x_0, u_0, ub, lb, u_1_pred, 
                    rel_l2_error=np.linalg.norm(Exact_u[idx_t_1] - u_1_pred) / np.linalg.norm(Exact_u[idx_t_1]))
 
 
-def plot_ide_disc_results(*a, **k):
-    raise NotImplementedError("discrete-time identification (ide_disc_burgers.py) is not provided; it is broken as shipped "
-                              "(SURVEY section 2 #11)")
+def plot_ide_disc_results(x_star, t_star, idx_t_0, idx_t_1, x_0, u_0, x_1, u_1, ub, lb, u_1_pred, Exact, lambda_1_value,
+                          lambda_1_value_noisy, lambda_2_value, lambda_2_value_noisy, x, t, save_path=None, save_hp=None):
+    """Artefacts of the discrete-time identification run (reference figure: burgersutil.py:263-330): both data snapshots, the
+    exact field (x by t), the identified coefficients with and without noise."""
+    return _finish(save_path, save_hp,
+                   lambda pl: _slices(pl, x_star, [Exact[:, idx_t_0], Exact[:, idx_t_1]], [None, None],
+                                      ["t = %.2f" % t_star[idx_t_0, 0], "t = %.2f" % t_star[idx_t_1, 0]]),
+                   Exact=Exact, x_star=x_star, t_star=t_star, x_0=x_0, u_0=u_0, x_1=x_1, u_1=u_1, lb=lb, ub=ub, U_1_pred=u_1_pred,
+                   idx_t=np.array([idx_t_0, idx_t_1]), lambdas=np.array([lambda_1_value, lambda_2_value], dtype=float),
+                   lambdas_noisy=np.array([lambda_1_value_noisy, lambda_2_value_noisy], dtype=float),
+                   lambdas_exact=np.array([1.0, 0.01 / np.pi]))

@@ -149,7 +149,7 @@ def make_nls():
     np.savez_compressed(os.path.join(OUT, "nls_inf.npz"), **out)
 
 
-if __name__ == "__main__" and "--disc" not in sys.argv:
+if __name__ == "__main__" and "--disc" not in sys.argv and "--ide-disc" not in sys.argv:
     make_burgers_inf()
     make_burgers_ide()
     make_nls()
@@ -187,3 +187,44 @@ def make_burgers_disc():
 
 if __name__ == "__main__" and "--disc" in sys.argv:
     make_burgers_disc()
+
+
+def make_burgers_ide_disc():
+    """Discrete-time Burgers identification, 1d-burgers/ide_disc_burgers.py, with the script's data (N_0=199, N_1=201,
+    idx_t 10 -> 90, hence dt = 0.8 and the upstream q=81 table)."""
+    sys.path.insert(0, os.path.join(ROOT, "pinns-tf2.0_b200", "1d-burgers"))
+    import burgersutil
+    rng = np.random.default_rng(81)
+    np.random.seed(1234)
+    lb, ub = np.array([-1.0]), np.array([1.0])
+    cwd = os.getcwd(); os.chdir(REF)
+    try:
+        x_0, u_0, x_1, u_1, x_star, t_star, dt, q, Exact_u, alpha, beta = burgersutil.prep_data(
+            os.path.join(REF, "1d-burgers", "data", "burgers_shock.mat"), N_0=199, N_1=201, lb=lb, ub=ub, noise=0.0, idx_t_0=10, idx_t_1=90)
+    finally:
+        os.chdir(cwd)
+    layers = [1, 50, 50, 50, q]                                             # ide_disc_burgers.py:34, :222
+    out = dict(layers=layers, lb=lb, ub=ub, dt=dt, q=q, x_0=x_0, u_0=u_0, x_1=x_1, u_1=u_1, IRK_alpha=alpha.astype(np.float32),
+               IRK_beta=beta.astype(np.float32), x_star=x_star)
+    wn = rp.glorot_normal_flat(layers, rng) + 0.02 * rng.standard_normal(rp.num_params(layers))
+    pb = rp.BurgersDiscreteIdentification(layers, lb, ub, dt, x_0, u_0, x_1, u_1, alpha, beta)
+    for tag, lam in (("", [0.0, -6.0]), ("2", [0.7, -4.0])):                # :151-152 initial values, then a generic point
+        w = np.concatenate([wn, lam])
+        f, g = rp.loss_and_flat_grad(pb, w)
+        f2, g2, parts = ty.burgers_ide_disc_loss_grad(w, layers, lb, ub, x_0, u_0, x_1, u_1, dt, alpha, beta)
+        check("burgers_ide_disc" + tag, f, g, f2, g2)
+        out["w" + tag], out["loss" + tag], out["grad" + tag], out["parts" + tag] = w, f, g, np.array(parts)
+    wa, la, _ = rp.adam_train(pb, out["w2"], 3, lr=1e-3)                    # :37-40 (tf_eps None -> 1e-7)
+    out["adam_losses"], out["adam_w"] = la, wa
+    tr = rp.lbfgs_fixed_step(lambda z: rp.loss_and_flat_grad(pb, z), out["w2"], max_iter=4, learning_rate=0.8, n_correction=50,
+                             tol_fun=np.finfo(float).eps)
+    out["lbfgs_x_eval"], out["lbfgs_f"], out["lbfgs_x_final"] = np.array(tr.x_eval), np.array(tr.f_hist), tr.x_final
+    out["x_star"] = x_star[::8]                                             # 32 probe positions keep the fixture small
+    U0, U1 = pb.predict(out["w2"], out["x_star"])
+    out["predict_U0"], out["predict_U1"] = U0, U1
+    np.savez_compressed(os.path.join(OUT, "burgers_ide_disc.npz"), **out)
+    print("burgers_ide_disc.npz", os.path.getsize(os.path.join(OUT, "burgers_ide_disc.npz")) // 1024, "KiB, q =", q, "P =", out["w"].size)
+
+
+if __name__ == "__main__" and "--ide-disc" in sys.argv:
+    make_burgers_ide_disc()

@@ -258,6 +258,53 @@ def run_burgers_disc(out, dev):
         out["burgers_disc_lbfgs_runs"] = np.array(0)
 
 
+def run_burgers_ide_disc(out, dev):
+    """1d-burgers/ide_disc_burgers.py:48-203.  The SCRIPT cannot run as shipped (Logger(frequency=10) :225; np.asscalar in its
+    prep_data branch), the class can: its own fit() (Adam loop :163-168, L-BFGS closure :171-185 -- here the loss IS taken inside
+    the tape) and predict() run here.  fit() reads the script-level `hp`, which is supplied in the class namespace."""
+    g = np.load(os.path.join(HERE, "burgers_ide_disc.npz"))
+    q = int(g["q"])
+
+    def fresh(**hpkw):
+        hp = hp_for(g["layers"], **hpkw)
+        cls = reference_class("1d-burgers/ide_disc_burgers.py", "BurgersInformedNN", {"hp": hp})
+        return cls(hp, RecordingLogger(hp), float(g["dt"]), g["lb"], g["ub"], q, g["IRK_alpha"], g["IRK_beta"])
+    t64 = lambda a: tf.convert_to_tensor(a, dtype="float64")
+    for tag in ("", "2"):
+        m = fresh()
+        m.lambda_1 = tf.Variable([0.0], dtype=m.dtype)                      # what fit() creates (:151-152) before set_weights can run
+        m.lambda_2 = tf.Variable([-6.0], dtype=m.dtype)
+        m.set_weights(t64(g["w" + tag]))
+        m.dummy_x_0, m.dummy_x_1 = m.createDummy(t64(g["x_0"])), m.createDummy(t64(g["x_1"]))       # :155-156
+        loss, grads = m.grad(t64(g["x_0"]), t64(g["u_0"]), t64(g["x_1"]), t64(g["u_1"]))
+        out["burgers_ide_disc_loss" + tag], out["burgers_ide_disc_grad" + tag] = float(loss), flat_grad_of(m, grads)
+        dev["burgers_ide_disc%s loss" % tag] = abs(float(loss) - float(g["loss" + tag])) / float(g["loss" + tag])
+        dev["burgers_ide_disc%s grad (incl. lambda_1, lambda_2)" % tag] = rel(out["burgers_ide_disc_grad" + tag], g["grad" + tag])
+    U0, U1 = m.predict(g["x_star"])
+    out["burgers_ide_disc_predict_U0"], out["burgers_ide_disc_predict_U1"] = np.asarray(U0), np.asarray(U1)
+    dev["burgers_ide_disc predict U_0, U_1"] = max(rel(np.asarray(U0), g["predict_U0"]), rel(np.asarray(U1), g["predict_U1"]))
+    # fit() always starts from lambda = (0, -6) and the net's own initial weights, so it is compared from THAT start:
+    m = fresh(tf_epochs=3, nt_epochs=4)
+    m.model.layers[1].set_weights(m.model.layers[1].get_weights())           # no-op; the net keeps its seeded initial weights
+    w_net0 = np.asarray(ref_nn.NeuralNetwork.get_weights(m, convert_to_tensor=False))
+    quiet_fit(m, g["x_0"], g["u_0"], g["x_1"], g["u_1"])
+    out["burgers_ide_disc_fit_w0"] = np.concatenate([w_net0, [0.0, -6.0]])
+    out["burgers_ide_disc_fit_adam_losses"] = np.array([v for _, v in m.logger.tf_losses])
+    out["burgers_ide_disc_fit_lbfgs_logged"] = np.array(m.logger.nt_losses)
+    out["burgers_ide_disc_fit_w"] = np.asarray(m.get_weights())
+    # the same schedule with the restated oracle from the same start
+    sys.path.insert(0, ROOT)
+    from oracle import reference_port as rp
+    pb = rp.BurgersDiscreteIdentification([int(v) for v in g["layers"]], g["lb"], g["ub"], float(g["dt"]), g["x_0"], g["u_0"],
+                                           g["x_1"], g["u_1"], g["IRK_alpha"], g["IRK_beta"])
+    wa, la, _ = rp.adam_train(pb, out["burgers_ide_disc_fit_w0"], 3, lr=1e-3)
+    tr = rp.lbfgs_fixed_step(lambda z: rp.loss_and_flat_grad(pb, z), wa, max_iter=4, learning_rate=0.8, n_correction=50,
+                             tol_fun=np.finfo(float).eps)
+    dev["burgers_ide_disc fit(): 3 Adam epochs, losses"] = rel(out["burgers_ide_disc_fit_adam_losses"], la)
+    dev["burgers_ide_disc fit(): + 4 L-BFGS its, logged f"] = rel(out["burgers_ide_disc_fit_lbfgs_logged"][:, 1], np.array(tr.logged)[:, 1])
+    dev["burgers_ide_disc fit(): final model weights"] = rel(out["burgers_ide_disc_fit_w"], tr.x_eval[-1])
+
+
 def run_burgers_default_schedule(out, dev):
     """The reference's default training run (1d-burgers/inf_cont_burgers.py:27-43: N_u=100, N_f=10000, 100 Adam epochs at 0.03,
     200 fixed-step L-BFGS iterations at 0.8, 50 corrections) through ITS fit(), from the initial weights and data of
@@ -294,7 +341,7 @@ def main():
     for k, (v, tol) in sched.items():
         print("%-70s rel. deviation from the oracle's value: %.2e (bound %.0e)" % (k, v, tol))
         assert v <= tol, k
-    for fn in (run_burgers_inf, run_burgers_ide, run_nls, run_burgers_disc):
+    for fn in (run_burgers_inf, run_burgers_ide, run_nls, run_burgers_disc, run_burgers_ide_disc):
         fn(out, dev)
     width = max(len(k) for k in dev)
     for k, v in dev.items():

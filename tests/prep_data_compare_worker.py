@@ -71,6 +71,14 @@ cases = [
     ("burgers discrete inference, noise", lambda m: m.prep_data(burgers, N_n=250, q=100, lb=np.array([-1.0]), ub=np.array([1.0]),
                                                               noise=0.05, idx_t_0=10, idx_t_1=90)),
 ]
+# discrete-time identification (ide_disc_burgers.py:216-218).  The reference branch calls np.asscalar, which numpy >= 1.23 no longer
+# has; it is supplied for the reference call only (np.asscalar(a) was a.item()).
+if not hasattr(np, "asscalar"):
+    np.asscalar = lambda a: a.item()
+cases.append(("burgers discrete identification", lambda m: m.prep_data(burgers, N_0=199, N_1=201, lb=np.array([-1.0]), ub=np.array([1.0]),
+                                                                        noise=0.0, idx_t_0=10, idx_t_1=90)))
+cases.append(("burgers discrete identification, noise", lambda m: m.prep_data(burgers, N_0=199, N_1=201, lb=np.array([-1.0]),
+                                                                               ub=np.array([1.0]), noise=0.01, idx_t_0=10, idx_t_1=90)))
 for name, fn in cases:
     np.random.seed(1234); a = fn(ref_b)
     np.random.seed(1234); b = fn(my_b)

@@ -144,3 +144,29 @@ def test_burgers_disc_golden_both_oracles():
         assert abs(fv - g["loss"]) <= 1e-13 * abs(g["loss"]) and rel(gv, g["grad"]) < 1e-12
     assert np.allclose(parts, g["parts"], rtol=1e-12)
     assert IRK.shape == (101, 100) and abs(IRK[-1].sum() - 1.0) < 1e-5        # last row: the quadrature weights b_j
+
+
+def test_burgers_ide_disc_golden_both_oracles():
+    """Discrete-time identification (1d-burgers/ide_disc_burgers.py:48-203): nested-autograd restatement (dummy-gradient trick)
+    and the closed-form Taylor oracle against the golden vector (q = 81 upstream table, float32 like the reference loads it)."""
+    g = load_golden("burgers_ide_disc")
+    layers = [int(v) for v in g["layers"]]
+    assert layers == [1, 50, 50, 50, 81] and g["IRK_alpha"].dtype == np.float32 and g["IRK_alpha"].shape == (81, 81)
+    pb = rp.BurgersDiscreteIdentification(layers, g["lb"], g["ub"], float(g["dt"]), g["x_0"], g["u_0"], g["x_1"], g["u_1"],
+                                           g["IRK_alpha"], g["IRK_beta"])
+    for tag in ("", "2"):
+        f, gr = rp.loss_and_flat_grad(pb, g["w" + tag])
+        f2, g2, parts = ty.burgers_ide_disc_loss_grad(g["w" + tag], layers, g["lb"], g["ub"], g["x_0"], g["u_0"], g["x_1"], g["u_1"],
+                                                      float(g["dt"]), g["IRK_alpha"], g["IRK_beta"])
+        for fv, gv in ((f, gr), (f2, g2)):
+            assert abs(fv - float(g["loss" + tag])) <= 1e-13 * abs(float(g["loss" + tag]))
+            assert np.linalg.norm(gv - g["grad" + tag]) <= 1e-12 * np.linalg.norm(g["grad" + tag])
+        assert np.allclose(parts, g["parts" + tag], rtol=1e-13)
+    # beta - alpha is rounded in float32 by the reference (numpy arithmetic before TensorFlow sees it): doing it in float64 is
+    # a DIFFERENT function at the 1e-10 level, which the pin against the reference's own code detects
+    pb64 = rp.BurgersDiscreteIdentification(layers, g["lb"], g["ub"], float(g["dt"]), g["x_0"], g["u_0"], g["x_1"], g["u_1"],
+                                             g["IRK_alpha"].astype(np.float64), g["IRK_beta"].astype(np.float64))
+    f64, _ = rp.loss_and_flat_grad(pb64, g["w2"])
+    assert 1e-14 < abs(f64 - float(g["loss2"])) / float(g["loss2"]) < 1e-8
+    U0, U1 = pb.predict(g["w2"], g["x_star"])
+    assert np.allclose(U0, g["predict_U0"], rtol=0, atol=1e-13) and np.allclose(U1, g["predict_U1"], rtol=0, atol=1e-13)

@@ -74,6 +74,27 @@ def test_reference_run_equals_oracle_golden_discrete_time():
     assert int(r["burgers_disc_lbfgs_runs"]) == 0
 
 
+def test_reference_run_equals_oracle_golden_discrete_time_identification():
+    """ide_disc_burgers.py's class (the script around it is broken as shipped): loss, gradient incl. lambda_1/lambda_2 at two
+    parameter points, both predictions.  This comparison is what exposed that the reference forms (beta - alpha) in float32."""
+    r, g = _ref_run(), load_golden("burgers_ide_disc")
+    for tag in ("", "2"):
+        assert abs(float(r["burgers_ide_disc_loss" + tag]) - float(g["loss" + tag])) <= TOL * float(g["loss" + tag])
+        assert _rel(r["burgers_ide_disc_grad" + tag], g["grad" + tag]) <= TOL
+    assert _rel(r["burgers_ide_disc_predict_U0"], g["predict_U0"]) <= TOL and _rel(r["burgers_ide_disc_predict_U1"], g["predict_U1"]) <= TOL
+    # its fit(): 3 Adam epochs + 4 L-BFGS iterations from the stored start, replayed here with the oracle
+    sys.path.insert(0, ROOT)
+    from oracle import reference_port as rp
+    pb = rp.BurgersDiscreteIdentification([int(v) for v in g["layers"]], g["lb"], g["ub"], float(g["dt"]), g["x_0"], g["u_0"],
+                                           g["x_1"], g["u_1"], g["IRK_alpha"], g["IRK_beta"])
+    wa, la, _ = rp.adam_train(pb, r["burgers_ide_disc_fit_w0"], 3, lr=1e-3)
+    tr = rp.lbfgs_fixed_step(lambda z: rp.loss_and_flat_grad(pb, z), wa, max_iter=4, learning_rate=0.8, n_correction=50,
+                             tol_fun=np.finfo(float).eps)
+    assert _rel(r["burgers_ide_disc_fit_adam_losses"], la) <= TOL
+    assert _rel(r["burgers_ide_disc_fit_lbfgs_logged"][:, 1], np.array(tr.logged)[:, 1]) <= 1e-12
+    assert _rel(r["burgers_ide_disc_fit_w"], tr.x_eval[-1]) <= 1e-12
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
 def test_reference_sources_reproduce_the_committed_run():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_reference_fixtures.py"), "--check"],
