@@ -259,3 +259,21 @@ def test_prep_data_equals_the_reference():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "prep_data_compare_worker.py"), ROOT],
                        capture_output=True, text=True, timeout=600, cwd="/tmp")
     assert r.returncode == 0 and "prep_data identical" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_unmodified_reference_script_runs_end_to_end_on_the_emulation(tmp_path):
+    """oracle/run_reference_on_emulation.py: the whole inf_cont_burgers.py (data prep, model, fit, predict, error, result
+    directory) executes on the CPU with a small hp.json; its printed log has the reference Logger's shape."""
+    import json
+    hp = {"N_u": 50, "N_f": 500, "layers": [2, 20, 20, 20, 20, 20, 20, 20, 20, 1], "tf_epochs": 3, "tf_lr": 0.03, "tf_b1": 0.9,
+          "tf_eps": None, "nt_epochs": 3, "nt_lr": 0.8, "nt_ncorr": 50, "log_frequency": 1}
+    (tmp_path / "hp.json").write_text(json.dumps(hp))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_reference_on_emulation.py"),
+                        os.path.join(REF, "1d-burgers", "inf_cont_burgers.py"), str(tmp_path / "hp.json")],
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    out = r.stdout
+    assert r.returncode == 0, out[-2000:] + r.stderr[-3000:]
+    assert "TensorFlow version: 2.0.0-rc0 (API emulation" in out and "-- Starting Adam optimization --" in out
+    assert out.count("tf_epoch = ") == 3 and out.count("nt_epoch = ") == 2      # the last L-BFGS iteration is never logged
+    assert "Training finished (epoch 6)" in out and "Saving results to directory" in out
