@@ -20,6 +20,21 @@ def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
 
+def load_reference_run():
+    """What the reference's OWN Python computed on the golden inputs (tests/golden/make_reference_fixtures.py)."""
+    return np.load(os.path.join(GOLDEN, "reference_run.npz"))
+
+
+def assert_matches_reference_run(loss, grad, loss_key, grad_key, tol=1e-10):
+    """The CUDA result against the numbers produced by the reference's own code (not only against the restated oracle)."""
+    r = load_reference_run()
+    ref_loss, ref_grad = float(r[loss_key]), np.asarray(r[grad_key], dtype=np.float64)
+    assert abs(float(loss) - ref_loss) <= tol * abs(ref_loss), (loss_key, float(loss), ref_loss)
+    grad = np.asarray(grad, dtype=np.float64)
+    assert grad.shape == ref_grad.shape, (grad_key, grad.shape, ref_grad.shape)
+    assert np.linalg.norm(grad - ref_grad) <= tol * np.linalg.norm(ref_grad), grad_key
+
+
 @pytest.fixture(scope="session")
 def lib_built():
     """Build libpinn_b200.so if it is stale/missing (nvcc cross-compiles without a GPU)."""

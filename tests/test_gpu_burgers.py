@@ -6,7 +6,7 @@ different summation order, so single evaluations are held to 1e-10 and short opt
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import assert_matches_reference_run, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -41,6 +41,7 @@ def test_loss_grad_matches_golden(cabi):
     assert abs(loss - g["loss"]) <= 1e-10 * abs(g["loss"])
     assert rel(grad, g["grad"]) < 1e-10
     assert np.allclose([parts[0], parts[2]], g["parts"], rtol=1e-10)
+    assert_matches_reference_run(loss, grad, "burgers_inf_loss", "burgers_inf_grad")      # the reference's own code, executed
     # the closure form: pass the weights with the call (get_loss_and_flat_grad, neuralnetwork.py:91-103)
     loss2, grad2, _ = p.loss_grad(w=g["w"])
     assert loss2 == loss and np.array_equal(grad, grad2)       # deterministic reduction order
@@ -101,6 +102,7 @@ def test_identification_matches_golden(cabi):
         assert abs(loss - g[fk]) <= 1e-10 * abs(g[fk])
         assert rel(grad, g[gk]) < 1e-10
         assert rel(grad[-2:], g[gk][-2:]) < 1e-9
+        assert_matches_reference_run(loss, grad, "burgers_ide_" + fk, "burgers_ide_" + gk)
         assert np.allclose(p.get_params(), [g[wk][-2], np.exp(g[wk][-1])], rtol=1e-15)      # (lambda_1, exp(lambda_2))
     p.set_weights(g["w"])
     losses = [p.adam_step(1e-3) for _ in range(5)]

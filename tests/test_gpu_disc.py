@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import PKG, load_golden
+from conftest import PKG, assert_matches_reference_run, load_golden
 
 pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.join(PKG, "shims"))
@@ -43,6 +43,7 @@ def test_golden_loss_grad_predict_adam(cabi):
     assert abs(loss - g["loss"]) <= 1e-10 * abs(g["loss"])
     assert rel(grad, g["grad"]) < 1e-10
     assert np.allclose(parts[:2], g["parts"], rtol=1e-10) and parts[2] == 0.0
+    assert_matches_reference_run(loss, grad, "burgers_disc_loss", "burgers_disc_grad")
     assert rel(p.predict(g["x_star"])[:, -1], g["predict"]) < 1e-12
     losses = [p.adam_step(1e-3, eps=1e-8) for _ in range(3)]
     assert rel(losses, g["adam_losses"]) < 1e-8 and rel(p.get_weights(), g["adam_w"]) < 1e-8

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import assert_matches_reference_run, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -41,6 +41,7 @@ def test_loss_grad_parts_both_ic_modes(cabi):
         assert abs(loss - g["loss_" + tag]) <= 1e-10 * abs(g["loss_" + tag])
         assert rel(grad, g["grad_" + tag]) < 1e-10
         assert np.allclose(parts, g["parts_" + tag], rtol=1e-10)      # (mse_0, mse_b, mse_f)
+        assert_matches_reference_run(loss, grad, "nls_loss_" + tag, "nls_grad_" + tag)
         loss2, grad2, _ = p.loss_grad(w=g["w"])
         assert loss2 == loss and np.array_equal(grad, grad2)          # deterministic
 

@@ -277,3 +277,22 @@ def test_unmodified_reference_script_runs_end_to_end_on_the_emulation(tmp_path):
     assert "TensorFlow version: 2.0.0-rc0 (API emulation" in out and "-- Starting Adam optimization --" in out
     assert out.count("tf_epoch = ") == 3 and out.count("nt_epoch = ") == 2      # the last L-BFGS iteration is never logged
     assert "Training finished (epoch 6)" in out and "Saving results to directory" in out
+
+
+def test_gpu_tests_reference_run_keys_exist():
+    """The GPU parity tests compare the CUDA results with reference_run.npz through conftest.assert_matches_reference_run;
+    exercise exactly those key pairs here (with the oracle's golden values standing in for the CUDA output), so that a typo
+    cannot surface only on the GPU box."""
+    from conftest import assert_matches_reference_run
+    g = load_golden("burgers_inf")
+    assert_matches_reference_run(float(g["loss"]), g["grad"], "burgers_inf_loss", "burgers_inf_grad")
+    g = load_golden("burgers_ide")
+    for fk, gk in (("loss", "grad"), ("loss2", "grad2")):
+        assert_matches_reference_run(float(g[fk]), g[gk], "burgers_ide_" + fk, "burgers_ide_" + gk)
+    g = load_golden("nls_inf")
+    for tag in ("q1", "x0t0"):
+        assert_matches_reference_run(float(g["loss_" + tag]), g["grad_" + tag], "nls_loss_" + tag, "nls_grad_" + tag)
+    g = load_golden("burgers_disc")
+    assert_matches_reference_run(float(g["loss"]), g["grad"], "burgers_disc_loss", "burgers_disc_grad")
+    with pytest.raises(AssertionError):
+        assert_matches_reference_run(float(g["loss"]) * (1 + 1e-8), g["grad"], "burgers_disc_loss", "burgers_disc_grad")
