@@ -296,3 +296,15 @@ def test_gpu_tests_reference_run_keys_exist():
     assert_matches_reference_run(float(g["loss"]), g["grad"], "burgers_disc_loss", "burgers_disc_grad")
     with pytest.raises(AssertionError):
         assert_matches_reference_run(float(g["loss"]) * (1 + 1e-8), g["grad"], "burgers_disc_loss", "burgers_disc_grad")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_lbfgs_control_flow_equals_the_reference():
+    """Every exit of the reference's lbfgs() (maxIter, maxEval, optimality at the start / later, no progress, step below tolX,
+    f change below tolX) plus rejected curvature pairs and history overflow: evaluation points, f history, returned x, logged
+    iterations, evaluation and iteration counts of oracle.reference_port.lbfgs_fixed_step equal the reference's on synthetic
+    objectives.  One known difference: 'no progress' at the very first iteration is an UnboundLocalError in the reference."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "lbfgs_compare_worker.py"), ROOT],
+                       capture_output=True, text=True, timeout=600, cwd="/tmp")
+    assert r.returncode == 0 and "lbfgs control flow identical" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "reference raises UnboundLocalError" in r.stdout
