@@ -47,7 +47,7 @@ def _ss_t(seconds):
 class Logger(object):
     def __init__(self, hp, stream=None):
         self.frequency = hp["log_frequency"]
-        self.out = stream or sys.stdout
+        self.out = stream                                   # None: whatever sys.stdout is at print time, like print()
         self.quiet = int(os.environ.get("RANK", "0")) != 0
         self.watch = _Stopwatch()
         self.error_fn = None
@@ -60,7 +60,7 @@ class Logger(object):
     # ------------------------------------------------------------------ helpers
     def _say(self, text):
         if not self.quiet:
-            print(text, file=self.out)
+            print(text, file=self.out if self.out is not None else sys.stdout)
 
     @staticmethod
     def _core_version():
