@@ -71,3 +71,26 @@ def test_header_is_plain_c_and_links_from_c(lib_built, tmp_path):
         return                                   # with a GPU the creation succeeds; the GPU tests cover that path
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "pinn_b200" in r.stdout and "no CUDA device" in r.stdout, r.stdout + r.stderr
+
+
+def test_hot_kernels_fit_their_resource_budget(lib_built):
+    """cuobjdump -res-usage of the built library: the two DMMA kernels are designed for one 256-thread CTA per SM with every
+    value in registers -- no stack (spill) frame, at most 255 registers; the default Burgers kernel must stay at <= 252 so that
+    8 warps fit the 64 K register file.  A regression here is a silent 2x slow-down, so it is pinned on the CPU."""
+    out = subprocess.run(["cuobjdump", "-res-usage", lib_built], capture_output=True, text=True).stdout
+    usage = {}
+    for m in re.finditer(r"Function (\S+?):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+)", out):
+        usage[m.group(1)] = tuple(int(v) for v in m.groups()[1:])
+    def find(*parts):
+        keys = [k for k in usage if all(p in k for p in parts)]
+        assert len(keys) == 1, (parts, keys)
+        return usage[keys[0]]
+    regs, stack, _ = find("burgers2", "fused_loss_grad")
+    assert regs <= 252 and stack == 0
+    regs, stack, _ = find("3nls", "fused_loss_grad")
+    assert regs <= 255 and stack == 0
+    for name in ("reduce_adam", "adam_update", "reduce_partials", "p2p_gather_reduce"):
+        regs, stack, _ = find(name)
+        assert regs <= 64 and stack == 0
+    regs, stack, _ = find("lbfgs_iterate", "ILi12ELi256E")        # the Burgers-size L-BFGS keeps its P-vector slice in registers
+    assert stack == 0
