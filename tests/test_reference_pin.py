@@ -308,3 +308,19 @@ def test_lbfgs_control_flow_equals_the_reference():
                        capture_output=True, text=True, timeout=600, cwd="/tmp")
     assert r.returncode == 0 and "lbfgs control flow identical" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     assert "reference raises UnboundLocalError" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_golden_fixtures_are_reproduced_by_their_generator(tmp_path):
+    """tests/golden/make_golden.py (committed with the fixtures it made) regenerates every array of the five problem fixtures
+    exactly; the generator reads only the reference's data files and the oracle."""
+    env = dict(os.environ, PINN_GOLDEN_OUT=str(tmp_path), PYTHONPATH=ROOT)
+    for flags in ([], ["--disc"], ["--ide-disc"]):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_golden.py")] + flags, env=env,
+                           capture_output=True, text=True, timeout=900, cwd="/tmp")
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for name in ("burgers_inf", "burgers_ide", "nls_inf", "burgers_disc", "burgers_ide_disc"):
+        a, b = load_golden(name), np.load(os.path.join(str(tmp_path), name + ".npz"))
+        assert sorted(a.files) == sorted(b.files), name
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (name, k)
