@@ -25,13 +25,20 @@ def _t(a):
 
 
 class LazyLoss(object):
-    """Loss of the most recent asynchronous Adam step; fetched from the device only when formatted/converted."""
+    """Loss of one asynchronous Adam step; fetched from the device only when formatted/converted.  The device keeps the loss of
+    the LATEST step only, so the value must be taken (float(), format, .numpy()) before the next step is enqueued -- which is
+    what the reference's loop does (it logs each epoch's loss before the next epoch).  Asking later is an error, not a silently
+    wrong number."""
 
-    def __init__(self, native):
-        self._n, self._v = native, None
+    def __init__(self, native, owner=None):
+        self._n, self._v, self._owner = native, None, owner
+        self._serial = getattr(owner, "_adam_serial", 0)
 
     def numpy(self):
         if self._v is None:
+            if self._owner is not None and self._owner._adam_serial != self._serial:
+                raise RuntimeError("this loss belongs to an earlier asynchronous training step and was never read; convert it "
+                                   "(float(loss)) before calling tf_optimization_step again")
             self._v = np.float64(self._n.last_loss())
         return self._v
 
@@ -242,7 +249,8 @@ class NeuralNetwork(object):
         self._bind(X_u, u)
         n = self._native()
         n.adam_step(self.tf_lr, self.tf_b1, self.tf_b2, self.tf_eps, sync=False)
-        return LazyLoss(n)
+        self._adam_serial = getattr(self, "_adam_serial", 0) + 1
+        return LazyLoss(n, self)
 
     def nt_optimization(self, X_u, u):
         self.logger.log_train_opt("LBFGS")

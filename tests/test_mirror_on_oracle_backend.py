@@ -271,3 +271,28 @@ def test_unmodified_scripts_complete_on_the_mirror(mirror, monkeypatch, tmp_path
     res = [os.path.join(d, f) for d, _, fs in os.walk(str(tmp_path)) for f in fs]
     if "ide_cont" not in script:                                 # that script plots without save_path (plt.show() in the reference)
         assert any(f.endswith("hp.json") and "results" in f for f in res) and any(f.endswith("fields.npz") for f in res), res
+
+
+def test_lazy_loss_is_current_or_an_error_never_stale(mirror):
+    """tf_optimization_step returns a loss that is read back from the device only on use; reading the loss of an EARLIER step
+    after a newer one was enqueued raises instead of returning the newer step's value."""
+    g = load_golden("burgers_inf")
+    NeuralNetwork = mirror["nn"].NeuralNetwork
+
+    class BurgersInformedNN(NeuralNetwork):
+        def __init__(self, hp, logger, X_f, ub, lb, nu):
+            super().__init__(hp, logger, ub, lb)
+            self.nu = nu
+            self.x_f, self.t_f = self.tensor(X_f[:, 0:1]), self.tensor(X_f[:, 1:2])
+
+    hp = hp_for(g["layers"])
+    with redirect_stdout(io.StringIO()):
+        p = BurgersInformedNN(hp, mirror["Logger"](hp), g["X_f"], g["ub"], g["lb"], float(g["nu"]))
+    p._w0 = g["w"].copy()
+    l0 = p.tf_optimization_step(g["X_u"], g["u"])
+    assert abs(float(l0) - g["adam_losses"][0][0]) <= 1e-12 * g["adam_losses"][0][0]      # read before the next step: correct
+    l1 = p.tf_optimization_step(g["X_u"], g["u"])
+    l2 = p.tf_optimization_step(g["X_u"], g["u"])
+    assert "%.6e" % l2 == "%.6e" % g["adam_losses"][0][2] and float(l0) == float(l0)       # resolved values stay valid
+    with pytest.raises(RuntimeError):
+        float(l1)                                                                          # never read, now stale
