@@ -57,6 +57,9 @@ constexpr int ROUND = CHAINS * TILE;      // 32 points per CTA round
 #ifndef PINN_WG_ROLLED
 #define PINN_WG_ROLLED 0
 #endif
+#ifndef PINN_WG_FAST
+#define PINN_WG_FAST 0                    // experiment (unmeasured): unconditional weight-gradient operand loads, see wgrad_task
+#endif
 constexpr int RING = PINN_RING;           // Z-bar ring slots per chain warp
 
 // shared memory carve-up (doubles)
@@ -69,7 +72,9 @@ constexpr int SM_RING = SM_STASH + CHAINS * STASH_PER_WARP;
 constexpr int SM_XT = SM_RING + CHAINS * RING * 640;
 constexpr int SM_RED = SM_XT + CHAINS * 2 * 16;
 constexpr int SM_BAR = SM_RED + 256;      // 1 + 2*CHAINS*RING mbarriers
-constexpr int SM_DOUBLES = SM_BAR + 1 + 2 * CHAINS * RING + 2;   // + phase-offset barrier
+constexpr int SM_SPECIAL = SM_BAR + 1 + 2 * CHAINS * RING + 2;   // + phase-offset barrier; then (PINN_WG_FAST) a [32 rows][W] page:
+                                                                 // column 0 = the bias ones-row (1 on the value stream's rows 0..7), column 1 = 0
+constexpr int SM_DOUBLES = SM_SPECIAL + (PINN_WG_FAST ? 32 * W : 0);
 constexpr int SMEM_BYTES = SM_DOUBLES * 8;   // ~195 KB
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -171,6 +176,28 @@ __device__ __forceinline__ void wgrad_task(double (&acc)[3][2], const Own& o, co
       w0x[s] = i < W ? sc0 * Wsm[i] : 0.0;
       w0t[s] = i < W ? sc1 * Wsm[W + i] : 0.0;
     }
+  }
+  if (L >= 2 && PINN_WG_FAST) {
+    // Experiment for the operand-fetch overhead seen in profiles/ncu_burgers_v2_r01_lines.md (2.2 instructions per operand per
+    // DMMA): choose each owned tile's A and B column pointer ONCE -- a padded lane points into the special page (ones-row or
+    // zeros) instead of being predicated -- so that the unrolled k loop is one LDS per operand with an immediate offset.
+    const double* SP = Wsm - SM_W + SM_SPECIAL;
+    const double* ap[3];
+    const double* bp[3];
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
+      const int i = 8 * o.mt[s] + g, j = 8 * o.nt[s] + g;
+      ap[s] = (i < W ? Aop + i : (i == W ? SP : SP + 1)) + q * W;
+      bp[s] = (j < W ? ZB + j : SP + 1) + q * W;
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+      const int off = (8 * (ks >> 1) + 4 * (ks & 1)) * W;       // physical row 8*stream + 4*(ks&1) (+ q, folded into the pointers)
+#pragma unroll
+      for (int s = 0; s < 3; s++)
+        if (s < o.n) dmma(acc[s], ap[s][off], bp[s][off]);      // warp-uniform
+    }
+    return;
   }
   if (L >= 2 && PINN_WG_ROLLED) {
     // regular hidden layers: rolled k loop (keeps the kernel within the instruction cache); slots 0,1 always exist
@@ -276,6 +303,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
 
+  if (PINN_WG_FAST)
+    for (int i = threadIdx.x; i < 32 * W; i += THREADS) sm[SM_SPECIAL + i] = (i % W == 0 && i / W < 8) ? 1.0 : 0.0;
   if (threadIdx.x == 0) {
     mbar_init(bars, 1);
     for (int i = 0; i < CHAINS * RING; i++) {
