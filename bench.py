@@ -3,21 +3,28 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload (config.workload): BASELINE.json configs[1] -- 1D Burgers, [2,20x8,1] tanh MLP, N_f = 100 000 collocation
-points per GPU (+ N_u = 100 data points), one Adam training step = fused loss/gradient evaluation + on-device
-Adam update.  A "step" is one pass of that hot path.  N > 1 (torchrun): collocation points are sharded, weak
-scaling (100 000 per GPU), one ncclAllReduce of [gradient | loss] per step.
+Workload (config.workload, identical on both arms): BASELINE.json configs[1] -- 1D Burgers, [2,20x8,1] tanh MLP,
+N_f = 100 000 collocation points per GPU (+ N_u = 100 data points), one Adam training step = fused loss/gradient
+evaluation + on-device Adam update.  A "step" is one pass of that hot path.  N > 1 (torchrun): collocation points are
+sharded, weak scaling (100 000 per GPU), one exchange of [gradient | loss] (3024 doubles) per step.
 
-value   : whole-job collocation points / second, inputs resident in HBM, each step timed with CUDA events on the
-          launching stream (L2 flushed between timed iterations), max over ranks.
-e2e     : the same metric through the public API with HOST buffers: every step uploads that step's collocation
-          batch from pinned host memory (pinn_set_collocation) and reads the loss back (pinn_adam_step(&loss)).
-roofline: fused kernel alone (CUDA events); algorithmic FLOPs = 24*S per collocation point + 6*S per data point
-          (S = 2860 weight entries) against the MEASURED FP64 pipe peak of this pool's B200
-          (profiles/microbench/fp64_peak_r01.jsonl: DMMA.8x8x4 37.0 TFLOP/s; MEASURED_PEAKS.json has no FP64 figure).
-          The path is FP64-pipe-bound (4 300 FLOP per HBM byte); the HBM fraction is reported beside it.
-cpu_baseline / --impl reference: the restated reference (oracle/reference_port.py: nested reverse-mode autograd,
-          torch CPU fp64, TF-2.0 Adam semantics) timed on this box's host cores.
+value    : whole-job collocation points / second, inputs resident in HBM, each step timed with CUDA events on the
+           launching stream (L2 flushed between timed iterations), max over ranks.
+e2e      : the same metric through the public API with HOST buffers: every step hands over that step's collocation batch in
+           pinned host memory and reads the loss back (pinn_adam_step(&loss)).
+roofline : fused kernel alone (CUDA events); algorithmic FLOPs = 24*S per collocation point + 6*S per data point
+           (S = 2860 weight entries) against the MEASURED FP64 pipe peak of this pool's B200
+           (profiles/microbench/fp64_peak_r01.jsonl: DMMA.8x8x4 37.0 TFLOP/s, which is also the HGX B200 datasheet figure;
+           MEASURED_PEAKS.json has no FP64 entry).  The path is FP64-pipe-bound (4 300 FLOP per HBM byte); the HBM fraction is
+           reported beside it.
+cpu_baseline / --impl reference: the restated reference (oracle/reference_port.py: nested reverse-mode autograd, torch CPU
+           fp64, TF-2.0 Adam semantics) timed on this box's host cores (fixed thread count, printed with nproc).
+parity_check (N > 1): before anything is timed, loss/gradient, 3 Adam steps and 4 L-BFGS iterations on the SHARDED handles are
+           compared with a world = 1 handle holding the whole point set on rank 0; the run fails when they differ by > 1e-10.
+cfg5     : BASELINE configs[4] -- N_f = 2 000 000 GLOBAL points strong-scaled over the N GPUs of this run (N = 1: all on one
+           GPU), Adam ms/step and L-BFGS ms/iteration.
+extras (N = 1): the other SURVEY section-8 configurations (cfg 1: N_f = 10 000; cfg 4: identification N = 2000; Schrodinger;
+           discrete time), each with its own cpu_baseline.
 """
 import argparse
 import json
@@ -40,11 +47,23 @@ S_WEIGHTS = 2 * 20 + 7 * 400 + 20            # 2860
 FLOP_PER_COLLOC = 24 * S_WEIGHTS             # 68 640 (forward 8S, input adjoint 8S, weight gradient 8S)
 FLOP_PER_DATA = 6 * S_WEIGHTS                # one stream
 N_F_PER_GPU = 100_000
+N_F_CFG5 = 2_000_000
 N_U = 100
 LB, UB = np.array([-1.0, 0.0]), np.array([1.0, 0.99])
 NU = 0.01 / np.pi
 ADAM_LR = 1e-3
-FP64_PEAK_TFLOPS_FALLBACK = 37.0
+FP64_PEAK_TFLOPS_DATASHEET = 37.0            # HGX B200 FP64 / FP64 tensor (dense), per GPU
+CPU_THREADS = 16                             # reference arm: fixed (round-1 calibration: 8-16 threads are fastest for torch's
+                                             # small-tensor ops on this pool's 128-CPU hosts; more threads are slower)
+PARITY_TOL = 1e-10
+NLS_LAYERS = [2, 100, 100, 100, 100, 2]
+NLS_LB, NLS_UB = np.array([-5.0, 0.0]), np.array([5.0, np.pi / 2])
+NLS_S = 2 * 100 + 3 * 100 * 100 + 100 * 2    # 30 400
+
+
+def workload_string(n_f):
+    return ("1d-burgers inf_cont [2,20x8,1] tanh, N_f=%d collocation points per GPU, N_u=100, Adam lr 1e-3, fp64 "
+            "(BASELINE configs[1])" % n_f)
 
 
 def fp64_peak():
@@ -57,109 +76,32 @@ def fp64_peak():
                 best = max(best or 0.0, d["dmma_tflops"])
     except Exception:
         pass
-    return (best, "measured (profiles/microbench/fp64_peak_r01.jsonl, DMMA.8x8x4)") if best else \
-        (FP64_PEAK_TFLOPS_FALLBACK, "fallback")
+    return (best, "measured (profiles/microbench/fp64_peak_r01.jsonl, DMMA.8x8x4); datasheet %.1f" % FP64_PEAK_TFLOPS_DATASHEET) \
+        if best else (FP64_PEAK_TFLOPS_DATASHEET, "datasheet fallback")
+
+
+def _ncu_summary(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from a committed `ncu --set full` summary under profiles/."""
+    for rnd in ("r02", "r01"):
+        path = os.path.join(ROOT, "profiles", "ncu_%s_%s_summary.csv" % (name, rnd))
+        try:
+            tot = 0.0
+            for line in open(path):
+                f = line.strip().split(",")
+                if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(f[1], None)
+                    if mult is None:
+                        return None, None
+                    tot += float(f[2]) * mult
+            if tot:
+                return tot, os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
 
 
 def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel, per launch, from the committed ncu --set full
-    capture (profiles/ncu_burgers_v2_r01_summary.csv)."""
-    try:
-        tot = 0.0
-        for line in open(os.path.join(ROOT, "profiles", "ncu_burgers_v2_r01_summary.csv")):
-            f = line.strip().split(",")
-            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(f[1], None)
-                if mult is None:
-                    return None
-                tot += float(f[2]) * mult
-        return tot or None
-    except Exception:
-        return None
-
-
-def measure_extras(pinn_cabi, n_f):
-    """Other SURVEY section-8 configurations, measured briefly on the same box (not the headline metric)."""
-    out = {}
-    try:
-        X_f, X_u, u = synthetic_problem(4321, n_f)
-        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, LAYERS, LB, UB)
-        p.set_pde_params([NU]); p.set_data(X_u, u); p.set_collocation(X_f[:, 0], X_f[:, 1]); p.set_weights(init_weights())
-        for _ in range(20):
-            p.adam_step(ADAM_LR, sync=False)
-        p.sync()
-        p.lbfgs(2, learning_rate=0.8, n_correction=50, tol_fun=float(np.finfo(float).eps))   # allocate history buffers
-        t0 = time.perf_counter()
-        r = p.lbfgs(60, learning_rate=0.8, n_correction=50, tol_fun=float(np.finfo(float).eps), sync_every=10)
-        dt = time.perf_counter() - t0
-        out["burgers_lbfgs"] = {"config": "BASELINE configs[1] L-BFGS phase: N_f=%d, lr 0.8, 50 corrections, sync every 10 its" % n_f,
-                                "ms_per_iteration": dt / max(1, r["n_iter"]) * 1e3, "points_per_s": n_f * r["n_iter"] / dt,
-                                "iterations": r["n_iter"]}
-        p.close()
-    except Exception as e:  # pragma: no cover
-        out["burgers_lbfgs"] = {"error": str(e)}
-    try:
-        rng = np.random.default_rng(7)
-        X_u = LB + (UB - LB) * rng.random((2000, 2)); u = rng.uniform(-1, 1, (2000, 1))
-        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_IDE, LAYERS, LB, UB)
-        p.set_data(X_u, u); p.set_weights(np.concatenate([init_weights(), [0.0, -6.0]]))
-        for _ in range(10):
-            p.adam_step(ADAM_LR, sync=False)
-        p.sync(); t0 = time.perf_counter()
-        for _ in range(100):
-            p.adam_step(ADAM_LR, sync=False)
-        p.sync(); dt = (time.perf_counter() - t0) / 100
-        out["burgers_identification"] = {"config": "BASELINE configs[3]: N=2000 data=collocation points, lambda_1, lambda_2 trainable",
-                                         "ms_per_step": dt * 1e3, "points_per_s": 2000 / dt}
-        p.close()
-    except Exception as e:  # pragma: no cover
-        out["burgers_identification"] = {"error": str(e)}
-    try:
-        L = [2, 100, 100, 100, 100, 2]
-        lb, ub = np.array([-5.0, 0.0]), np.array([5.0, np.pi / 2])
-        rng = np.random.default_rng(9)
-        X_f = lb + (ub - lb) * rng.random((20000, 2)); tb = rng.uniform(0, ub[1], (50, 1)); x0 = rng.uniform(-5, 5, (50, 1))
-        uv0 = np.stack([2 / np.cosh(x0[:, 0]), 0 * x0[:, 0]], 1)
-        from neuralnetwork import _glorot_normal
-        p = pinn_cabi.Pinn(pinn_cabi.NLS_INF, L, lb, ub)
-        p.set_collocation(X_f[:, 0], X_f[:, 1]); p.set_boundary(tb); p.set_data(x0, uv0)
-        p.set_weights(_glorot_normal(L, np.random.default_rng(1234)))
-        for _ in range(3):
-            p.adam_step(0.05, 0.99, 0.999, 0.1, sync=False)
-        p.sync(); t0 = time.perf_counter()
-        for _ in range(20):
-            p.adam_step(0.05, 0.99, 0.999, 0.1, sync=False)
-        p.sync(); dt = (time.perf_counter() - t0) / 20
-        k_ms = p.time_kernel_ms(5) / 5
-        flops = 20150 * 24 * 30400.0
-        out["schrodinger"] = {"config": "BASELINE configs[2]: [2,100x4,2], N_f=20000, N_0=N_b=50, Adam lr .05 b1 .99 eps .1",
-                              "ms_per_step": dt * 1e3, "points_per_s": 20000 / dt, "kernel_ms": k_ms,
-                              "roofline_frac_fp64": flops / (k_ms * 1e-3) / 1e12 / fp64_peak()[0]}
-        p.close()
-    except Exception as e:  # pragma: no cover
-        out["schrodinger"] = {"error": str(e)}
-    try:
-        q = 500
-        L = [1, 50, 50, 50, q + 1]
-        rng = np.random.default_rng(11)
-        from neuralnetwork import _glorot_normal
-        x0 = rng.uniform(-1, 1, (250, 1)); u0 = -np.sin(np.pi * x0)
-        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_DISC, L, [-1.0], [1.0])
-        p.set_pde_params([NU, 0.8]); p.set_irk(rng.standard_normal((q + 1, q)) / q); p.set_boundary(np.array([-1.0, 1.0]))
-        p.set_data(x0, u0); p.set_weights(_glorot_normal(L, np.random.default_rng(1234)))
-        for _ in range(5):
-            p.adam_step(1e-3, eps=1e-8, sync=False)
-        p.sync(); t0 = time.perf_counter()
-        for _ in range(50):
-            p.adam_step(1e-3, eps=1e-8, sync=False)
-        p.sync(); dt = (time.perf_counter() - t0) / 50
-        out["burgers_discrete_time"] = {"config": "1d-burgers/inf_disc_burgers.py: [1,50,50,50,501], N=250 + 2 boundary points, q=500 "
-                                                  "(synthetic stage matrix), generic fused kernel", "ms_per_step": dt * 1e3,
-                                        "points_per_s": 250 / dt}
-        p.close()
-    except Exception as e:  # pragma: no cover
-        out["burgers_discrete_time"] = {"error": str(e)}
-    return out
+    return _ncu_summary("burgers_v2")[0]
 
 
 def hbm_peak():
@@ -177,9 +119,14 @@ def synthetic_problem(seed, n_f):
     return X_f, X_u, u
 
 
-def init_weights():
+def init_weights(layers=None):
     from neuralnetwork import _glorot_normal
-    return _glorot_normal(LAYERS, np.random.default_rng(1234))
+    return _glorot_normal(layers or LAYERS, np.random.default_rng(1234))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
 class ClockSampler(object):
@@ -220,74 +167,307 @@ class ClockSampler(object):
                 "samples": len(self.samples)}
 
 
-def time_reference_port(n_f, steps, warmup, seed=1234):
-    """The restated reference on the host cores: loss + flat gradient (nested reverse mode) + Adam update."""
-    import torch
-    from oracle import reference_port as rp
-    # Thread count: torchrun exports OMP_NUM_THREADS=1 (cripples this arm) and "every logical CPU" oversubscribes
-    # torch's small-tensor ops badly (measured: 4x slower per doubling past the core count).  Calibrate on a small
-    # problem and keep the fastest count -- the reference arm gets the best the host can give it.
+# ------------------------------------------------------------------------------------------------ CPU (reference) arm
+def cpu_threads():
+    """Thread count of the CPU arm: fixed per box (min(16, CPUs available)), so that repeated runs are comparable.
+    torchrun exports OMP_NUM_THREADS=1, which would cripple this arm, hence the explicit set_num_threads."""
     try:
         ncpu = len(os.sched_getaffinity(0))
     except Exception:
         ncpu = os.cpu_count() or 1
-    Xc, Xuc, uc = synthetic_problem(seed + 1, max(2000, n_f // 4))
+    return max(1, min(CPU_THREADS, ncpu)), ncpu
+
+
+def time_port_steps(problem, w, steps, warmup, lr=ADAM_LR, b1=0.9, b2=0.999, eps=None):
+    """Mean seconds per (loss + flat gradient + Adam update) of the restated reference on the host cores."""
+    from oracle import reference_port as rp
+    st = rp.adam_init(w.size)
+    ts, f = [], None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        f, g = rp.loss_and_flat_grad(problem, w)
+        w = rp.adam_update(w, g, st, lr, b1, b2, eps)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)), f
+
+
+def time_reference_port(n_f, steps, warmup, seed=1234, budget_s=110.0):
+    """The restated reference on the host cores: loss + flat gradient (nested reverse mode) + Adam update.
+    Bounded sample: the whole (warmup + steps) run stays within ~budget_s whatever --steps the caller passes; throughput in
+    points/s is nearly size-independent at these sizes (1.5e5 - 4e5 pts/s from N_f = 1e4 to 1e5)."""
+    import torch
+    from oracle import reference_port as rp
+    threads, ncpu = cpu_threads()
+    torch.set_num_threads(threads)
+    Xc, Xuc, uc = synthetic_problem(seed + 1, 5000)
     pbc = rp.BurgersInference(LAYERS, LB, UB, NU, Xc, Xuc, uc)
     wc = init_weights()
-    best_t, best_n = None, 1
-    for cand in (1, 2, 4, 8, 16, 32, 64, 128):
-        if cand > ncpu:
-            break
-        torch.set_num_threads(cand)
-        rp.loss_and_flat_grad(pbc, wc)
-        dt = 1e30
-        for _ in range(3):                       # best of three: a single timing is too noisy to rank thread counts
-            t0 = time.perf_counter()
-            rp.loss_and_flat_grad(pbc, wc)
-            dt = min(dt, time.perf_counter() - t0)
-        if best_t is None or dt < best_t:
-            best_t, best_n = dt, cand
-        elif dt > 2.0 * best_t:
-            break
-    torch.set_num_threads(best_n)
-    # bounded sample: keep the whole (warmup + steps) run within ~2.5 minutes whatever --steps the caller passes; throughput
-    # in points/s is nearly size-independent at these sizes (1.5e5 - 3e5 pts/s from N_f = 1e4 to 1e5)
-    est_step = best_t * n_f / max(1, Xc.shape[0])
-    budget_s = 110.0
+    rp.loss_and_flat_grad(pbc, wc)
+    t0 = time.perf_counter()
+    rp.loss_and_flat_grad(pbc, wc)
+    est_step = (time.perf_counter() - t0) * n_f / 5000.0
     if est_step * (steps + warmup) > budget_s:
         n_f = max(2000, int(n_f * budget_s / (est_step * (steps + warmup))))
     X_f, X_u, u = synthetic_problem(seed, n_f)
     pb = rp.BurgersInference(LAYERS, LB, UB, NU, X_f, X_u, u)
-    w = init_weights()
-    st = rp.adam_init(w.size)
-    ts = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        f, g = rp.loss_and_flat_grad(pb, w)
-        w = rp.adam_update(w, g, st, ADAM_LR)
-        if i >= warmup:
-            ts.append(time.perf_counter() - t0)
-    return float(np.mean(ts)), torch.get_num_threads(), f, n_f
+    sec, f = time_port_steps(pb, init_weights(), steps, warmup)
+    return sec, threads, f, n_f
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    n_f = N_F_PER_GPU
+    n_f = args.n_f
     sec, cores, _, n_used = time_reference_port(n_f, args.steps, args.warmup)
+    _, ncpu = cpu_threads()
     val = n_used / sec
     line = {
         "impl": "reference", "metric": "collocation-points/sec per training step (1D Burgers 8x20 tanh, Adam step)",
         "value": val, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "1d-burgers inf_cont [2,20x8,1] tanh, N_f=%d per step sample, N_u=100, Adam lr 1e-3 (BASELINE configs[1])" % n_used},
-        "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} Adam steps of N_f={n_used} after {args.warmup} warm-up, oracle/reference_port.py "
-                                   "(TF-free restatement; TensorFlow 2.0 is not installable here)"},
+        "config": {"workload": workload_string(n_f)},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "nproc": ncpu, "kind": "port",
+                         "sample": f"{args.steps} Adam steps on a bounded sample of N_f={n_used} points after {args.warmup} warm-up, "
+                                   "oracle/reference_port.py (TF-free restatement of the reference's nested-tape step; "
+                                   "TensorFlow 2.0 is not installable here)"},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU helpers
+def timed_adam_steps(p, steps, flush, lr=ADAM_LR, b1=0.9, b2=0.999, eps=1e-7, ev0=0):
+    """Per-step device times (ms): CUDA events on the launching stream around each asynchronous step."""
+    for i in range(steps):
+        if flush:
+            p.flush_l2()
+        p.event_record(ev0 + 2 * i)
+        p.adam_step(lr, b1, b2, eps, sync=False)
+        p.event_record(ev0 + 2 * i + 1)
+    p.sync()
+    return [p.event_elapsed_ms(ev0 + 2 * i, ev0 + 2 * i + 1) for i in range(steps)]
+
+
+def timed_lbfgs(p, iters, ev0=0):
+    """Device time (ms) per L-BFGS iteration: events around one pinn_lbfgs call that enqueues all iterations blind."""
+    eps = float(np.finfo(float).eps)
+    p.lbfgs(2, learning_rate=0.8, n_correction=50, tol_fun=eps)       # allocates the history buffers
+    p.sync()
+    p.event_record(ev0)
+    r = p.lbfgs(iters, learning_rate=0.8, n_correction=50, tol_fun=eps, sync_every=iters)
+    p.event_record(ev0 + 1)
+    p.sync()
+    return p.event_elapsed_ms(ev0, ev0 + 1) / max(1, r["n_iter"]), r["n_iter"]
+
+
+def max_over_ranks(dist, v):
+    if dist is None:
+        return float(v)
+    import torch
+    tt = torch.tensor([float(v)], dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt.item())
+
+
+def parity_check(pinn_cabi, dist, p, rank, local_rank, world, n_f, X_u, u):
+    """Sharded (world ranks) against whole-set (one GPU, rank 0) evaluation of the SAME points the bench times: loss and
+    gradient, 3 Adam steps, 4 L-BFGS iterations.  Every rank executes the same number of exchanges."""
+    eps = float(np.finfo(float).eps)
+    w0 = init_weights()
+    p.set_weights(w0); p.adam_reset()
+    lN, gN, _ = p.loss_grad()
+    aN = [p.adam_step(ADAM_LR) for _ in range(3)]
+    wN = p.get_weights()
+    p.set_weights(w0); p.adam_reset()
+    rN = p.lbfgs(4, learning_rate=0.8, n_correction=50, tol_fun=eps, sync_every=2, want_x_final=True)
+    p.set_weights(w0); p.adam_reset()
+    p.sync()
+    dist.barrier()                       # the other ranks wait HERE (on the host), not inside an exchange kernel
+    out = [None]
+    if rank == 0:
+        whole = np.concatenate([synthetic_problem(1234 + r, n_f)[0] for r in range(world)], 0)
+        s = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, LAYERS, LB, UB, device=local_rank)
+        s.set_pde_params([NU]); s.set_data(X_u, u); s.set_collocation(whole[:, 0], whole[:, 1]); s.set_weights(w0)
+        l1, g1, _ = s.loss_grad()
+        a1 = [s.adam_step(ADAM_LR) for _ in range(3)]
+        w1 = s.get_weights()
+        s.set_weights(w0); s.adam_reset()
+        r1 = s.lbfgs(4, learning_rate=0.8, n_correction=50, tol_fun=eps, sync_every=2, want_x_final=True)
+        s.close()
+        res = {"rel_loss": abs(lN - l1) / abs(l1), "rel_grad": rel(gN, g1), "rel_adam_losses": rel(aN, a1),
+               "rel_adam_weights": rel(wN, w1), "lbfgs_iters_equal": bool(rN["n_iter"] == r1["n_iter"] and rN["n_eval"] == r1["n_eval"]),
+               "rel_lbfgs_x": rel(rN["x_final"], r1["x_final"]), "rel_lbfgs_f_hist": rel(rN["f_hist"], r1["f_hist"]),
+               "tolerance": PARITY_TOL, "points": int(whole.shape[0]), "world": world,
+               "what": "sharded handles (this run's collocation shards) vs one world=1 handle holding all points on rank 0"}
+        res["ok"] = bool(res["lbfgs_iters_equal"] and all(res[k] <= PARITY_TOL for k in
+                                                         ("rel_loss", "rel_grad", "rel_adam_losses", "rel_adam_weights",
+                                                          "rel_lbfgs_x", "rel_lbfgs_f_hist")))
+        out = [res]
+    dist.broadcast_object_list(out, src=0)
+    # replicated state really is replicated: every rank holds bit-identical weights after the sharded Adam steps
+    import torch
+    wt = torch.from_numpy(np.ascontiguousarray(wN))
+    ws = [torch.empty_like(wt) for _ in range(world)]
+    dist.all_gather(ws, wt)
+    out[0]["weights_bitwise_identical_across_ranks"] = bool(all(torch.equal(ws[0], x) for x in ws))
+    out[0]["ok"] = bool(out[0]["ok"] and out[0]["weights_bitwise_identical_across_ranks"])
+    return out[0]
+
+
+def cfg5_block(p, dist, rank, world, steps=20, iters=20):
+    """BASELINE configs[4]: N_f = 2 000 000 global points, strong-scaled over the ranks of this run."""
+    n5 = N_F_CFG5 // world
+    rng = np.random.default_rng(5000 + rank)
+    X = LB + (UB - LB) * rng.random((n5, 2))
+    p.set_collocation(X[:, 0], X[:, 1], n_global=n5 * world)
+    p.set_weights(init_weights()); p.adam_reset()
+    for _ in range(3):
+        p.adam_step(ADAM_LR, sync=False)
+    p.sync()
+    if dist is not None:
+        dist.barrier()
+    ms = timed_adam_steps(p, steps, flush=True)
+    adam_ms = max_over_ranks(dist, float(np.mean(ms)))
+    lb_ms, n_it = timed_lbfgs(p, iters)
+    lb_ms = max_over_ranks(dist, lb_ms)
+    return {"config": "BASELINE configs[4]: Burgers inf_cont, N_f=%d GLOBAL points strong-scaled over %d GPU(s) (%d per GPU), N_u=100; "
+                      "Adam lr 1e-3, then L-BFGS lr 0.8 / 50 corrections" % (n5 * world, world, n5),
+            "n_f_global": n5 * world, "n_gpus": world, "adam_ms_per_step": adam_ms, "adam_points_per_s": n5 * world / (adam_ms * 1e-3),
+            "adam_steps_timed": steps, "lbfgs_ms_per_iteration": lb_ms, "lbfgs_points_per_s": n5 * world / (lb_ms * 1e-3),
+            "lbfgs_iterations_timed": n_it, "timing": "CUDA events on the launching stream, L2 flushed between Adam steps, max over ranks"}
+
+
+def _port_baseline(make_problem, w, steps, warmup, n_pts, what, **adam):
+    import torch
+    threads, ncpu = cpu_threads()
+    torch.set_num_threads(threads)
+    sec, _ = time_port_steps(make_problem(), w, steps, warmup, **adam)
+    return {"value": n_pts / sec, "unit": "points/s", "ms_per_step": sec * 1e3, "cores": threads, "nproc": ncpu, "kind": "port",
+            "sample": "%d Adam steps after %d warm-up, %s (oracle/reference_port.py)" % (steps, warmup, what)}
+
+
+def measure_extras(pinn_cabi, n_f, with_cpu=True):
+    """Other SURVEY section-8 configurations, measured briefly on the same box (not the headline metric), each with the
+    restated reference timed on the host cores beside it."""
+    from oracle import reference_port as rp
+    out = {}
+    peak = fp64_peak()[0]
+    eps = float(np.finfo(float).eps)
+    # ---- BASELINE configs[1] L-BFGS phase at the headline size
+    try:
+        X_f, X_u, u = synthetic_problem(4321, n_f)
+        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, LAYERS, LB, UB)
+        p.set_pde_params([NU]); p.set_data(X_u, u); p.set_collocation(X_f[:, 0], X_f[:, 1]); p.set_weights(init_weights())
+        for _ in range(20):
+            p.adam_step(ADAM_LR, sync=False)
+        ms, n_it = timed_lbfgs(p, 60)
+        out["burgers_lbfgs"] = {"config": "BASELINE configs[1] L-BFGS phase: N_f=%d, lr 0.8, 50 corrections, all iterations enqueued blind" % n_f,
+                                "ms_per_iteration": ms, "points_per_s": n_f / (ms * 1e-3), "iterations": n_it}
+        p.close()
+    except Exception as e:  # pragma: no cover
+        out["burgers_lbfgs"] = {"error": str(e)}
+    # ---- BASELINE configs[0] size (the north_star target is quoted at N_f = 10 000): Adam and L-BFGS
+    try:
+        n1 = 10000
+        X_f, X_u, u = synthetic_problem(1234, n1)
+        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, LAYERS, LB, UB)
+        p.set_pde_params([NU]); p.set_data(X_u, u); p.set_collocation(X_f[:, 0], X_f[:, 1]); p.set_weights(init_weights())
+        for _ in range(20):
+            p.adam_step(ADAM_LR, sync=False)
+        p.sync()
+        ms = float(np.mean(timed_adam_steps(p, 200, flush=False)))
+        k_ms = p.time_kernel_ms(50) / 50
+        lb_ms, n_it = timed_lbfgs(p, 100)
+        d = {"config": "BASELINE configs[0] size on 1xB200: N_f=10000, N_u=100, Adam lr 1e-3; L-BFGS lr 0.8 / 50 corrections",
+             "adam_ms_per_step": ms, "adam_points_per_s": n1 / (ms * 1e-3), "kernel_ms": k_ms,
+             "roofline_frac_fp64": (n1 * FLOP_PER_COLLOC + N_U * FLOP_PER_DATA) / (k_ms * 1e-3) / 1e12 / peak,
+             "lbfgs_ms_per_iteration": lb_ms, "lbfgs_points_per_s": n1 / (lb_ms * 1e-3), "lbfgs_iterations": n_it,
+             "timing": "CUDA events, 200 back-to-back asynchronous steps (inputs 160 KB: L2-resident by nature)"}
+        p.close()
+        if with_cpu:
+            d["cpu_baseline"] = _port_baseline(lambda: rp.BurgersInference(LAYERS, LB, UB, NU, X_f, X_u, u), init_weights(), 8, 2, n1,
+                                               "N_f=10000 (the whole configuration)")
+            d["speedup_vs_cpu_baseline"] = d["adam_points_per_s"] / d["cpu_baseline"]["value"]
+        out["burgers_cfg1_10k"] = d
+    except Exception as e:  # pragma: no cover
+        out["burgers_cfg1_10k"] = {"error": str(e)}
+    # ---- BASELINE configs[3]: identification
+    try:
+        rng = np.random.default_rng(7)
+        X_u = LB + (UB - LB) * rng.random((2000, 2)); u = rng.uniform(-1, 1, (2000, 1))
+        w_ide = np.concatenate([init_weights(), [0.0, -6.0]])
+        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_IDE, LAYERS, LB, UB)
+        p.set_data(X_u, u); p.set_weights(w_ide)
+        for _ in range(20):
+            p.adam_step(ADAM_LR, sync=False)
+        p.sync()
+        ms = float(np.mean(timed_adam_steps(p, 200, flush=False)))
+        lb_ms, n_it = timed_lbfgs(p, 100)
+        d = {"config": "BASELINE configs[3]: N=2000 data=collocation points, lambda_1, lambda_2 trainable; Adam lr 1e-3, L-BFGS lr 0.8",
+             "ms_per_step": ms, "points_per_s": 2000 / (ms * 1e-3), "lbfgs_ms_per_iteration": lb_ms, "lbfgs_iterations": n_it}
+        p.close()
+        if with_cpu:
+            d["cpu_baseline"] = _port_baseline(lambda: rp.BurgersIdentification(LAYERS, LB, UB, X_u, u), w_ide, 10, 2, 2000,
+                                               "N=2000 (the whole configuration)")
+            d["speedup_vs_cpu_baseline"] = d["points_per_s"] / d["cpu_baseline"]["value"]
+        out["burgers_identification"] = d
+    except Exception as e:  # pragma: no cover
+        out["burgers_identification"] = {"error": str(e)}
+    # ---- BASELINE configs[2]: Schrodinger
+    try:
+        rng = np.random.default_rng(9)
+        n_nls = 20000
+        X_f = NLS_LB + (NLS_UB - NLS_LB) * rng.random((n_nls, 2)); tb = rng.uniform(0, NLS_UB[1], (50, 1)); x0 = rng.uniform(-5, 5, (50, 1))
+        uv0 = np.stack([2 / np.cosh(x0[:, 0]), 0 * x0[:, 0]], 1)
+        w_nls = init_weights(NLS_LAYERS)
+        p = pinn_cabi.Pinn(pinn_cabi.NLS_INF, NLS_LAYERS, NLS_LB, NLS_UB)
+        p.set_collocation(X_f[:, 0], X_f[:, 1]); p.set_boundary(tb); p.set_data(x0, uv0)
+        p.set_weights(w_nls)
+        for _ in range(3):
+            p.adam_step(0.05, 0.99, 0.999, 0.1, sync=False)
+        p.sync()
+        ms = float(np.mean(timed_adam_steps(p, 30, flush=True, lr=0.05, b1=0.99, b2=0.999, eps=0.1)))
+        p.time_kernel_ms(2)
+        k_ms = p.time_kernel_ms(10) / 10
+        flops = (n_nls + 150) * 24.0 * NLS_S
+        traffic, traffic_src = _ncu_summary("nls")
+        alg_bytes = 16.0 * (n_nls + 150) + 2 * 8.0 * 30802
+        d = {"config": "BASELINE configs[2]: [2,100x4,2], N_f=20000, N_0=N_b=50, Adam lr .05 b1 .99 eps .1",
+             "ms_per_step": ms, "points_per_s": n_nls / (ms * 1e-3), "kernel_ms": k_ms,
+             "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA.8x8x4)", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak,
+                          "unit": "TFLOP/s", "frac": flops / (k_ms * 1e-3) / 1e12 / peak, "kernel": "pinn::nls::fused_loss_grad",
+                          "algorithmic_flop_per_point": 24 * NLS_S, "traffic": traffic, "traffic_source": traffic_src,
+                          "algorithmic_bytes": alg_bytes},
+             "roofline_frac_fp64": flops / (k_ms * 1e-3) / 1e12 / peak}
+        p.close()
+        if with_cpu:
+            d["cpu_baseline"] = _port_baseline(lambda: rp.SchrodingerInference(NLS_LAYERS, NLS_LB, NLS_UB, X_f[:5000], tb, x0, uv0), w_nls,
+                                               4, 1, 5000, "bounded sample: N_f=5000 of the 20000 points", lr=0.05, b1=0.99, eps=0.1)
+            d["speedup_vs_cpu_baseline"] = d["points_per_s"] / d["cpu_baseline"]["value"]
+        out["schrodinger"] = d
+    except Exception as e:  # pragma: no cover
+        out["schrodinger"] = {"error": str(e)}
+    # ---- discrete time (SURVEY 8(f)2)
+    try:
+        q = 500
+        L = [1, 50, 50, 50, q + 1]
+        rng = np.random.default_rng(11)
+        x0 = rng.uniform(-1, 1, (250, 1)); u0 = -np.sin(np.pi * x0)
+        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_DISC, L, [-1.0], [1.0])
+        p.set_pde_params([NU, 0.8]); p.set_irk(rng.standard_normal((q + 1, q)) / q); p.set_boundary(np.array([-1.0, 1.0]))
+        p.set_data(x0, u0); p.set_weights(init_weights(L))
+        for _ in range(5):
+            p.adam_step(1e-3, eps=1e-8, sync=False)
+        p.sync()
+        ms = float(np.mean(timed_adam_steps(p, 50, flush=False, lr=1e-3, eps=1e-8)))
+        out["burgers_discrete_time"] = {"config": "1d-burgers/inf_disc_burgers.py: [1,50,50,50,501], N=250 + 2 boundary points, q=500 "
+                                                  "(synthetic stage matrix)", "ms_per_step": ms, "points_per_s": 250 / (ms * 1e-3)}
+        p.close()
+    except Exception as e:  # pragma: no cover
+        out["burgers_discrete_time"] = {"error": str(e)}
+    return out
 
 
 def main():
@@ -299,6 +479,7 @@ def main():
     ap.add_argument("--n-f", type=int, default=N_F_PER_GPU, help="collocation points per GPU (default: BASELINE configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -308,8 +489,8 @@ def main():
         args.warmup = args.warmup if args.warmup is not None else 3
         run_reference_arm(args, rank, world)
         return
-    args.steps = args.steps if args.steps is not None else 50
-    args.warmup = args.warmup if args.warmup is not None else 10
+    args.steps = args.steps if args.steps is not None else 200      # no flags: a longer timed region than the driver's K
+    args.warmup = args.warmup if args.warmup is not None else 20
     if args.warmup < 3:
         args.warmup = 3
 
@@ -324,8 +505,8 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         # Control plane (uid exchange, barriers, max over ranks) on gloo: the ONLY NCCL communicator in this process is
-        # the library's data-path one (gradient allreduce).  Two NCCL communicators with kernels in flight at the same
-        # time can deadlock (observed at 4 ranks when torch's NCCL barrier overlapped the library's allreduce).
+        # the library's data-path one.  Two NCCL communicators with kernels in flight at the same time can deadlock
+        # (observed at 4 ranks when torch's NCCL barrier overlapped the library's allreduce).
         dist.init_process_group("gloo")
         box = [pinn_cabi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
@@ -335,7 +516,7 @@ def main():
 
     def barrier():
         for hh in handle:
-            hh.sync()                      # drain the library's stream (incl. its NCCL kernels) first
+            hh.sync()                      # drain the library's stream (incl. its exchange kernels) first
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -348,6 +529,8 @@ def main():
     handle.append(p)
     import sharding
     used_p2p = sharding.connect_p2p(dist, p, world) if dist is not None else False
+    exchange = "none" if world == 1 else ("fused reduce + NVLink all-to-all push + Adam kernel (reduce_exchange, P2P stores into peer memory)"
+                                          if used_p2p else "reduce_partials + ncclAllReduce + adam_update")
     p.set_pde_params([NU])
     p.set_data(X_u, u, weight=1.0 if rank == 0 else 0.0)
     # pinned host copies of this rank's collocation batch (e2e leg uploads them every step)
@@ -359,6 +542,16 @@ def main():
     p.set_collocation_ptr(C.cast(hx_ptr, dp), C.cast(ht_ptr, dp), n_f, n_f_global)
     p.set_weights(init_weights())
 
+    # ---------------- multi-GPU parity BEFORE anything is timed: sharded vs whole-set evaluation of the timed points
+    parity = None
+    if dist is not None:
+        parity = parity_check(pinn_cabi, dist, p, rank, local_rank, world, n_f, X_u, u)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU parity check failed", "parity_check": parity}), flush=True)
+            barrier()
+            os._exit(3)
+
     # ---------------- device-resident steps, CUDA events per step, L2 flushed between timed iterations
     for _ in range(args.warmup):
         p.adam_step(ADAM_LR, sync=False)
@@ -366,52 +559,42 @@ def main():
     l0 = p.launch_count()
     with ClockSampler(local_rank) as clocks:
         t_wall0 = time.perf_counter()
-        for i in range(args.steps):
-            p.flush_l2()
-            p.event_record(2 * i)
-            p.adam_step(ADAM_LR, sync=False)
-            p.event_record(2 * i + 1)
-        p.sync()
+        ms_steps = timed_adam_steps(p, args.steps, flush=True)
         barrier()
         launches = p.launch_count() - l0          # kernels of this library launched inside the timed region
         wall = time.perf_counter() - t_wall0
-        # keep the sampler alive for at least ~1.5 s of load so that it sees clocks under load.  The number of extra steps
-        # is decided by rank 0 and broadcast: every rank MUST execute the same number of exchanges (a time-based loop per
-        # rank deadlocks the collective as soon as the counts differ).
+        # keep the sampler alive for at least ~1.5 s of load so that it sees clocks under load; the same (fixed) number of
+        # extra steps on every rank -- ranks MUST execute the same number of exchanges
         extra = int(max(0.0, 1.5 - wall) / max(wall / args.steps, 1e-5)) + 1
         if dist is not None:
             te = torch.tensor([extra], dtype=torch.int64)
             dist.broadcast(te, src=0)
             extra = int(te.item())
-        for _ in range(extra):
+        long_ms = timed_adam_steps(p, min(extra, 2000), flush=False, ev0=2 * args.steps)
+        for _ in range(max(0, extra - 2000)):
             p.adam_step(ADAM_LR, sync=False)
         p.sync()
         barrier()
-    ms_steps = [p.event_elapsed_ms(2 * i, 2 * i + 1) for i in range(args.steps)]
-    ms_step = float(np.mean(ms_steps))
-    # launches inside the timed region: world == 1: fused + reduce_adam; world > 1: fused + reduce (+ NCCL) + adam
+    ms_step = max_over_ranks(dist, float(np.mean(ms_steps)))
     launches_per_step = launches / args.steps
-    if dist is not None:
-        tt = torch.tensor([ms_step], dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_step = float(tt.item())
     value = n_f_global / (ms_step * 1e-3)
 
     # ---------------- fused kernel alone (roofline)
     barrier()
     p.time_kernel_ms(3)
-    k_iters = 20
-    ms_kernel = p.time_kernel_ms(k_iters) / k_iters
+    k_iters = 50
+    ms_kernel = min(p.time_kernel_ms(k_iters) / k_iters for _ in range(3))
     flops = n_f * FLOP_PER_COLLOC + (N_U * FLOP_PER_DATA if rank == 0 else 0)
     peak, peak_src = fp64_peak()
     hbm, hbm_src = hbm_peak()
     achieved = flops / (ms_kernel * 1e-3) / 1e12
     alg_bytes = 16.0 * n_f + 8.0 * 3021 + 8.0 * 3024
+    traffic, traffic_src = _ncu_summary("burgers_v2")
     roofline = {"bound": "tensor", "pipe": "fp64 (DMMA.8x8x4 + DFMA share one pipe)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic_bytes(),
-                "traffic_unit": "bytes per launch (dram read+write, ncu --set full, profiles/ncu_burgers_v2_r01_summary.csv)",
-                "algorithmic_bytes": alg_bytes,
-                "kernel": "pinn::burgers::fused_loss_grad", "kernel_ms": ms_kernel,
+                "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                "traffic_unit": "bytes per launch (dram read+write, ncu --set full, %s)" % traffic_src,
+                "algorithmic_bytes": alg_bytes, "algorithmic_flop_per_launch": flops,
+                "kernel": "pinn::burgers2::fused_loss_grad", "kernel_ms": ms_kernel,
                 "hbm": {"achieved": alg_bytes / (ms_kernel * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                         "frac": alg_bytes / (ms_kernel * 1e-3) / 1e9 / hbm, "peak_source": hbm_src,
                         "note": "algorithmic bytes 16 B/point + weights in + gradient out; the path is FP64-bound"}}
@@ -433,11 +616,7 @@ def main():
             setter(C.cast(hx_ptr, dp), C.cast(ht_ptr, dp), n_f, n_f_global)
             lv = p.adam_step(ADAM_LR, sync=True)
         barrier()
-        sec = (time.perf_counter() - t0) / args.steps
-        if dist is not None:
-            tt = torch.tensor([sec], dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            sec = float(tt.item())
+        sec = max_over_ranks(dist, (time.perf_counter() - t0) / args.steps)
         return sec, lv
 
     e2e_copy_s, loss = e2e_loop(False)
@@ -449,15 +628,26 @@ def main():
            "mode": "mapped (zero-copy: kernel reads the pinned batch over PCIe)" if e2e_map_s <= e2e_copy_s else "copy",
            "copy_mode": {"value": n_f_global / e2e_copy_s, "ms_per_step": e2e_copy_s * 1e3},
            "mapped_mode": {"value": n_f_global / e2e_map_s, "ms_per_step": e2e_map_s * 1e3}}
+    kernel_info = p.kernel_info()
+
+    # ---------------- BASELINE configs[4]: 2 000 000 global points over the GPUs of this run (replaces p's collocation set)
+    cfg5 = None
+    if not args.no_cfg5:
+        barrier()
+        try:
+            cfg5 = cfg5_block(p, dist, rank, world)
+        except Exception as e:  # pragma: no cover
+            cfg5 = {"error": str(e)}
+        barrier()
 
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
-        extras = measure_extras(pinn_cabi, n_f)
+        extras = measure_extras(pinn_cabi, n_f, with_cpu=not args.no_cpu_baseline)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sec, cores, _, n_used = time_reference_port(n_f, 12, 3)
-        cpu = {"value": n_used / sec, "unit": "points/s", "cores": cores, "kind": "port",
-               "sample": f"12 Adam steps of N_f={n_used} after 3 warm-up, oracle/reference_port.py (nested reverse-mode, torch CPU fp64)"}
+        sec, cores, _, n_used = time_reference_port(n_f, 10, 3, budget_s=40.0)
+        cpu = {"value": n_used / sec, "unit": "points/s", "cores": cores, "nproc": cpu_threads()[1], "kind": "port",
+               "sample": f"10 Adam steps of N_f={n_used} after 3 warm-up, oracle/reference_port.py (nested reverse-mode, torch CPU fp64)"}
 
     if rank == 0:
         line = {
@@ -465,14 +655,23 @@ def main():
             "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "ms_per_step_median": float(np.median(ms_steps)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "1d-burgers inf_cont [2,20x8,1] tanh, N_f=%d per GPU (%d global), N_u=100, Adam lr 1e-3 "
-                                   "(BASELINE configs[1])" % (n_f, n_f_global),
+            "config": {"workload": workload_string(n_f), "global_points": n_f_global,
                        "l2": "flushed (256 MB memset) between timed iterations; inputs are 1.6 MB, the path is compute-bound",
-                       "parallelism": "dp%d (collocation shards; per step one exchange of 3024 doubles: %s)" % (world, "fused NVLink P2P gather-reduce-Adam kernel" if used_p2p else ("ncclAllReduce" if world > 1 else "none"))},
+                       "parallelism": "dp%d (collocation shards; per step one exchange of 3024 doubles = 24 KB per rank pair: %s)" % (world, exchange)},
             "clocks": clocks.summary(),
             "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches_per_step,
-            "roofline": roofline, "kernel_info": p.kernel_info(), "final_loss": loss,
+            "roofline": roofline, "kernel_info": kernel_info, "final_loss": loss,
+            "long_run": {"steps": len(long_ms), "ms_per_step": float(np.mean(long_ms)), "ms_per_step_median": float(np.median(long_ms)),
+                         "note": "back-to-back asynchronous steps without L2 flush, timed per step with CUDA events (this rank)"},
         }
+        if world > 1:
+            line["nvlink_bytes_per_step"] = {"per_rank_sent": (world - 1) * 3024 * 8 if used_p2p else None,
+                                             "note": "push exchange: every rank stores its 3024-double vector into each peer's buffer"
+                                             if used_p2p else "NCCL allreduce (ring/tree chosen by NCCL)"}
+        if parity is not None:
+            line["parity_check"] = parity
+        if cfg5 is not None:
+            line["cfg5"] = cfg5
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if extras is not None:

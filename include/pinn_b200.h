@@ -63,13 +63,16 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
 int pinn_destroy(pinn_t* h);
 int pinn_nccl_unique_id(void* out128);
 
-/* Fused NVLink P2P exchange (optional, world > 1): instead of reduce -> ncclAllReduce -> Adam, every rank publishes its
- * reduced [gradient | loss] vector in a small IPC-exported buffer and ONE kernel per rank gathers all peers' vectors with
- * P2P loads over NVLink, sums them in rank order (bitwise identical on all ranks) and applies Adam.  Usage: each rank calls
+/* Fused NVLink push exchange (world > 1; replaces reduce -> ncclAllReduce -> Adam by ONE kernel per evaluation): every rank
+ * owns a small IPC-exported exchange buffer; the tail kernel of an evaluation reduces the per-CTA partials, STORES the
+ * result into every peer's buffer over NVLink (P2P stores, nobody pulls), waits on its local flags, sums the ranks' vectors
+ * in a fixed order (bitwise identical on all ranks) and applies Adam in the same pass.  Usage: each rank calls
  * pinn_p2p_export (64-byte cudaIpcMemHandle), the handles are all-gathered by the caller's control plane, then each rank
- * calls pinn_p2p_connect(handles[world][64]).  Without it the NCCL communicator of pinn_create is used. */
+ * calls pinn_p2p_connect(handles[world][64]).  All ranks must use the same path: if mapping fails anywhere, every rank
+ * calls pinn_p2p_enable(h, 0) and the NCCL communicator of pinn_create carries the exchange instead. */
 int pinn_p2p_export(pinn_t* h, void* out64);
 int pinn_p2p_connect(pinn_t* h, const void* handles, int world);
+int pinn_p2p_enable(pinn_t* h, int on);
 
 /* Number of entries of the flat parameter vector (net params [+2 for identification]). */
 int64_t pinn_num_params(const pinn_t* h);
@@ -117,8 +120,8 @@ int pinn_loss_grad(pinn_t* h, const double* w_or_null, double* loss_out, double*
 
 /* tf_optimization_step (utils/neuralnetwork.py:112-116) with TF-2.0 Keras Adam semantics
  * (alpha_t = lr sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= alpha_t m/(sqrt(v)+eps)).
- * loss_out == NULL: fully asynchronous (CUDA-graph replay, no host sync).  The loss is the one evaluated
- * BEFORE the update, as in the reference. */
+ * loss_out == NULL: fully asynchronous (two kernel launches enqueued on the handle's stream, no host sync; the loss goes to
+ * a device ring, see pinn_last_loss).  The loss is the one evaluated BEFORE the update, as in the reference. */
 int pinn_adam_step(pinn_t* h, double lr, double b1, double b2, double eps, double* loss_out_or_null);
 int pinn_adam_reset(pinn_t* h);
 /* Loss values of the last n asynchronous Adam steps are kept in a device ring; read the most recent one. */
@@ -135,11 +138,18 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
                int sync_every, pinn_log_cb log_cb, void* user, int* n_iter_out, int* n_eval_out, int* reason_out,
                double* x_final_or_null);
 
+/* f_hist of the last pinn_lbfgs run (custom_lbfgs.py:66-67,186-187: the initial f and the f of every evaluation, including
+ * the ones that hit a stop test and were therefore not logged).  *n_out = number of evaluations; f_hist_out may be NULL to
+ * query the count. */
+int pinn_lbfgs_history(pinn_t* h, double* f_hist_out, int capacity, int* n_out);
+
 /* predict (utils/neuralnetwork.py:151-153): forward only on (n,in_dim) points -> (n,out_dim). */
 int pinn_predict(pinn_t* h, const double* X, int64_t n, int in_dim, double* out);
-/* f_model on the stored collocation set (inf_cont_burgers.py:65-90,95-98).  out: n_colloc * n_res doubles
- * (n_res = 1 Burgers, 2 NLS: f_u then f_v per point). */
-int pinn_residual(pinn_t* h, double* f_out);
+/* f_model on the stored residual points (inf_cont_burgers.py:65-90,95-98): the collocation set, or the data points for
+ * identification (ide_cont_burgers.py:88-91).  f_out: n_rows * n_res doubles (n_res = 1 Burgers, 2 NLS: f_u then f_v per
+ * point); n_rows must equal pinn_num_residual_points(h) -- a mismatch is an error, never a short or long write. */
+int64_t pinn_num_residual_points(const pinn_t* h);
+int pinn_residual(pinn_t* h, double* f_out, int64_t n_rows);
 /* u, u_x, u_t, u_xx at arbitrary points (parity probes): out is (n, 4*out_dim), [u.., u_x.., u_t.., u_xx..]. */
 int pinn_derivatives(pinn_t* h, const double* X, int64_t n, double* out);
 

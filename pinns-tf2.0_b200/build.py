@@ -30,19 +30,22 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, out=None, extra_flags=None):
+    """out / extra_flags: build a variant of the library next to the product one (kernel experiments)."""
+    if out is None and not force and up_to_date():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    extra = os.environ.get("PINN_EXTRA_NVCC_FLAGS", "").split()
+    extra = os.environ.get("PINN_EXTRA_NVCC_FLAGS", "").split() + list(extra_flags or [])
+    out = out or LIB
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart", "-ldl"]
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -60,6 +60,21 @@ constexpr int ROUND = CHAINS * TILE;      // 32 points per CTA round
 #ifndef PINN_WG_FAST
 #define PINN_WG_FAST 0                    // experiment (unmeasured): unconditional weight-gradient operand loads, see wgrad_task
 #endif
+#ifndef PINN_WG_ROWS
+#define PINN_WG_ROWS 1                    // weight-gradient tiles owned by ROWS: warp position k < 3 owns (mt = k; nt = 0,1,2), k == 3 rests;
+#endif                                    // one A fragment feeds three DMMAs, operand pointers chosen once (no predicates in the k loop)
+#ifndef PINN_ABL_NOACT
+#define PINN_ABL_NOACT 0                  // timing ablation: no activation arithmetic in the chain warps
+#endif
+#ifndef PINN_ABL_NODMMA
+#define PINN_ABL_NODMMA 0                 // timing ablation: no chain DMMAs
+#endif
+#ifndef PINN_ABL_NOSTAGE
+#define PINN_ABL_NOSTAGE 0                // timing ablation: chain warps neither stage nor synchronise (use with PINN_ABL_NOWG)
+#endif
+#ifndef PINN_ABL_NOWG
+#define PINN_ABL_NOWG 0                   // timing ablation (wrong gradients): weight-gradient warps only do the ring handshake
+#endif
 constexpr int RING = PINN_RING;           // Z-bar ring slots per chain warp
 
 // shared memory carve-up (doubles)
@@ -74,7 +89,7 @@ constexpr int SM_RED = SM_XT + CHAINS * 2 * 16;
 constexpr int SM_BAR = SM_RED + 256;      // 1 + 2*CHAINS*RING mbarriers
 constexpr int SM_SPECIAL = SM_BAR + 1 + 2 * CHAINS * RING + 2;   // + phase-offset barrier; then (PINN_WG_FAST) a [32 rows][W] page:
                                                                  // column 0 = the bias ones-row (1 on the value stream's rows 0..7), column 1 = 0
-constexpr int SM_DOUBLES = SM_SPECIAL + (PINN_WG_FAST ? 32 * W : 0);
+constexpr int SM_DOUBLES = SM_SPECIAL + ((PINN_WG_FAST || PINN_WG_ROWS) ? 32 * W : 0);
 constexpr int SMEM_BYTES = SM_DOUBLES * 8;   // ~195 KB
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -105,6 +120,7 @@ __device__ __forceinline__ void load_rows(double (&V)[4][3][2], const double* T,
 
 // outputs of a tanh layer from its pre-activation streams (in place): Z -> (a, s z_x, s z_t, s (z_xx - 2 a z_x^2))
 __device__ __forceinline__ void act_forward(double (&Z)[4][3][2]) {
+  if (PINN_ABL_NOACT) return;
 #pragma unroll
   for (int nt = 0; nt < 3; nt++)
 #pragma unroll
@@ -121,6 +137,7 @@ __device__ __forceinline__ void act_forward(double (&Z)[4][3][2]) {
 
 // adjoints of the outputs (A, overwritten with the adjoints of the pre-activations) given the outputs H
 __device__ __forceinline__ void act_backward_out(double (&A)[4][3][2], const double (&H)[4][3][2]) {
+  if (PINN_ABL_NOACT) return;
 #pragma unroll
   for (int nt = 0; nt < 3; nt++)
 #pragma unroll
@@ -144,6 +161,13 @@ __device__ __forceinline__ void act_backward_out(double (&A)[4][3][2], const dou
 struct Own { int n; int mt[3]; int nt[3]; };
 __device__ __forceinline__ Own ownership(int l, int wg) {
   Own o;
+  if (PINN_WG_ROWS) {
+    const int k = l == 0 ? wg : ((wg - l) & 3);
+    o.n = (l == 0 ? k == 0 : k < 3) ? 3 : 0;
+    o.mt[0] = o.mt[1] = o.mt[2] = l == 0 ? 0 : (k < 3 ? k : 0);
+    o.nt[0] = 0; o.nt[1] = 1; o.nt[2] = 2;
+    return o;
+  }
   if (l == 0) {
     o.n = wg == 0 ? 2 : (wg == 1 ? 1 : 0);
     o.mt[0] = o.mt[1] = o.mt[2] = 0;
@@ -176,6 +200,41 @@ __device__ __forceinline__ void wgrad_task(double (&acc)[3][2], const Own& o, co
       w0x[s] = i < W ? sc0 * Wsm[i] : 0.0;
       w0t[s] = i < W ? sc1 * Wsm[W + i] : 0.0;
     }
+  }
+  if (PINN_WG_ROWS) {
+    // row ownership: tiles (mt; nt = 0,1,2).  B column pointers (padded columns read the zero column of the special page) and,
+    // for regular layers, the A column pointer (bias unit -> ones column, padding -> zero column) are chosen once.
+    const double* SP = Wsm - SM_W + SM_SPECIAL;
+    const int i = 8 * o.mt[0] + g;
+    const double* bp0 = ZB + g + q * W;
+    const double* bp1 = ZB + 8 + g + q * W;
+    const double* bp2 = (16 + g < W ? ZB + 16 + g : SP + 1) + q * W;
+    const double* ap = (i < W ? Aop + i : (i == W ? SP : SP + 1)) + q * W;          // L >= 2: [32 rows][W] outputs of layer L-1
+    const double* ap1 = (i < W ? Aop + i : SP + 1) + q * W;                          // L == 1: a-only stash [8 rows][W]
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+      const int st = ks >> 1;
+      const int off = (8 * st + 4 * (ks & 1)) * W;              // physical row 8*stream + 4*(ks&1) (+ q, folded into the pointers)
+      double a;
+      if (L >= 2) {
+        a = ap[off];
+      } else if (L == 1) {
+        const double av = ap1[4 * (ks & 1) * W];
+        const double sd = fma(-av, av, 1.0);
+        const double v = st == 0 ? av : (st == 1 ? sd * w0x[0] : (st == 2 ? sd * w0t[0] : -2.0 * av * sd * w0x[0] * w0x[0]));
+        a = (i == W && st == 0) ? 1.0 : v;                      // i >= W: av = 0 and w0x = w0t = 0, so v = 0
+      } else {
+        const int pr = 4 * (ks & 1) + q;
+        const double xv = Aop[pr * 2 + 0], tv = Aop[pr * 2 + 1];
+        a = i == 0 ? (st == 0 ? xv : (st == 1 ? sc0 : 0.0))
+                   : (i == 1 ? (st == 0 ? tv : (st == 2 ? sc1 : 0.0)) : ((i == 2 && st == 0) ? 1.0 : 0.0));
+      }
+      const double b0 = bp0[off], b1 = bp1[off], b2 = bp2[off];
+      dmma(acc[0], a, b0);
+      dmma(acc[1], a, b1);
+      dmma(acc[2], a, b2);
+    }
+    return;
   }
   if (L >= 2 && PINN_WG_FAST) {
     // Experiment for the operand-fetch overhead seen in profiles/ncu_burgers_v2_r01_lines.md (2.2 instructions per operand per
@@ -268,7 +327,7 @@ __device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it,
     const double* stash = sm + SM_STASH + c * STASH_PER_WARP;
     const double* Aop = L >= 2 ? stash + STASH0 + (L - 2) * STASHL : (L == 1 ? stash : sm + SM_XT + (c * 2 + (it & 1)) * 16);
     const double* ZB = sm + SM_RING + (c * RING + slot) * 640;
-    if (o.n > 0) wgrad_task<L>(acc, o, Aop, ZB, sm + SM_W, sc0, sc1, lane);
+    if (!PINN_ABL_NOWG && o.n > 0) wgrad_task<L>(acc, o, Aop, ZB, sm + SM_W, sc0, sc1, lane);
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty(bars, c, slot));
   }
@@ -303,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
 
-  if (PINN_WG_FAST)
+  if (PINN_WG_FAST || PINN_WG_ROWS)
     for (int i = threadIdx.x; i < 32 * W; i += THREADS) sm[SM_SPECIAL + i] = (i % W == 0 && i / W < 8) ? 1.0 : 0.0;
   if (threadIdx.x == 0) {
     mbar_init(bars, 1);
@@ -344,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     // The chain warps are consumed in two halves (chains 0,1 then chains 2,3).  Ring back-pressure then shifts the
     // halves by one phase: while one half runs its forward pass (which produces no weight-gradient work), the other
     // half runs its backward pass and keeps these warps -- and the FP64 pipe of every sub-partition -- busy.
-    for (int it2 = 0; it2 < 2 * my_rounds; it2++) {
+    for (int it2 = 0; it2 < (PINN_ABL_NOSTAGE ? 0 : 2 * my_rounds); it2++) {
       const int it = it2 >> 1, half = it2 & 1;
       wgrad_layer<7>(a7, wg, it, half, sm, bars, sc0, sc1, lane);
       wgrad_layer<6>(a6, wg, it, half, sm, bars, sc0, sc1, lane);
@@ -424,8 +483,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       act_forward(H);
       // the a-only stash of layer 0 (and, with RING = 3, the layer-1 stash) is still the A operand of the previous
       // tile's last tasks: wait until the layer-1 task (J = 6) has been consumed; consumers retire tasks in order
-      if (it > 0) wait_consumed(bars, c, 8 * (it - 1) + 6);
-      {
+      if (!PINN_ABL_NOSTAGE && it > 0) wait_consumed(bars, c, 8 * (it - 1) + 6);
+      if (!PINN_ABL_NOSTAGE) {
         double* r0 = stash + pg * W;
         *reinterpret_cast<double2*>(r0 + 2 * q) = make_double2(H[0][0][0], H[0][0][1]);
         *reinterpret_cast<double2*>(r0 + 8 + 2 * q) = make_double2(H[0][1][0], H[0][1][1]);
@@ -444,13 +503,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
             Z[0][nt][e] = (col < W) ? Wl[W * W + col] : 0.0;
             Z[1][nt][e] = Z[2][nt][e] = Z[3][nt][e] = 0.0;
           }
-        burgers::mma_layer(Z, H, Wl, W, 1, lane);
+        if (!PINN_ABL_NODMMA) burgers::mma_layer(Z, H, Wl, W, 1, lane);
         act_forward(Z);
 #pragma unroll
         for (int s = 0; s < 4; s++)
 #pragma unroll
           for (int nt = 0; nt < 3; nt++) { H[s][nt][0] = Z[s][nt][0]; H[s][nt][1] = Z[s][nt][1]; }
-        if (l < NHID - 1) burgers::stage_rows(stash + STASH0 + (l - 1) * STASHL, H, lane);
+        if (!PINN_ABL_NOSTAGE && l < NHID - 1) burgers::stage_rows(stash + STASH0 + (l - 1) * STASHL, H, lane);
       }
       if (PINN_PHASE_OFFSET && it == 0 && c < 2) { __syncwarp(); if (lane == 0) mbar_arrive(bars + 1 + 2 * CHAINS * RING); }
       // ---------------- output layer (20 -> 1), residual, seeds
@@ -512,12 +571,14 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
 #pragma unroll 1
       for (int l = NHID - 1; l >= 1; l--) {
         const int T = 8 * it + (7 - l), slot = T % RING;
-        if (l < NHID - 1) load_rows(H, stash + STASH0 + (l - 1) * STASHL, lane);   // outputs of layer l (l=7: registers)
+        if (!PINN_ABL_NOSTAGE && l < NHID - 1) load_rows(H, stash + STASH0 + (l - 1) * STASHL, lane);   // outputs of layer l (l=7: registers)
         act_backward_out(A, H);                                                      // A := Z-bar
-        if (T >= RING) wait_consumed(bars, c, T - RING);                             // the slot's previous task is done
-        burgers::stage_rows(sm + SM_RING + (c * RING + slot) * 640, A, lane);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
+        if (!PINN_ABL_NOSTAGE) {
+          if (T >= RING) wait_consumed(bars, c, T - RING);                           // the slot's previous task is done
+          burgers::stage_rows(sm + SM_RING + (c * RING + slot) * 640, A, lane);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
+        }
         // adjoint of the layer inputs: A_new = Z-bar * W_l^T
         {
           const double* Wl = Wsm + woff(l);
@@ -526,7 +587,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           for (int s = 0; s < 4; s++)
 #pragma unroll
             for (int nt = 0; nt < 3; nt++) An[s][nt][0] = An[s][nt][1] = 0.0;
-          burgers::mma_layer(An, A, Wl, 1, W, lane);
+          if (!PINN_ABL_NODMMA) burgers::mma_layer(An, A, Wl, 1, W, lane);
 #pragma unroll
           for (int s = 0; s < 4; s++)
 #pragma unroll
@@ -556,10 +617,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           }
         act_backward_out(A, H);
         const int T = 8 * it + 7, slot = T % RING;
-        if (T >= RING) wait_consumed(bars, c, T - RING);
-        burgers::stage_rows(sm + SM_RING + (c * RING + slot) * 640, A, lane);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
+        if (!PINN_ABL_NOSTAGE) {
+          if (T >= RING) wait_consumed(bars, c, T - RING);
+          burgers::stage_rows(sm + SM_RING + (c * RING + slot) * 640, A, lane);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
+        }
       }
     }
 

@@ -35,43 +35,22 @@ struct ReduceMap {
   int n_extra;
 };
 
-// 8 lanes per output entry: coalesced 64-byte... each lane sums every 8th CTA partial, then a 3-step shuffle
-// tree in fixed order (deterministic).  blockDim = 256 -> 32 entries per block.
-// Optional publication for the P2P exchange: the LAST block to finish makes the reduced vector visible system-wide and
-// raises this rank's flag (saves a separate one-thread launch).  pub_counter must be zero on entry and is reset.
-struct Publish {
-  unsigned long long* flag;     // nullptr: no publication
-  unsigned long long seq;
-  int* counter;
-};
-
+// 8 lanes per output entry: each lane sums every 8th CTA partial, then a 3-step shuffle tree in fixed order
+// (deterministic).  blockDim = 256 -> 32 entries per block.
 __global__ void reduce_partials(const double* __restrict__ partials, int n_cta, int stride, double* __restrict__ R,
-                                ReduceMap map, const int* __restrict__ run_flag, Publish pub) {
-  const bool skip = run_flag && *run_flag != 0;      // a skipped evaluation still publishes (ranks must not diverge)
+                                ReduceMap map, const int* __restrict__ run_flag) {
+  if (run_flag && *run_flag != 0) return;
   const int sub = threadIdx.x & 7;
   const int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
   const bool ok = i < map.n_out;
   const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
   double s = 0.0;
-  if (ok && !skip)
+  if (ok)
     for (int b = sub; b < n_cta; b += 8) s += partials[(size_t)b * stride + src];
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (ok && sub == 0 && !skip) R[i] = s;
-  if (pub.flag) {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int done = atomicAdd(pub.counter, 1);
-      if (done == (int)gridDim.x - 1) {
-        *pub.counter = 0;
-        __threadfence_system();
-        *(volatile unsigned long long*)pub.flag = pub.seq;
-        __threadfence_system();
-      }
-    }
-  }
+  if (ok && sub == 0) R[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -146,63 +125,108 @@ __global__ void reduce_adam(const double* __restrict__ partials, int n_cta, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused gather-reduce(-Adam) over NVLink peer memory (multi-GPU, one process per GPU).  Every rank's reduced vector
-// R_r = [grad | loss parts] lives in a small IPC-exported exchange buffer (2 slots + 2 flags).  After its local
-// reduction a rank publishes flag[slot] = seq; this kernel, on every rank, waits for all peers' flags, loads all R_r
-// straight from peer memory (P2P loads over NVLink / NVSwitch), sums them in RANK ORDER (so all ranks obtain bitwise
-// identical sums) and, when `adam` is set, applies the Adam update in the same pass.  Replaces
-// ncclAllReduce + adam_update (3 launches, ~40 us of latency) by one launch; NCCL remains as a fallback.
-// Slot reuse is safe with two slots: a rank publishes evaluation k+1 only after it has consumed every peer's slot of
-// evaluation k, so once all flags of k+1 are visible nobody reads slot k any more.
+// Fused reduce -> all-to-all PUSH over NVLink peer memory -> (Adam) : ONE kernel per rank and evaluation (multi-GPU, one
+// process per GPU).  Replaces reduce_partials + ncclAllReduce + adam_update (3 launches + the NCCL kernel).
+//
+// Every rank owns an IPC-exported exchange buffer   data[2 parities][world][slot_len] doubles, flag[2][world][n_blocks] u64.
+// Block b of rank r reduces its 32 entries of the per-CTA partials (fixed order), STORES them into slot [parity][r] of EVERY
+// rank's buffer (sub-lane k of an entry writes to peer k: remote stores are fire-and-forget, nobody pulls), fences, and
+// raises flag[parity][r][b] = seq on every peer.  It then waits on its LOCAL flags of all ranks for the same block --
+// a local spin, no NVLink round trips -- sums the world slots in a fixed butterfly order (bitwise identical on all ranks,
+// so replicated optimiser state never diverges) and applies Adam to its entries in the same pass.
+// seq / parity come from a device-side counter of published evaluations (identical on all ranks), so an evaluation that
+// is skipped on the device (L-BFGS stopped: *run_flag != 0 on every rank alike) consumes neither.  Two parities suffice: a
+// rank publishes evaluation k+1 only after it has seen every peer's evaluation k, and a peer publishes k only after it
+// has finished consuming k-1 (stream order), so slot parity (k+1)&1 is no longer being read anywhere.
+// The wait is bounded (~20 s by the global timer): a dead peer raises *err instead of hanging the GPU, and the update is
+// skipped; the host reports it at the next synchronising call.
 // ------------------------------------------------------------------------------------------------
 constexpr int P2P_MAX = 8;
-struct P2PPeers {
-  const double* buf[P2P_MAX];                 // peer exchange buffers: [2][slot_len] doubles, then 2 flags
-  const unsigned long long* flag[P2P_MAX];
+struct XchgPeers {
+  double* data[P2P_MAX];                 // peer exchange buffers
+  unsigned long long* flag[P2P_MAX];
   int world, rank;
+  int slot_len;                          // doubles per (parity, rank) slot
+  int n_blocks;                          // flags per (parity, rank)
 };
 
-__global__ void p2p_publish(unsigned long long* flag, unsigned long long seq) {
-  __threadfence_system();
-  *(volatile unsigned long long*)flag = seq;
-  __threadfence_system();
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
-__global__ void p2p_gather_reduce(P2PPeers peers, int slot, int slot_len, unsigned long long seq, int n, double* __restrict__ R,
-                                  int* __restrict__ err, int adam, double* __restrict__ w, double* __restrict__ m,
-                                  double* __restrict__ v, int P, int* __restrict__ step, double lr, double b1, double b2,
-                                  double eps, double* __restrict__ loss_ring, int ring) {
-  if (threadIdx.x < peers.world) {
-    const volatile unsigned long long* f = peers.flag[threadIdx.x] + slot;
-    long long spins = 0;
-    while (*f < seq) {
-      if (++spins > (1LL << 25)) { atomicExch(err, 1); break; }      // bounded: report, do not hang
-      __nanosleep(64);
-    }
-  }
+// xseq[0] = published evaluations so far, xseq[1] = blocks finished in the current launch
+__global__ void __launch_bounds__(256)
+reduce_exchange(const double* __restrict__ partials, int n_cta, int stride, ReduceMap map, const int* __restrict__ run_flag,
+                XchgPeers peers, int* __restrict__ xseq, double* __restrict__ R, int* __restrict__ err, int adam,
+                double* __restrict__ w, double* __restrict__ m, double* __restrict__ v, int P, int* __restrict__ step,
+                double lr, double b1, double b2, double eps, double* __restrict__ loss_ring, int ring) {
+  if (run_flag && *run_flag != 0) return;          // identical on every rank (replicated L-BFGS state)
+  const unsigned long long seq = (unsigned long long)(*(volatile int*)xseq) + 1;
+  const int parity = (int)(seq & 1);
+  const int sub = threadIdx.x & 7;
+  const int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const bool ok = i < map.n_out;
+  const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
+  double s = 0.0;
+  if (ok)
+    for (int b = sub; b < n_cta; b += 8) s += partials[(size_t)b * stride + src];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);          // every sub-lane holds the entry's local sum
+  // ---- push: sub-lane k stores the entry into rank k's buffer, slot [parity][my rank]
+  const size_t slot = ((size_t)parity * peers.world + peers.rank) * peers.slot_len;
+  if (ok && sub < peers.world) peers.data[sub][slot + i] = s;
   __threadfence_system();
   __syncthreads();
-  const int t = adam ? step[0] + 1 : 0;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    double s = 0.0;
-    for (int r = 0; r < peers.world; r++) s += *((const volatile double*)(peers.buf[r] + (size_t)slot * slot_len + i));
-    R[i] = s;
-    if (adam && i < P) adam_entry(w, m, v, s, i, t, lr, b1, b2, eps);
+  if (threadIdx.x < peers.world)
+    st_release_sys(peers.flag[threadIdx.x] + ((size_t)parity * peers.world + peers.rank) * peers.n_blocks + blockIdx.x, seq);
+  // ---- wait for every rank's copy of this block's entries (local flags)
+  if (threadIdx.x < peers.world) {
+    const unsigned long long* f = peers.flag[peers.rank] + ((size_t)parity * peers.world + threadIdx.x) * peers.n_blocks + blockIdx.x;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(f) < seq) {
+      if (globaltimer_ns() - t0 > 20000000000ULL) { atomicExch(err, 1); break; }
+      __nanosleep(32);
+    }
   }
-  if (adam) {
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int done = atomicAdd(step + 1, 1);
-      if (done == (int)gridDim.x - 1) {
-        __threadfence();
+  __syncthreads();
+  const bool dead = *(volatile int*)err != 0;       // a peer never published: leave R, weights and optimiser state untouched
+  // ---- sum over ranks: sub-lane k loads rank k's value from the LOCAL buffer, butterfly in a fixed order
+  double tot = 0.0;
+  if (ok && sub < peers.world)
+    tot = __ldcv(peers.data[peers.rank] + ((size_t)parity * peers.world + sub) * peers.slot_len + i);
+  tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+  tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+  tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+  const int t = adam ? step[0] + 1 : 0;
+  if (ok && sub == 0 && !dead) {
+    R[i] = tot;
+    if (adam && i < P) adam_entry(w, m, v, tot, i, t, lr, b1, b2, eps);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(xseq + 1, 1);
+    if (done == (int)gridDim.x - 1) {
+      __threadfence();
+      if (adam && !dead) {
         const volatile double* Rv = R;
         loss_ring[(t - 1) % ring] = Rv[P] + Rv[P + 1] + Rv[P + 2];
-        step[1] = 0;
         step[0] += 1;
-        __threadfence();
       }
+      xseq[1] = 0;
+      xseq[0] += 1;
+      __threadfence();
     }
   }
 }

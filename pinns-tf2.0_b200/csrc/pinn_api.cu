@@ -122,22 +122,19 @@ struct pinn_handle {
   double *d_gold = nullptr, *d_d = nullptr, *d_S = nullptr, *d_Y = nullptr, *d_xfinal = nullptr, *d_fhist = nullptr;
   int* d_logged = nullptr;
   int lb_corr_cap = 0, lb_iter_cap = 0;
+  std::vector<double> lb_fhist;             // f of every evaluation of the last pinn_lbfgs run (custom_lbfgs.py f_hist)
 
   // scratch for predict / derivatives
   double *d_px = nullptr, *d_pout = nullptr;
   long long px_cap = 0, pout_cap = 0;
 
   ncclComm_t comm = nullptr;
-  // fused NVLink P2P exchange (optim_kernels.cuh: p2p_gather_reduce)
-  double* d_xchg = nullptr;            // [2][xchg_len] doubles + 2 flags (IPC-exported)
-  int xchg_len = 0;
-  bool p2p_ready = false;
-  pinn::P2PPeers peers{};
+  // fused NVLink push exchange (optim_kernels.cuh: reduce_exchange)
+  double* d_xchg = nullptr;            // [2][world][slot_len] doubles, then [2][world][n_blocks] u64 flags (IPC-exported)
+  bool p2p_ready = false, p2p_mapped = false;
+  pinn::XchgPeers peers{};
   void* peer_base[pinn::P2P_MAX] = {nullptr};
-  unsigned long long p2p_seq = 0;
-  pinn::Publish pub{};                 // publication request for the reduction that is about to be enqueued
-  int* d_pub_counter = nullptr;
-  double* reduce_dst = nullptr;        // where reduce_partials writes: d_R, or this evaluation's exchange slot
+  int* d_xseq = nullptr;               // [0] published evaluations, [1] block counter
   int* d_p2p_err = nullptr;
 };
 
@@ -155,10 +152,19 @@ bool is_nls_net(const std::vector<int>& L) {
 }
 
 int nls_upload_points(pinn_t* h);
-int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only);
-int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only);
+int nls_launch_eval(pinn_t* h, const int* run_flag);
+int generic_launch_eval(pinn_t* h, const int* run_flag);
 int disc_upload_points(pinn_t* h);
-int p2p_exchange(pinn_t* h, bool adam, double lr, double b1, double b2, double eps);
+
+// after a stream synchronisation: has the fused P2P exchange reported a peer that never published?
+int check_p2p(pinn_t* h) {
+  if (!h->p2p_ready) return 0;
+  int e = 0;
+  if (cudaMemcpy(&e, h->d_p2p_err, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return fail("reading the P2P error flag failed");
+  if (e) return fail("P2P exchange timed out waiting for a peer rank (a rank died or the evaluation counts diverged); "
+                     "weights and optimiser state were left untouched by that step");
+  return 0;
+}
 
 pinn::NetDesc net_desc(const pinn_t* h) {
   pinn::NetDesc nd{};
@@ -200,9 +206,12 @@ int ensure_points(pinn_t* h, long long need_d, long long need_c) {
       CUDA_TRY(cudaMemcpyAsync(nx + nd - h->n_aux, h->d_x + h->dcap - h->n_aux, h->n_aux * 8, cudaMemcpyDeviceToDevice, h->stream));
       CUDA_TRY(cudaMemcpyAsync(nt + nd - h->n_aux, h->d_t + h->dcap - h->n_aux, h->n_aux * 8, cudaMemcpyDeviceToDevice, h->stream));
     }
-    if (h->n_c) {
-      CUDA_TRY(cudaMemcpyAsync(nx + nd, h->d_x + h->dcap, h->n_c * 8, cudaMemcpyDeviceToDevice, h->stream));
-      CUDA_TRY(cudaMemcpyAsync(nt + nd, h->d_t + h->dcap, h->n_c * 8, cudaMemcpyDeviceToDevice, h->stream));
+    // the device-resident collocation block: nothing to preserve while the batch is a zero-copy mapping of pinned host
+    // memory (n_c then counts the HOST batch and ccap may be 0), and never more than the old region held
+    const long long keep_c = h->map_x ? 0 : (h->n_c < h->ccap ? h->n_c : h->ccap);
+    if (keep_c) {
+      CUDA_TRY(cudaMemcpyAsync(nx + nd, h->d_x + h->dcap, keep_c * 8, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(cudaMemcpyAsync(nt + nd, h->d_t + h->dcap, keep_c * 8, cudaMemcpyDeviceToDevice, h->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     cudaFree(h->d_x); cudaFree(h->d_t);
@@ -211,96 +220,104 @@ int ensure_points(pinn_t* h, long long need_d, long long need_c) {
   return 0;
 }
 
-int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false, bool defer_exchange = false) {
-  const bool skip_reduce = fused_only;
-  const bool p2p = h->world > 1 && h->p2p_ready && !fused_only;
-  h->pub = pinn::Publish{};
-  if (p2p) {
-    ++h->p2p_seq;                                               // this evaluation's sequence number / slot
-    const int slot = (int)(h->p2p_seq & 1);
-    h->reduce_dst = h->d_xchg + (size_t)slot * h->xchg_len;
-    h->pub.flag = reinterpret_cast<unsigned long long*>(h->d_xchg + 2 * (size_t)h->xchg_len) + slot;
-    h->pub.seq = h->p2p_seq;
-    h->pub.counter = h->d_pub_counter;
-  } else {
-    h->reduce_dst = h->d_R;
-  }
-  if (h->kernel_kind == 2) {
-    if (generic_launch_eval(h, run_flag, fused_only)) return -1;
-    if (fused_only) return 0;
-  } else if (h->pde == PINN_BURGERS_INF || h->pde == PINN_BURGERS_IDE) {
-    namespace B = pinn::burgers;
-    const bool ide = h->pde == PINN_BURGERS_IDE;
-    const long long n_total = ide ? h->n_d : h->n_d + h->n_c;
-    if (n_total <= 0) return fail("no points set (pinn_set_collocation / pinn_set_data)");
-    B::Args a{};
-    a.w = h->d_w;
-    a.x = h->d_x + (h->dcap - h->n_d); a.t = h->d_t + (h->dcap - h->n_d); a.utgt = h->d_u;
-    a.xc = h->map_x; a.tc = h->map_t;
-    if (h->map_x && h->burgers_kernel != 2) return fail("zero-copy collocation needs the v2 Burgers kernel");
-    a.n_total = n_total;
-    a.c0 = ide ? 0 : h->n_d;
-    a.n_c = ide ? h->n_d : h->n_c;
-    a.d0 = 0;
-    a.n_d = h->n_d;
-    const long long nfg = ide ? h->n_d : h->n_c_global;
-    a.wf = nfg > 0 ? 1.0 / (double)nfg : 0.0;
-    a.wd = h->n_d > 0 ? h->data_weight / (double)h->n_d : 0.0;
-    a.lb0 = h->lb[0]; a.lb1 = h->lb[1];
-    a.dx0 = h->ub[0] - h->lb[0]; a.dx1 = h->ub[1] - h->lb[1];
-    a.nu = h->nu; a.ide = ide ? 1 : 0;
-    a.partials = h->d_partials;
-    a.run_flag = run_flag;
-    const long long rounds = (n_total + B::ROUND - 1) / B::ROUND;
-    int grid = (int)(rounds < h->n_cta ? rounds : h->n_cta);
-    if (h->burgers_kernel == 2)
-      pinn::burgers2::fused_loss_grad<<<grid, pinn::burgers2::THREADS, pinn::burgers2::SMEM_BYTES, h->stream>>>(a);
+struct AdamArgs { double lr, b1, b2, eps; };
+
+// The tail of an evaluation: fixed-order reduction of the per-CTA partials into R = [grad | loss parts] on every rank,
+// optionally fused with the Adam update.
+//   world == 1      : reduce_partials, or reduce_adam (one kernel)
+//   world > 1, P2P  : reduce_exchange -- reduction + NVLink all-to-all push + rank-ordered sum (+ Adam) in ONE kernel
+//   world > 1, NCCL : reduce_partials + ncclAllReduce(P+3 doubles) (+ adam_update)
+int launch_tail(pinn_t* h, const int* run_flag, const AdamArgs* ad) {
+  const pinn::ReduceMap& map = h->last_map;
+  const int nb = (map.n_out + 31) / 32;
+  if (h->world == 1) {
+    if (ad)
+      pinn::reduce_adam<<<nb, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, h->d_R, map, h->d_w, h->d_m, h->d_v,
+                                                    h->P, h->d_step, ad->lr, ad->b1, ad->b2, ad->eps, h->d_loss_ring, LOSS_RING);
     else
-      B::fused_loss_grad<<<grid, B::THREADS, B::SMEM_BYTES, h->stream>>>(a);
+      pinn::reduce_partials<<<nb, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, h->d_R, map, run_flag);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
-    pinn::ReduceMap map{};
-    map.p_net = B::P_NET;
-    map.n_extra = 0;
-    if (ide) { map.extra_src[map.n_extra++] = B::IDX_DL1; map.extra_src[map.n_extra++] = B::IDX_DL2; }
-    map.extra_src[map.n_extra++] = B::IDX_LD;
-    map.extra_src[map.n_extra++] = 3023;        // (boundary part: always 0 for Burgers)
-    map.extra_src[map.n_extra++] = B::IDX_LF;
-    map.n_out = map.p_net + map.n_extra;
-    h->last_map = map; h->last_grid = grid; h->last_stride = B::PSTRIDE;
-    if (skip_reduce) return 0;
-    pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, B::PSTRIDE, h->reduce_dst, map, run_flag, h->pub);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-  } else {
-    if (nls_launch_eval(h, run_flag, fused_only)) return -1;
-    if (fused_only) return 0;
+    return 0;
   }
-  if (h->world > 1) {
-    // one exchange over [gradient | loss parts].  A skipped evaluation (L-BFGS stopped) still takes part
-    // with stale but rank-identical participation so that ranks never diverge.
-    if (h->p2p_ready) {
-      if (!defer_exchange && p2p_exchange(h, false, 0, 0, 0, 0)) return -1;
-    } else {
-      int rc = g_nccl.AllReduce(h->d_R, h->d_R, (size_t)h->P + 3, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
-      if (rc != 0) return fail(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
-    }
+  if (h->p2p_ready) {
+    if (nb != h->peers.n_blocks || map.n_out > h->peers.slot_len) return fail("internal: exchange buffer geometry mismatch");
+    pinn::reduce_exchange<<<nb, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, map, run_flag, h->peers, h->d_xseq,
+                                                      h->d_R, h->d_p2p_err, ad ? 1 : 0, h->d_w, h->d_m, h->d_v, h->P, h->d_step,
+                                                      ad ? ad->lr : 0.0, ad ? ad->b1 : 0.0, ad ? ad->b2 : 0.0, ad ? ad->eps : 0.0,
+                                                      h->d_loss_ring, LOSS_RING);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return 0;
+  }
+  pinn::reduce_partials<<<nb, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, h->d_R, map, run_flag);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  // one exchange over [gradient | loss parts].  A skipped evaluation (L-BFGS stopped) still takes part with
+  // stale but rank-identical participation so that ranks never diverge.
+  int rc = g_nccl.AllReduce(h->d_R, h->d_R, (size_t)h->P + 3, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+  if (rc != 0) return fail(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+  if (ad) {
+    pinn::adam_update<<<(h->P + 127) / 128, 128, 0, h->stream>>>(h->d_w, h->d_m, h->d_v, h->d_R, h->P, h->d_step, ad->lr, ad->b1,
+                                                                   ad->b2, ad->eps, h->d_loss_ring, LOSS_RING);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
   }
   return 0;
 }
 
-// The local reduction of this evaluation has been enqueued into the exchange slot: publish it and run the fused
-// gather-reduce(-Adam) kernel over peer memory.
-int p2p_exchange(pinn_t* h, bool adam, double lr, double b1, double b2, double eps) {
-  const int n = h->P + 3;
-  const unsigned long long seq = h->p2p_seq;
-  const int slot = (int)(seq & 1);
-  pinn::p2p_gather_reduce<<<(n + 255) / 256, 256, 0, h->stream>>>(h->peers, slot, h->xchg_len, seq, n, h->d_R, h->d_p2p_err,
-                                                                  adam ? 1 : 0, h->d_w, h->d_m, h->d_v, h->P, h->d_step, lr, b1,
-                                                                  b2, eps, h->d_loss_ring, LOSS_RING);
+int burgers_launch_eval(pinn_t* h, const int* run_flag) {
+  namespace B = pinn::burgers;
+  const bool ide = h->pde == PINN_BURGERS_IDE;
+  const long long n_total = ide ? h->n_d : h->n_d + h->n_c;
+  if (n_total <= 0) return fail("no points set (pinn_set_collocation / pinn_set_data)");
+  B::Args a{};
+  a.w = h->d_w;
+  a.x = h->d_x + (h->dcap - h->n_d); a.t = h->d_t + (h->dcap - h->n_d); a.utgt = h->d_u;
+  a.xc = h->map_x; a.tc = h->map_t;
+  if (h->map_x && h->burgers_kernel != 2) return fail("zero-copy collocation needs the v2 Burgers kernel");
+  a.n_total = n_total;
+  a.c0 = ide ? 0 : h->n_d;
+  a.n_c = ide ? h->n_d : h->n_c;
+  a.d0 = 0;
+  a.n_d = h->n_d;
+  const long long nfg = ide ? h->n_d : h->n_c_global;
+  a.wf = nfg > 0 ? 1.0 / (double)nfg : 0.0;
+  a.wd = h->n_d > 0 ? h->data_weight / (double)h->n_d : 0.0;
+  a.lb0 = h->lb[0]; a.lb1 = h->lb[1];
+  a.dx0 = h->ub[0] - h->lb[0]; a.dx1 = h->ub[1] - h->lb[1];
+  a.nu = h->nu; a.ide = ide ? 1 : 0;
+  a.partials = h->d_partials;
+  a.run_flag = run_flag;
+  const long long rounds = (n_total + B::ROUND - 1) / B::ROUND;
+  int grid = (int)(rounds < h->n_cta ? rounds : h->n_cta);
+  if (h->burgers_kernel == 2)
+    pinn::burgers2::fused_loss_grad<<<grid, pinn::burgers2::THREADS, pinn::burgers2::SMEM_BYTES, h->stream>>>(a);
+  else
+    B::fused_loss_grad<<<grid, B::THREADS, B::SMEM_BYTES, h->stream>>>(a);
   CUDA_TRY(cudaGetLastError());
-  h->launches += 1;
+  h->launches++;
+  pinn::ReduceMap map{};
+  map.p_net = B::P_NET;
+  map.n_extra = 0;
+  if (ide) { map.extra_src[map.n_extra++] = B::IDX_DL1; map.extra_src[map.n_extra++] = B::IDX_DL2; }
+  map.extra_src[map.n_extra++] = B::IDX_LD;
+  map.extra_src[map.n_extra++] = 3023;        // (boundary part: always 0 for Burgers)
+  map.extra_src[map.n_extra++] = B::IDX_LF;
+  map.n_out = map.p_net + map.n_extra;
+  h->last_map = map; h->last_grid = grid; h->last_stride = B::PSTRIDE;
   return 0;
+}
+
+// one evaluation: the fused loss/gradient kernel of the handle's PDE, then (unless fused_only) the tail
+int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false, const AdamArgs* ad = nullptr) {
+  int rc;
+  if (h->kernel_kind == 2) rc = generic_launch_eval(h, run_flag);
+  else if (h->pde == PINN_BURGERS_INF || h->pde == PINN_BURGERS_IDE) rc = burgers_launch_eval(h, run_flag);
+  else rc = nls_launch_eval(h, run_flag);
+  if (rc) return -1;
+  if (fused_only) return 0;
+  return launch_tail(h, run_flag, ad);
 }
 
 // DISC: data region = [x_0 data points | x_1 boundary points], right-aligned like every data block (t is unused)
@@ -319,7 +336,7 @@ int disc_upload_points(pinn_t* h) {
   return 0;
 }
 
-int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
+int generic_launch_eval(pinn_t* h, const int* run_flag) {
   namespace G = pinn::generic;
   const bool disc = h->pde == PINN_BURGERS_DISC;
   if (disc && (!h->d_irk || h->irk_q + 1 != h->layers.back())) return fail("discrete-time model: call pinn_set_irk first");
@@ -377,10 +394,6 @@ int generic_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
   map.extra_src[map.n_extra++] = h->P_net + 5;
   map.n_out = map.p_net + map.n_extra;
   h->last_map = map; h->last_grid = grid; h->last_stride = h->pstride;
-  if (fused_only) return 0;
-  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, h->pstride, h->reduce_dst, map, run_flag, h->pub);
-  CUDA_TRY(cudaGetLastError());
-  h->launches++;
   return 0;
 }
 
@@ -407,7 +420,7 @@ int nls_upload_points(pinn_t* h) {
   return 0;
 }
 
-int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
+int nls_launch_eval(pinn_t* h, const int* run_flag) {
   namespace N = pinn::nls;
   const long long n0 = h->n_d, n0p = (n0 + 1) & ~1LL, nb = h->n_b;
   const long long n_total = h->n_aux + h->n_c;
@@ -448,10 +461,6 @@ int nls_launch_eval(pinn_t* h, const int* run_flag, bool fused_only) {
   map.extra_src[0] = N::IDX_L0; map.extra_src[1] = N::IDX_LB; map.extra_src[2] = N::IDX_LF;
   map.n_out = map.p_net + map.n_extra;
   h->last_map = map; h->last_grid = grid; h->last_stride = N::PSTRIDE;
-  if (fused_only) return 0;
-  pinn::reduce_partials<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, grid, N::PSTRIDE, h->reduce_dst, map, run_flag, h->pub);
-  CUDA_TRY(cudaGetLastError());
-  h->launches++;
   return 0;
 }
 
@@ -464,16 +473,22 @@ const char* pinn_version(void) { return "pinn_b200 0.1 (sm_100a, fp64 DMMA)"; }
 
 int pinn_p2p_export(pinn_t* h, void* out64) {
   if (!h || !out64) return fail("pinn_p2p_export: null argument");
+  if (h->world < 2 || h->world > pinn::P2P_MAX) return fail("pinn_p2p_export: needs 2..8 ranks");
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->d_xchg) {
-    h->xchg_len = ((h->P + 3 + 15) / 16) * 16;
-    const size_t bytes = (size_t)2 * h->xchg_len * 8 + 64;
-    CUDA_TRY(cudaMalloc((void**)&h->d_xchg, bytes));
-    CUDA_TRY(cudaMemset(h->d_xchg, 0, bytes));
+    const int n = h->P + 3;
+    h->peers.world = h->world; h->peers.rank = h->rank;
+    h->peers.slot_len = ((n + 15) / 16) * 16;
+    h->peers.n_blocks = (n + 31) / 32;
+    const size_t data_bytes = (size_t)2 * h->world * h->peers.slot_len * 8;
+    const size_t flag_bytes = (size_t)2 * h->world * h->peers.n_blocks * 8;
+    CUDA_TRY(cudaMalloc((void**)&h->d_xchg, data_bytes + flag_bytes));
+    CUDA_TRY(cudaMemset(h->d_xchg, 0, data_bytes + flag_bytes));
     CUDA_TRY(cudaMalloc((void**)&h->d_p2p_err, 4));
     CUDA_TRY(cudaMemset(h->d_p2p_err, 0, 4));
-    CUDA_TRY(cudaMalloc((void**)&h->d_pub_counter, 4));
-    CUDA_TRY(cudaMemset(h->d_pub_counter, 0, 4));
+    CUDA_TRY(cudaMalloc((void**)&h->d_xseq, 8));
+    CUDA_TRY(cudaMemset(h->d_xseq, 0, 8));
+    CUDA_TRY(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t hd;
   CUDA_TRY(cudaIpcGetMemHandle(&hd, h->d_xchg));
@@ -487,7 +502,7 @@ int pinn_p2p_connect(pinn_t* h, const void* handles, int world) {
   if (world != h->world || world < 2 || world > pinn::P2P_MAX) return fail("pinn_p2p_connect: world must match pinn_create (2..8)");
   if (!h->d_xchg) return fail("pinn_p2p_connect: call pinn_p2p_export first");
   CUDA_TRY(cudaSetDevice(h->device));
-  h->peers.world = world; h->peers.rank = h->rank;
+  const size_t data_doubles = (size_t)2 * world * h->peers.slot_len;
   for (int r = 0; r < world; r++) {
     void* base = nullptr;
     if (r == h->rank) {
@@ -499,11 +514,18 @@ int pinn_p2p_connect(pinn_t* h, const void* handles, int world) {
       if (e != cudaSuccess) { cudaGetLastError(); return fail(std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e)); }
       h->peer_base[r] = base;
     }
-    h->peers.buf[r] = (const double*)base;
-    h->peers.flag[r] = reinterpret_cast<const unsigned long long*>((const double*)base + 2 * (size_t)h->xchg_len);
+    h->peers.data[r] = (double*)base;
+    h->peers.flag[r] = reinterpret_cast<unsigned long long*>((double*)base + data_doubles);
   }
+  h->p2p_mapped = true;
   h->p2p_ready = true;
-  h->p2p_seq = 0;
+  return 0;
+}
+
+int pinn_p2p_enable(pinn_t* h, int on) {
+  if (!h) return fail("null handle");
+  if (on && !h->p2p_mapped) return fail("pinn_p2p_enable: call pinn_p2p_connect first");
+  h->p2p_ready = on != 0;
   return 0;
 }
 
@@ -636,7 +658,7 @@ int pinn_destroy(pinn_t* h) {
   for (int r = 0; r < pinn::P2P_MAX; r++) if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
   if (h->d_xchg) cudaFree(h->d_xchg);
   if (h->d_p2p_err) cudaFree(h->d_p2p_err);
-  if (h->d_pub_counter) cudaFree(h->d_pub_counter);
+  if (h->d_xseq) cudaFree(h->d_xseq);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   double* bufs[] = {h->d_w, h->d_R, h->d_partials, h->d_m, h->d_v, h->d_loss_ring, h->d_x, h->d_t, h->d_u, h->d_scrH, h->d_scrA, h->d_scrS, h->d_gH, h->d_gA, h->d_gS, h->d_irk, h->d_gold,
                     h->d_d, h->d_S, h->d_Y, h->d_xfinal, h->d_fhist, h->d_px, h->d_pout};
@@ -843,6 +865,7 @@ int pinn_loss_grad(pinn_t* h, const double* w_or_null, double* loss_out, double*
   CUDA_TRY(cudaMemcpyAsync(parts, h->d_R + h->P, 24, cudaMemcpyDeviceToHost, h->stream));
   if (grad_out_or_null) CUDA_TRY(cudaMemcpyAsync(grad_out_or_null, h->d_R, h->P * 8, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (check_p2p(h)) return -1;
   if (loss_out) *loss_out = parts[0] + parts[1] + parts[2];
   if (parts_out_or_null) { parts_out_or_null[0] = parts[0]; parts_out_or_null[1] = parts[1]; parts_out_or_null[2] = parts[2]; }
   return 0;
@@ -851,30 +874,15 @@ int pinn_loss_grad(pinn_t* h, const double* w_or_null, double* loss_out, double*
 int pinn_adam_step(pinn_t* h, double lr, double b1, double b2, double eps, double* loss_out_or_null) {
   if (!h) return fail("null handle");
   CUDA_TRY(cudaSetDevice(h->device));
-  if (h->world == 1) {
-    // fused kernel, then ONE kernel that reduces the per-CTA partials and applies Adam
-    if (launch_eval(h, nullptr, true)) return -1;
-    const pinn::ReduceMap& map = h->last_map;
-    pinn::reduce_adam<<<(map.n_out + 31) / 32, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, h->d_R, map,
-                                                                    h->d_w, h->d_m, h->d_v, h->P, h->d_step, lr, b1, b2, eps,
-                                                                    h->d_loss_ring, LOSS_RING);
-    CUDA_TRY(cudaGetLastError());
-    h->launches += 1;
-  } else if (h->p2p_ready) {
-    // fused kernel + local reduction, then ONE kernel: wait for the peers, P2P gather-reduce over NVLink, Adam
-    if (launch_eval(h, nullptr, false, true)) return -1;
-    if (p2p_exchange(h, true, lr, b1, b2, eps)) return -1;
-  } else {
-    if (launch_eval(h, nullptr)) return -1;      // fused + reduce + allreduce
-    pinn::adam_update<<<(h->P + 127) / 128, 128, 0, h->stream>>>(h->d_w, h->d_m, h->d_v, h->d_R, h->P, h->d_step, lr, b1, b2,
-                                                                   eps, h->d_loss_ring, LOSS_RING);
-    CUDA_TRY(cudaGetLastError());
-    h->launches += 1;
-  }
+  // fused kernel, then the tail: ONE more kernel on a single GPU (reduce + Adam) and with the NVLink push exchange
+  // (reduce + exchange + Adam); reduce + ncclAllReduce + Adam on the NCCL path
+  const AdamArgs ad{lr, b1, b2, eps};
+  if (launch_eval(h, nullptr, false, &ad)) return -1;
   h->adam_steps++;
   if (loss_out_or_null) {
     CUDA_TRY(cudaMemcpyAsync(loss_out_or_null, h->d_loss_ring + ((h->adam_steps - 1) % LOSS_RING), 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (check_p2p(h)) return -1;
   }
   return 0;
 }
@@ -895,6 +903,7 @@ int pinn_last_loss(pinn_t* h, double* loss_out) {
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemcpyAsync(loss_out, h->d_loss_ring + ((h->adam_steps - 1) % LOSS_RING), 8, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (check_p2p(h)) return -1;
   return 0;
 }
 
@@ -974,6 +983,7 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
     CUDA_TRY(cudaMemcpyAsync(fh.data(), h->d_fhist, (size_t)(max_iter + 2) * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(lg.data(), h->d_logged, (size_t)(max_iter + 2) * 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (check_p2p(h)) return -1;
     // iterations whose stop tests have run: all < n_iter, plus n_iter itself unless its evaluation is pending
     const int upto = st.pending ? st.n_iter - 1 : st.n_iter;
     for (int it = reported + 1; it <= upto; it++)
@@ -981,6 +991,7 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
     if (upto > reported) reported = upto;
     if (st.status != 0) break;
   }
+  h->lb_fhist.assign(fh.begin(), fh.begin() + (st.n_eval < (int)fh.size() ? st.n_eval : (int)fh.size()));
   if (n_iter_out) *n_iter_out = st.n_iter;
   if (n_eval_out) *n_eval_out = st.n_eval;
   if (reason_out) *reason_out = st.status;
@@ -990,6 +1001,17 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
     const double* src = (st.status == PINN_LBFGS_MAX_ITER) ? h->d_xfinal : h->d_w;
     CUDA_TRY(cudaMemcpyAsync(x_final_or_null, src, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+int pinn_lbfgs_history(pinn_t* h, double* f_hist_out, int capacity, int* n_out) {
+  if (!h || !n_out) return fail("pinn_lbfgs_history: null argument");
+  const int n = (int)h->lb_fhist.size();
+  *n_out = n;
+  if (f_hist_out) {
+    if (capacity < n) return fail("pinn_lbfgs_history: buffer too small");
+    for (int i = 0; i < n; i++) f_hist_out[i] = h->lb_fhist[i];
   }
   return 0;
 }
@@ -1028,11 +1050,20 @@ int pinn_derivatives(pinn_t* h, const double* X, int64_t n, double* out) {
   return forward_generic(h, X, nullptr, nullptr, n, h ? h->layers[0] : 2, out, 4);
 }
 
-int pinn_residual(pinn_t* h, double* f_out) {
+int64_t pinn_num_residual_points(const pinn_t* h) {
+  if (!h) return -1;
+  if (h->pde == PINN_BURGERS_DISC) return 0;
+  return h->pde == PINN_BURGERS_IDE ? h->n_d : h->n_c;
+}
+
+int pinn_residual(pinn_t* h, double* f_out, int64_t n_rows) {
   if (!h || !f_out) return fail("null argument");
   if (h->pde == PINN_BURGERS_DISC) return fail("pinn_residual: not defined for the discrete-time model");
   const bool ide = h->pde == PINN_BURGERS_IDE;
   const int64_t n = ide ? h->n_d : h->n_c;
+  if (n_rows != n)
+    return fail("pinn_residual: the output buffer holds " + std::to_string(n_rows) + " rows but " + std::to_string(n) +
+                " residual points are stored (pinn_num_residual_points)");
   if (n == 0) return 0;
   const long long off = ide ? h->dcap - h->n_d : h->dcap;
   std::vector<double> D(n * 4 * h->layers.back());
@@ -1066,12 +1097,7 @@ int pinn_sync(pinn_t* h) {
   if (!h) return fail("null handle");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (h->p2p_ready) {
-    int e = 0;
-    CUDA_TRY(cudaMemcpy(&e, h->d_p2p_err, 4, cudaMemcpyDeviceToHost));
-    if (e) return fail("P2P exchange timed out waiting for a peer rank (a rank died or the evaluation counts diverged)");
-  }
-  return 0;
+  return check_p2p(h);
 }
 
 int pinn_host_alloc(void** out, int64_t bytes) {

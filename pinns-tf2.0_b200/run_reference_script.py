@@ -109,8 +109,11 @@ def main(argv):
         sys.path.insert(0, pth)
     # result artefacts (hp.json, fields.npz, figure) land under <launch directory>/<eqn>/results/, not in the scratch directory
     os.environ.setdefault("PINN_RESULTS_ROOT", os.getcwd())
+    # optional script arguments that name files (the hp.json of `script.py hp.json`) were given relative to the caller's
+    # directory, not to the scratch directory the script runs in
+    rest = [os.path.abspath(a) if os.path.exists(a) else a for a in argv[2:]]
     os.chdir(wd)
-    sys.argv = [script] + argv[2:]
+    sys.argv = [script] + rest
     src = open(script, encoding="utf-8").read()
     try:
         compile(src, script, "exec")

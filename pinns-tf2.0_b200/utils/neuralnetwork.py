@@ -130,6 +130,7 @@ class NeuralNetwork(object):
         self._h = None
         self._w0 = _glorot_normal(self.layers, np.random.default_rng(self.weight_seed))
         self._bound = None
+        self._bound_refs = None
 
     # ------------------------------------------------------------------ native handle
     def _n_net_params(self):
@@ -295,8 +296,10 @@ def _native_f_model(self, *args):
             U, Ux, Ut, Uxx = n.derivatives(np.asarray(args[0], dtype=np.float64))
             w = n.get_weights()
             return _t(Ut + w[-2] * U * Ux - np.exp(w[-1]) * Uxx)
-        return _t(n.residual(np.asarray(self._bound_refs[0]).shape[0]))
-    f = n.residual(np.asarray(self.x_f).shape[0])
+        if self._bound is None:
+            raise pinn_cabi.PinnError("f_model(): no data points are bound yet -- call fit()/grad() first, or pass the points")
+        return _t(n.residual())
+    f = n.residual()
     if f.shape[1] == 2:
         return _t(f[:, 0:1]), _t(f[:, 1:2])
     return _t(f)

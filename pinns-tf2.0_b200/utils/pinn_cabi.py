@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.realpath(__file__))
-LIB_PATH = os.path.join(_HERE, "..", "lib", "libpinn_b200.so")
+# PINN_LIB: load another build of the same library (kernel experiments: profiles/kernel_variants.py)
+LIB_PATH = os.environ.get("PINN_LIB") or os.path.join(_HERE, "..", "lib", "libpinn_b200.so")
 
 BURGERS_INF, BURGERS_IDE, NLS_INF, BURGERS_DISC = 0, 1, 2, 3
 LBFGS_REASONS = {0: "running", 1: "max iterations", 2: "max evaluations", 3: "optimality", 4: "step below tolX",
@@ -29,6 +30,7 @@ SIGNATURES = {
     "pinn_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "pinn_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pinn_p2p_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "pinn_p2p_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pinn_num_params": (C.c_int64, [C.c_void_p]),
     "pinn_set_pde_params": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "pinn_get_params": (C.c_int, [C.c_void_p, _dp, C.c_int]),
@@ -45,8 +47,10 @@ SIGNATURES = {
     "pinn_last_loss": (C.c_int, [C.c_void_p, _dp]),
     "pinn_lbfgs": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, LOG_CB, C.c_void_p,
                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _dp]),
+    "pinn_lbfgs_history": (C.c_int, [C.c_void_p, _dp, C.c_int, C.POINTER(C.c_int)]),
     "pinn_predict": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int, _dp]),
-    "pinn_residual": (C.c_int, [C.c_void_p, _dp]),
+    "pinn_num_residual_points": (C.c_int64, [C.c_void_p]),
+    "pinn_residual": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "pinn_derivatives": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp]),
     "pinn_sync": (C.c_int, [C.c_void_p]),
     "pinn_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
@@ -141,6 +145,9 @@ class Pinn(object):
         buf = C.create_string_buffer(blob, len(blob))
         self._ck(self.lib.pinn_p2p_connect(self.h, C.cast(buf, C.c_void_p), len(handles)))
 
+    def p2p_enable(self, on):
+        self._ck(self.lib.pinn_p2p_enable(self.h, 1 if on else 0))
+
     # ---- problem definition
     def set_pde_params(self, params):
         a = _arr(params).reshape(-1)
@@ -228,8 +235,12 @@ class Pinn(object):
         self._ck(self.lib.pinn_lbfgs(self.h, int(max_iter), float(learning_rate), int(n_correction), float(tol_fun),
                                      float(tol_x), int(sync_every), cb, None, C.byref(n_it), C.byref(n_ev), C.byref(reason),
                                      _p(xf) if xf is not None else None))
+        nh = C.c_int()
+        self._ck(self.lib.pinn_lbfgs_history(self.h, None, 0, C.byref(nh)))
+        fh = np.empty(max(nh.value, 1))
+        self._ck(self.lib.pinn_lbfgs_history(self.h, _p(fh), fh.size, C.byref(nh)))
         return {"n_iter": n_it.value, "n_eval": n_ev.value, "reason": reason.value,
-                "reason_str": LBFGS_REASONS.get(reason.value, "?"), "x_final": xf}
+                "reason_str": LBFGS_REASONS.get(reason.value, "?"), "x_final": xf, "f_hist": [float(v) for v in fh[:nh.value]]}
 
     # ---- off-path
     def predict(self, X):
@@ -247,10 +258,15 @@ class Pinn(object):
         self._ck(self.lib.pinn_derivatives(self.h, _p(X), X.shape[0], _p(out)))
         return out[:, 0], out[:, 1], out[:, 2], out[:, 3]
 
-    def residual(self, n):
+    def residual(self, n=None):
+        """f_model on the stored residual points.  The buffer is sized from the count the handle holds; a caller-supplied
+        `n` is only checked against it."""
         nres = 2 if self.pde == NLS_INF else 1
-        out = np.empty((int(n), nres))
-        self._ck(self.lib.pinn_residual(self.h, _p(out)))
+        stored = int(self.lib.pinn_num_residual_points(self.h))
+        if n is not None and int(n) != stored:
+            raise PinnError(f"residual: {stored} residual points are stored, caller expected {int(n)}")
+        out = np.empty((stored, nres))
+        self._ck(self.lib.pinn_residual(self.h, _p(out), stored))
         return out
 
     def sync(self):

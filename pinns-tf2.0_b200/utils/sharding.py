@@ -31,14 +31,31 @@ def exchange_nccl_uid(dist, rank, make_uid):
 
 
 def connect_p2p(dist, pinn, world):
-    """All-gather the ranks' IPC handles through the control plane and map the peers' exchange buffers (fused NVLink P2P
-    gather-reduce-Adam instead of ncclAllReduce).  Opt-in with PINN_COLLECTIVE=p2p: measured on 2xB200 it is correct
-    (tests/mgpu_check.py) but not faster than NCCL's low-latency allreduce for this 24 KB message (0.488-0.536 ms vs
-    0.484-0.486 ms per step), so NCCL is the default."""
-    if world < 2 or os.environ.get("PINN_COLLECTIVE", "nccl") != "p2p":
+    """All-gather the ranks' IPC handles through the control plane and map the peers' exchange buffers: the evaluation's
+    tail then runs as ONE kernel (reduction + NVLink all-to-all push + rank-ordered sum + Adam) instead of
+    reduce -> ncclAllReduce -> Adam.  Default; PINN_COLLECTIVE=nccl keeps the NCCL path.  The decision is collective: if
+    the export or the mapping fails on ANY rank, every rank falls back to NCCL."""
+    if world < 2 or os.environ.get("PINN_COLLECTIVE", "p2p") == "nccl":
         return False
+    try:
+        mine = pinn.p2p_export()
+    except Exception:
+        mine = None
     handles = [None] * world
-    dist.all_gather_object(handles, pinn.p2p_export())
-    pinn.p2p_connect(handles)
+    dist.all_gather_object(handles, mine)
+    ok = all(h is not None for h in handles)
+    if ok:
+        try:
+            pinn.p2p_connect(handles)
+        except Exception:
+            ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok))
+    ok = all(flags)
+    if not ok:
+        try:
+            pinn.p2p_enable(False)
+        except Exception:
+            pass
     dist.barrier()
-    return True
+    return ok

@@ -16,6 +16,33 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def _cuda_device_present():
+    try:
+        import ctypes
+        n = ctypes.c_int(0)
+        rt = ctypes.CDLL("libcudart.so")
+        return rt.cudaGetDeviceCount(ctypes.byref(n)) == 0 and n.value > 0
+    except Exception:
+        try:
+            import torch
+            return torch.cuda.is_available()
+        except Exception:
+            return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a box without a GPU skips the gpu-marked tests instead of failing in pinn_create (the oracle
+    stand-in plugin of tests/test_gpu_testcode_dryrun.py runs them on the CPU on purpose and opts out)."""
+    if os.environ.get("PINN_GPU_TESTS_ON_ORACLE") == "1" or config.pluginmanager.hasplugin("oracle_backend_plugin"):
+        return
+    if _cuda_device_present():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200); there is no CPU fallback")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 

@@ -132,7 +132,7 @@ class OraclePinn(object):
         (U, Ux, Ut, Uxx), _ = ty.forward(self._net_w(), self.layers, self.lb, self.ub, np.asarray(X, float))
         return U, Ux, Ut, Uxx
 
-    def residual(self, n):
+    def residual(self, n=None):
         if self.pde == NLS_INF:
             (H, _, Ht, Hxx), _ = ty.forward(self.w, self.layers, self.lb, self.ub, self.X_f)
             h2 = H[:, 0] ** 2 + H[:, 1] ** 2

@@ -48,7 +48,16 @@ class FakePinn(object):
         return {"grid": 148, "block": 256, "dyn_smem": 196376, "regs": 252, "local_bytes": 0, "sms": 148}
 
     def lbfgs(self, max_iter, **k):
-        return {"n_iter": max_iter, "n_eval": max_iter, "reason": 1, "reason_str": "max iterations", "x_final": None}
+        return {"n_iter": max_iter, "n_eval": max_iter, "reason": 1, "reason_str": "max iterations", "x_final": np.ones(self.P),
+                "f_hist": [0.5] * max_iter}
+
+    def loss_grad(self, w=None, want_grad=True):
+        return 0.25, np.ones(self.P), np.zeros(3)
+
+    def get_weights(self):
+        return np.ones(self.P)
+
+    adam_reset = _noop
 
 
 def test_bench_gpu_arm_control_flow_with_fake_backend(monkeypatch):
@@ -59,7 +68,9 @@ def test_bench_gpu_arm_control_flow_with_fake_backend(monkeypatch):
     monkeypatch.setattr(pinn_cabi, "Pinn", FakePinn)
     monkeypatch.setattr(pinn_cabi, "host_alloc", lambda n: (np.zeros(n), C.c_void_p(0)))
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setattr(bench, "time_reference_port", lambda n_f, steps, warmup, seed=1234: (0.4, 8, 0.1, n_f))
+    monkeypatch.setattr(bench, "time_reference_port", lambda n_f, steps, warmup, seed=1234, budget_s=0: (0.4, 8, 0.1, n_f))
+    monkeypatch.setattr(bench, "_port_baseline", lambda make, w, steps, warmup, n, what, **kw: {"value": 1e5, "unit": "points/s", "cores": 8,
+                                                                                                  "kind": "port", "sample": what})
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "4", "--warmup", "1"])
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         monkeypatch.delenv(k, raising=False)
@@ -75,13 +86,19 @@ def test_bench_gpu_arm_control_flow_with_fake_backend(monkeypatch):
     assert d["warmup"] == 3 and d["steps"] == 4              # warm-up is raised to the minimum of 3
     assert d["dtype"] == "f64" and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["vs_baseline"] is None
     assert d["gpu_launches"] == 2 * 4 and abs(d["ms_per_step"] - 0.46) < 1e-9
+    assert d["config"]["workload"] == bench.workload_string(100000)        # the string both arms print
+    c5 = d["cfg5"]
+    assert c5["n_f_global"] == 2000000 and c5["n_gpus"] == 1 and c5["adam_ms_per_step"] > 0 and c5["lbfgs_ms_per_iteration"] > 0
     assert abs(d["value"] - 100000 / 0.46e-3) / d["value"] < 1e-9
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "copy_mode", "mapped_mode"}
     assert d["e2e"]["h2d_bytes_per_step"] == 1600000 and d["e2e"]["d2h_bytes_per_step"] == 8
     r = d["roofline"]
     assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"] > 1e6
-    assert set(d["extras"]) == {"burgers_lbfgs", "burgers_identification", "schrodinger", "burgers_discrete_time"}
-    assert all("error" not in v for v in d["extras"].values())
+    assert set(d["extras"]) == {"burgers_lbfgs", "burgers_cfg1_10k", "burgers_identification", "schrodinger", "burgers_discrete_time"}
+    assert all("error" not in v for v in d["extras"].values()), d["extras"]
+    for k in ("burgers_cfg1_10k", "burgers_identification", "schrodinger"):
+        assert d["extras"][k]["cpu_baseline"]["kind"] == "port"
+    assert d["extras"]["schrodinger"]["roofline"]["bound"] == "tensor"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 8
 
 
@@ -116,6 +133,9 @@ def test_bench_two_ranks_gloo(tmp_path):
     assert d["n_gpus"] == 2 and "cpu_baseline" not in d and "extras" not in d
     assert abs(d["value"] - 200000 / 0.46e-3) / d["value"] < 1e-9          # whole-job aggregate over both shards
     assert "ncclAllReduce" in d["config"]["parallelism"]
+    pc = d["parity_check"]                                                  # sharded vs whole-set evaluation ran before the timing
+    assert pc["ok"] and pc["world"] == 2 and pc["points"] == 200000 and pc["lbfgs_iters_equal"] and pc["weights_bitwise_identical_across_ranks"]
+    assert d["cfg5"]["n_gpus"] == 2 and d["cfg5"]["n_f_global"] == 2000000
 
 
 def test_reference_arm_under_two_ranks_only_rank0_works(tmp_path, monkeypatch):
@@ -124,3 +144,6 @@ def test_reference_arm_under_two_ranks_only_rank0_works(tmp_path, monkeypatch):
     assert outs[1].strip() == ""
     d = json.loads(outs[0].strip().split("\n")[-1])
     assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"]["workload"] == bench.workload_string(2000)           # same string as the GPU arm prints for this --n-f

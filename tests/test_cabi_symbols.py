@@ -89,7 +89,7 @@ def test_hot_kernels_fit_their_resource_budget(lib_built):
     assert regs <= 252 and stack == 0
     regs, stack, _ = find("3nls", "fused_loss_grad")
     assert regs <= 255 and stack == 0
-    for name in ("reduce_adam", "adam_update", "reduce_partials", "p2p_gather_reduce"):
+    for name in ("reduce_adam", "adam_update", "reduce_partials", "reduce_exchange"):
         regs, stack, _ = find(name)
         assert regs <= 64 and stack == 0
     regs, stack, _ = find("lbfgs_iterate", "ILi12ELi256E")        # the Burgers-size L-BFGS keeps its P-vector slice in registers
