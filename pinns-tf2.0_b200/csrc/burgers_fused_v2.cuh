@@ -1,6 +1,6 @@
 // Fused Burgers PINN loss + gradient kernel, v2: warp-specialised (sm_100a, fp64 DMMA).
 //
-// Same mathematics and fragment scheme as burgers_fused.cuh (v1, kept as a cross-check), re-organised so that
+// Same mathematics and DMMA fragment scheme as burgers_fused.cuh (v1, kept as a cross-check), re-organised so that
 // the FP64 pipe of every SM sub-partition always has two warps to draw from and nobody waits at a block barrier:
 //
 //   warps 0-3  "chain" warps  : own an 8-point tile each; forward DMMA chain through the 8 tanh layers, residual,
@@ -12,15 +12,33 @@
 //                               backward formula needs and the A operand of the weight-gradient GEMM.
 //   warps 4-7  "wgrad" warps  : consume (stash[l-1], Z-bar_l) pairs of all four chain warps and run the
 //                               weight-gradient GEMM  G_l[i][j] += sum_rows H_{l-1}[row][i] Zbar_l[row][j]  with DMMA.
-//                               The 3x3 output tiles of a layer are OWNED by warps (3/2/2/2, the heavy role rotates
-//                               with the layer so the four sub-partitions stay balanced), so accumulators live in
-//                               registers for the whole kernel: no shared-memory accumulator, no atomics, no
-//                               cross-warp reduction, and a fixed summation order (deterministic results).
+//                               The 3x3 output tiles of a layer are OWNED by warps, a ROW of tiles each: position
+//                               k = (warp - layer) & 3 < 3 owns tiles (mt = k; nt = 0,1,2), position 3 rests (the resting
+//                               role rotates with the layer so the four sub-partitions stay balanced).  One A fragment
+//                               feeds three DMMAs, operand column pointers are chosen once per task (padded lanes point
+//                               into a ones/zeros page), so the unrolled k loop is 4 LDS + 3 DMMA without predicates.
+//                               Accumulators live in registers for the whole kernel: no shared-memory accumulator, no
+//                               atomics, no cross-warp reduction, and a fixed summation order (deterministic results).
+//
+// Register layout of a chain warp ("V5").  A DMMA accumulator fragment (lane = 4g+q) holds point g, units 8nt+2q+e; hidden
+// width 20 makes the third N tile half padding (units 20..23 in lanes q >= 2).  Between the GEMMs the 20 units of a point
+// are therefore kept as FIVE values per lane and stream: j = 2nt+e for the first two tiles and, for j = 4, unit
+// {16,18,17,19}[q] -- one quad shuffle moves the odd units of tile 2 from lanes q < 2 to lanes q >= 2.  This is exactly
+// the A-operand layout of k-step j of the next GEMM (the contraction index is permuted: k-step j contracts the units the
+// four lanes of a quad hold in slot j), so accumulators chain from layer to layer in registers, and the activation
+// arithmetic (tanh and the Taylor/adjoint formulas) runs on 5 instead of 6 values per lane -- no lane computes padding.
 //
 // Backward through a tanh layer in terms of its outputs (s = 1 - a^2; A* = adjoints of the outputs):
 //   Z_xx = s A_xx;  Z_t = s A_t;  Z_x = s A_x - 4 a a_x A_xx;
 //   Z    = s A - 2 a (a_x A_x + a_t A_t) - 2 A_xx (a a_xx + a_x^2)
 // (algebraically identical to SURVEY Appendix A; no division by s, so saturated units are safe).
+//
+// Small point sets: `chains` (1..4) chain warps per CTA are used, so that e.g. 2000 points (250 tiles) run as 125 CTAs x 2
+// tiles instead of 63 CTAs x 4 -- the latency of a launch is one tile either way, but the sub-partitions are less loaded.
+//
+// Measured and dropped (profiles/kernel_variants_r02.md): 3-slot ring, per-tile-pair ownership 3/2/2/2 (0.451 -> 0.416 ms
+// with row ownership), holding the weight-gradient DMMAs back while the co-resident chain warp is in a DMMA phase
+// (slower: the weight-gradient warps starve), publishing Z-bar after the chain warp's own input-adjoint GEMM (no change).
 #pragma once
 #include "burgers_fused.cuh"
 
@@ -44,36 +62,19 @@ using burgers::Args;
 
 constexpr int CHAINS = 4;
 constexpr int THREADS = 256;              // 4 chain warps + 4 wgrad warps
-constexpr int ROUND = CHAINS * TILE;      // 32 points per CTA round
+constexpr int ROUND = CHAINS * TILE;      // 32 points per full CTA round
 #ifndef PINN_RING
 #define PINN_RING 2
 #endif
-#ifndef PINN_PHASE_OFFSET
-#define PINN_PHASE_OFFSET 0
+// timing ablations (they compute WRONG gradients on purpose; profiles/kernel_variants.py)
+#ifndef PINN_ABL_NOWG
+#define PINN_ABL_NOWG 0                   // weight-gradient warps only do the ring handshake
 #endif
-#ifndef PINN_XT_PREFETCH
-#define PINN_XT_PREFETCH 1
-#endif
-#ifndef PINN_WG_ROLLED
-#define PINN_WG_ROLLED 0
-#endif
-#ifndef PINN_WG_FAST
-#define PINN_WG_FAST 0                    // experiment (unmeasured): unconditional weight-gradient operand loads, see wgrad_task
-#endif
-#ifndef PINN_WG_ROWS
-#define PINN_WG_ROWS 1                    // weight-gradient tiles owned by ROWS: warp position k < 3 owns (mt = k; nt = 0,1,2), k == 3 rests;
-#endif                                    // one A fragment feeds three DMMAs, operand pointers chosen once (no predicates in the k loop)
 #ifndef PINN_ABL_NOACT
-#define PINN_ABL_NOACT 0                  // timing ablation: no activation arithmetic in the chain warps
+#define PINN_ABL_NOACT 0                  // no activation arithmetic in the chain warps
 #endif
 #ifndef PINN_ABL_NODMMA
-#define PINN_ABL_NODMMA 0                 // timing ablation: no chain DMMAs
-#endif
-#ifndef PINN_ABL_NOSTAGE
-#define PINN_ABL_NOSTAGE 0                // timing ablation: chain warps neither stage nor synchronise (use with PINN_ABL_NOWG)
-#endif
-#ifndef PINN_ABL_NOWG
-#define PINN_ABL_NOWG 0                   // timing ablation (wrong gradients): weight-gradient warps only do the ring handshake
+#define PINN_ABL_NODMMA 0                 // no chain DMMAs
 #endif
 constexpr int RING = PINN_RING;           // Z-bar ring slots per chain warp
 
@@ -87,10 +88,10 @@ constexpr int SM_RING = SM_STASH + CHAINS * STASH_PER_WARP;
 constexpr int SM_XT = SM_RING + CHAINS * RING * 640;
 constexpr int SM_RED = SM_XT + CHAINS * 2 * 16;
 constexpr int SM_BAR = SM_RED + 256;      // 1 + 2*CHAINS*RING mbarriers
-constexpr int SM_SPECIAL = SM_BAR + 1 + 2 * CHAINS * RING + 2;   // + phase-offset barrier; then (PINN_WG_FAST) a [32 rows][W] page:
-                                                                 // column 0 = the bias ones-row (1 on the value stream's rows 0..7), column 1 = 0
-constexpr int SM_DOUBLES = SM_SPECIAL + ((PINN_WG_FAST || PINN_WG_ROWS) ? 32 * W : 0);
-constexpr int SMEM_BYTES = SM_DOUBLES * 8;   // ~195 KB
+constexpr int SM_SPECIAL = SM_BAR + 1 + 2 * CHAINS * RING + 1;   // [32 rows][W] page: column 0 = the bias ones-row (1 on the value
+                                                                 // stream's rows 0..7), column 1 = 0
+constexpr int SM_DOUBLES = SM_SPECIAL + 32 * W;
+constexpr int SMEM_BYTES = SM_DOUBLES * 8;   // ~201 KB
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -102,232 +103,173 @@ __device__ __forceinline__ uint64_t* bar_empty(uint64_t* bars, int c, int slot) 
 __device__ __forceinline__ void wait_produced(uint64_t* bars, int c, int T) { mbar_wait(bar_full(bars, c, T % RING), (T / RING) & 1); }
 __device__ __forceinline__ void wait_consumed(uint64_t* bars, int c, int T) { mbar_wait(bar_empty(bars, c, T % RING), (T / RING) & 1); }
 
-// C-layout read of a [rows][20] staged tile: stream block s, this lane's point row and columns
-__device__ __forceinline__ void load_rows(double (&V)[4][3][2], const double* T, int lane) {
+// ---------------------------------------------------------------------------------------------------
+// chain warps: the V5 register layout
+// ---------------------------------------------------------------------------------------------------
+// hidden unit held in slot j of lane-quad position q (== the unit k-step j contracts for this lane)
+__device__ __forceinline__ int unit5(int j, int q) { return j < 4 ? 8 * (j >> 1) + 2 * q + (j & 1) : (q < 2 ? 16 + 2 * q : 13 + 2 * q); }
+
+// accumulator fragments (C layout) -> V5: slots 0..3 are the first two tiles, slot 4 gathers units 16..19 across the quad
+__device__ __forceinline__ void c_to_v5(double (&V)[4][5], const double (&Z)[4][3][2], int lane) {
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    V[s][0] = Z[s][0][0]; V[s][1] = Z[s][0][1]; V[s][2] = Z[s][1][0]; V[s][3] = Z[s][1][1];
+    const double odd = __shfl_sync(0xffffffffu, Z[s][2][1], (lane & ~3) | (lane & 1));   // units 17, 19 live in lanes q = 0, 1
+    V[s][4] = (lane & 2) ? odd : Z[s][2][0];
+  }
+}
+
+// Z[s][nt][:] += V_s * Bmat, Bmat[k][n] = Wl[k*ldk + n*ldn]  (forward: ldk = 20, ldn = 1; input adjoint: ldk = 1, ldn = 20,
+// i.e. the transposed weight).  N columns >= 20 read as zero.  5 k-steps x 4 streams x 3 N tiles = 60 DMMA.
+__device__ __forceinline__ void mma_layer5(double (&Z)[4][3][2], const double (&V)[4][5], const double* Wl, int ldk, int ldn,
+                                           int lane) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < 5; ks++) {
+    const int k = unit5(ks, q);
+    double b[3];
+#pragma unroll
+    for (int nt = 0; nt < 3; nt++) {
+      const int n = 8 * nt + g;
+      b[nt] = (n < W) ? Wl[k * ldk + n * ldn] : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+#pragma unroll
+      for (int nt = 0; nt < 3; nt++) dmma(Z[s][nt], V[s][ks], b[nt]);
+  }
+}
+
+// outputs of a tanh layer from its pre-activation streams (in place): (z, z_x, z_t, z_xx) -> (a, s z_x, s z_t, s (z_xx - 2 a z_x^2))
+__device__ __forceinline__ void act_forward5(double (&V)[4][5]) {
+  if (PINN_ABL_NOACT) return;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const double a = tanh_fast(V[0][j]);
+    const double zx = V[1][j];
+    const double s = fma(-a, a, 1.0);
+    V[0][j] = a;
+    V[1][j] = s * zx;
+    V[2][j] = s * V[2][j];
+    V[3][j] = s * fma(-2.0 * a * zx, zx, V[3][j]);
+  }
+}
+
+// adjoints of the outputs (A, overwritten with the adjoints of the pre-activations) given the outputs H
+__device__ __forceinline__ void act_backward5(double (&A)[4][5], const double (&H)[4][5]) {
+  if (PINN_ABL_NOACT) return;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const double a = H[0][j], ax = H[1][j], at = H[2][j], axx = H[3][j];
+    const double A0 = A[0][j], Ax = A[1][j], At = A[2][j], Axx = A[3][j];
+    const double s = fma(-a, a, 1.0);
+    const double u1 = fma(ax, Ax, at * At);
+    const double u2 = fma(a, axx, ax * ax);
+    double z = fma(-2.0 * a, u1, s * A0);
+    z = fma(-2.0 * Axx, u2, z);
+    A[0][j] = z;
+    A[1][j] = fma(-4.0 * a * ax, Axx, s * Ax);
+    A[2][j] = s * At;
+    A[3][j] = s * Axx;
+  }
+}
+
+// V5 <-> a staged [32 rows][20 units] tile T[row = 8 s + prow(g)][unit] (ld = 20): two 16-byte accesses for the first two
+// N tiles and one 8-byte access for this lane's unit of 16..19 per stream; all bank-conflict-free with the prow() row order.
+__device__ __forceinline__ void stage5(double* T, const double (&V)[4][5], int lane) {
   const int pg = prow(lane >> 2), q = lane & 3;
+  const int u4 = unit5(4, q);
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    double* row = T + (8 * s + pg) * W;
+    *reinterpret_cast<double2*>(row + 2 * q) = make_double2(V[s][0], V[s][1]);
+    *reinterpret_cast<double2*>(row + 8 + 2 * q) = make_double2(V[s][2], V[s][3]);
+    row[u4] = V[s][4];
+  }
+}
+__device__ __forceinline__ void load5(double (&V)[4][5], const double* T, int lane) {
+  const int pg = prow(lane >> 2), q = lane & 3;
+  const int u4 = unit5(4, q);
 #pragma unroll
   for (int s = 0; s < 4; s++) {
     const double* row = T + (8 * s + pg) * W;
     const double2 c0 = *reinterpret_cast<const double2*>(row + 2 * q);
     const double2 c1 = *reinterpret_cast<const double2*>(row + 8 + 2 * q);
-    double2 c2 = make_double2(0.0, 0.0);
-    if (q < 2) c2 = *reinterpret_cast<const double2*>(row + 16 + 2 * q);
-    V[s][0][0] = c0.x; V[s][0][1] = c0.y;
-    V[s][1][0] = c1.x; V[s][1][1] = c1.y;
-    V[s][2][0] = c2.x; V[s][2][1] = c2.y;
+    V[s][0] = c0.x; V[s][1] = c0.y; V[s][2] = c1.x; V[s][3] = c1.y;
+    V[s][4] = row[u4];
   }
 }
 
-// outputs of a tanh layer from its pre-activation streams (in place): Z -> (a, s z_x, s z_t, s (z_xx - 2 a z_x^2))
-__device__ __forceinline__ void act_forward(double (&Z)[4][3][2]) {
-  if (PINN_ABL_NOACT) return;
-#pragma unroll
-  for (int nt = 0; nt < 3; nt++)
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const double a = tanh_fast(Z[0][nt][e]);
-      const double zx = Z[1][nt][e];
-      const double s = fma(-a, a, 1.0);
-      Z[0][nt][e] = a;
-      Z[1][nt][e] = s * zx;
-      Z[2][nt][e] = s * Z[2][nt][e];
-      Z[3][nt][e] = s * fma(-2.0 * a * zx, zx, Z[3][nt][e]);
-    }
-}
-
-// adjoints of the outputs (A, overwritten with the adjoints of the pre-activations) given the outputs H
-__device__ __forceinline__ void act_backward_out(double (&A)[4][3][2], const double (&H)[4][3][2]) {
-  if (PINN_ABL_NOACT) return;
-#pragma unroll
-  for (int nt = 0; nt < 3; nt++)
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const double a = H[0][nt][e], ax = H[1][nt][e], at = H[2][nt][e], axx = H[3][nt][e];
-      const double A0 = A[0][nt][e], Ax = A[1][nt][e], At = A[2][nt][e], Axx = A[3][nt][e];
-      const double s = fma(-a, a, 1.0);
-      const double u1 = fma(ax, Ax, at * At);
-      const double u2 = fma(a, axx, ax * ax);
-      double z = fma(-2.0 * a, u1, s * A0);
-      z = fma(-2.0 * Axx, u2, z);
-      A[0][nt][e] = z;
-      A[1][nt][e] = fma(-4.0 * a * ax, Axx, s * Ax);
-      A[2][nt][e] = s * At;
-      A[3][nt][e] = s * Axx;
-    }
-}
-
-// ---- wgrad-warp tile ownership.  Hidden layer l: warp position k = (wg - l) & 3; k == 0 owns tiles 0,1,2, k owns
-// tiles 2k+1, 2k+2 (tile t = 3*mt + nt).  Layer 0 (MT = 1): warp 0 owns nt 0,1; warp 1 owns nt 2.
-struct Own { int n; int mt[3]; int nt[3]; };
-__device__ __forceinline__ Own ownership(int l, int wg) {
-  Own o;
-  if (PINN_WG_ROWS) {
-    const int k = l == 0 ? wg : ((wg - l) & 3);
-    o.n = (l == 0 ? k == 0 : k < 3) ? 3 : 0;
-    o.mt[0] = o.mt[1] = o.mt[2] = l == 0 ? 0 : (k < 3 ? k : 0);
-    o.nt[0] = 0; o.nt[1] = 1; o.nt[2] = 2;
-    return o;
-  }
-  if (l == 0) {
-    o.n = wg == 0 ? 2 : (wg == 1 ? 1 : 0);
-    o.mt[0] = o.mt[1] = o.mt[2] = 0;
-    o.nt[0] = wg == 0 ? 0 : 2; o.nt[1] = 1; o.nt[2] = 0;
-    return o;
-  }
+// ---------------------------------------------------------------------------------------------------
+// wgrad warps
+// ---------------------------------------------------------------------------------------------------
+// tile-row ownership: hidden layer l: position k = (wg - l) & 3; k < 3 owns (mt = k; nt = 0,1,2).  Layer 0 has one tile row
+// (inputs x^, t^ and the bias unit): warp 0.
+__device__ __forceinline__ int owned_row(int l, int wg) {
+  if (l == 0) return wg == 0 ? 0 : -1;
   const int k = (wg - l) & 3;
-  o.n = k == 0 ? 3 : 2;
-  const int ft = k == 0 ? 0 : 2 * k + 1;
-#pragma unroll
-  for (int s = 0; s < 3; s++) {
-    const int t = ft + s;
-    o.mt[s] = t / 3;
-    o.nt[s] = t - 3 * (t / 3);
-  }
-  return o;
+  return k < 3 ? k : -1;
 }
 
-// one weight-gradient task: accumulate this warp's owned tiles of layer L for one chain warp's 8-point tile
+// one weight-gradient task: accumulate this warp's tile row of layer L for one chain warp's 8-point tile.
+// Rows of the staged operands: R = 8*stream + 4*(ks&1) + q for k-step ks (K = 32 rows = 8 k-steps); A[row][i] = input unit i
+// of layer L (i == 20: the bias ones-row on the value stream), B[row][j] = Z-bar.
 template <int L>
-__device__ __forceinline__ void wgrad_task(double (&acc)[3][2], const Own& o, const double* Aop, const double* ZB,
-                                           const double* Wsm, double sc0, double sc1, int lane) {
+__device__ __forceinline__ void wgrad_task(double (&acc)[3][2], int mt, const double* Aop, const double* ZB, const double* sm,
+                                           double sc0, double sc1, int lane) {
   const int g = lane >> 2, q = lane & 3;
-  // layer-1 inputs are synthesised from the a-only stash of layer 0: per-lane constants of the units this lane reads
-  double w0x[3], w0t[3];
-  if (L == 1) {
-#pragma unroll
-    for (int s = 0; s < 3; s++) {
-      const int i = 8 * o.mt[s] + g;
-      w0x[s] = i < W ? sc0 * Wsm[i] : 0.0;
-      w0t[s] = i < W ? sc1 * Wsm[W + i] : 0.0;
-    }
-  }
-  if (PINN_WG_ROWS) {
-    // row ownership: tiles (mt; nt = 0,1,2).  B column pointers (padded columns read the zero column of the special page) and,
-    // for regular layers, the A column pointer (bias unit -> ones column, padding -> zero column) are chosen once.
-    const double* SP = Wsm - SM_W + SM_SPECIAL;
-    const int i = 8 * o.mt[0] + g;
-    const double* bp0 = ZB + g + q * W;
-    const double* bp1 = ZB + 8 + g + q * W;
-    const double* bp2 = (16 + g < W ? ZB + 16 + g : SP + 1) + q * W;
-    const double* ap = (i < W ? Aop + i : (i == W ? SP : SP + 1)) + q * W;          // L >= 2: [32 rows][W] outputs of layer L-1
-    const double* ap1 = (i < W ? Aop + i : SP + 1) + q * W;                          // L == 1: a-only stash [8 rows][W]
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) {
-      const int st = ks >> 1;
-      const int off = (8 * st + 4 * (ks & 1)) * W;              // physical row 8*stream + 4*(ks&1) (+ q, folded into the pointers)
-      double a;
-      if (L >= 2) {
-        a = ap[off];
-      } else if (L == 1) {
-        const double av = ap1[4 * (ks & 1) * W];
-        const double sd = fma(-av, av, 1.0);
-        const double v = st == 0 ? av : (st == 1 ? sd * w0x[0] : (st == 2 ? sd * w0t[0] : -2.0 * av * sd * w0x[0] * w0x[0]));
-        a = (i == W && st == 0) ? 1.0 : v;                      // i >= W: av = 0 and w0x = w0t = 0, so v = 0
-      } else {
-        const int pr = 4 * (ks & 1) + q;
-        const double xv = Aop[pr * 2 + 0], tv = Aop[pr * 2 + 1];
-        a = i == 0 ? (st == 0 ? xv : (st == 1 ? sc0 : 0.0))
-                   : (i == 1 ? (st == 0 ? tv : (st == 2 ? sc1 : 0.0)) : ((i == 2 && st == 0) ? 1.0 : 0.0));
-      }
-      const double b0 = bp0[off], b1 = bp1[off], b2 = bp2[off];
-      dmma(acc[0], a, b0);
-      dmma(acc[1], a, b1);
-      dmma(acc[2], a, b2);
-    }
-    return;
-  }
-  if (L >= 2 && PINN_WG_FAST) {
-    // Experiment for the operand-fetch overhead seen in profiles/ncu_burgers_v2_r01_lines.md (2.2 instructions per operand per
-    // DMMA): choose each owned tile's A and B column pointer ONCE -- a padded lane points into the special page (ones-row or
-    // zeros) instead of being predicated -- so that the unrolled k loop is one LDS per operand with an immediate offset.
-    const double* SP = Wsm - SM_W + SM_SPECIAL;
-    const double* ap[3];
-    const double* bp[3];
-#pragma unroll
-    for (int s = 0; s < 3; s++) {
-      const int i = 8 * o.mt[s] + g, j = 8 * o.nt[s] + g;
-      ap[s] = (i < W ? Aop + i : (i == W ? SP : SP + 1)) + q * W;
-      bp[s] = (j < W ? ZB + j : SP + 1) + q * W;
-    }
-#pragma unroll
-    for (int ks = 0; ks < 8; ks++) {
-      const int off = (8 * (ks >> 1) + 4 * (ks & 1)) * W;       // physical row 8*stream + 4*(ks&1) (+ q, folded into the pointers)
-#pragma unroll
-      for (int s = 0; s < 3; s++)
-        if (s < o.n) dmma(acc[s], ap[s][off], bp[s][off]);      // warp-uniform
-    }
-    return;
-  }
-  if (L >= 2 && PINN_WG_ROLLED) {
-    // regular hidden layers: rolled k loop (keeps the kernel within the instruction cache); slots 0,1 always exist
-    const int i0 = 8 * o.mt[0] + g, i1 = 8 * o.mt[1] + g, i2 = 8 * o.mt[2] + g;
-    const int j0 = 8 * o.nt[0] + g, j1 = 8 * o.nt[1] + g, j2 = 8 * o.nt[2] + g;
-    const bool three = o.n == 3;
-#pragma unroll 2
-    for (int ks = 0; ks < 8; ks++) {
-      const int R = 4 * ks + q;
-      const double one = ks < 2 ? 1.0 : 0.0;       // ones-row (bias) on the value stream: rows 0..7
-      const double* ar = Aop + R * W;
-      const double* br = ZB + R * W;
-      const double a0 = i0 < W ? ar[i0] : (i0 == W ? one : 0.0);
-      const double a1 = i1 < W ? ar[i1] : (i1 == W ? one : 0.0);
-      const double b0 = j0 < W ? br[j0] : 0.0;
-      const double b1 = j1 < W ? br[j1] : 0.0;
-      dmma(acc[0], a0, b0);
-      dmma(acc[1], a1, b1);
-      if (three) {
-        const double a2 = i2 < W ? ar[i2] : (i2 == W ? one : 0.0);
-        const double b2 = j2 < W ? br[j2] : 0.0;
-        dmma(acc[2], a2, b2);
-      }
-    }
-    return;
-  }
+  const double* SP = sm + SM_SPECIAL;
+  const double* Wsm = sm + SM_W;
+  const int i = 8 * mt + g;
+  const double* bp0 = ZB + g + q * W;
+  const double* bp1 = ZB + 8 + g + q * W;
+  const double* bp2 = (16 + g < W ? ZB + 16 + g : SP + 1) + q * W;
+  const double* ap = (i < W ? Aop + i : (i == W ? SP : SP + 1)) + q * W;          // L >= 2: [32 rows][W] outputs of layer L-1
+  const double* ap1 = (i < W ? Aop + i : SP + 1) + q * W;                          // L == 1: a-only stash [8 rows][W]
+  // layer-1 inputs are synthesised from the a-only stash of layer 0: per-lane constants of the unit this lane reads
+  const double w0x = (L == 1 && i < W) ? sc0 * Wsm[i] : 0.0;
+  const double w0t = (L == 1 && i < W) ? sc1 * Wsm[W + i] : 0.0;
 #pragma unroll
   for (int ks = 0; ks < 8; ks++) {
-    const int st = ks >> 1;                 // stream of this k-step's rows
-    const int pr = 4 * (ks & 1) + q;        // physical point row
-    const int R = 8 * st + pr;
-#pragma unroll
-    for (int s = 0; s < 3; s++) {
-      if (s < o.n) {                        // warp-uniform
-        const int i = 8 * o.mt[s] + g;
-        const int j = 8 * o.nt[s] + g;
-        double a;
-        if (L >= 2) {
-          a = i < W ? Aop[R * W + i] : ((i == W && st == 0) ? 1.0 : 0.0);
-        } else if (L == 1) {
-          const double av = i < W ? Aop[pr * W + i] : 0.0;
-          const double sd = fma(-av, av, 1.0);
-          const double v = st == 0 ? av : (st == 1 ? sd * w0x[s] : (st == 2 ? sd * w0t[s] : -2.0 * av * sd * w0x[s] * w0x[s]));
-          a = i < W ? v : ((i == W && st == 0) ? 1.0 : 0.0);
-        } else {
-          // layer 0: inputs (x^, t^) on the value stream, (sc0, 0) on the x stream, (0, sc1) on the t stream; unit 2 = ones
-          const double xv = Aop[pr * 2 + 0], tv = Aop[pr * 2 + 1];
-          a = i == 0 ? (st == 0 ? xv : (st == 1 ? sc0 : 0.0))
-                     : (i == 1 ? (st == 0 ? tv : (st == 2 ? sc1 : 0.0)) : ((i == 2 && st == 0) ? 1.0 : 0.0));
-        }
-        const double b = j < W ? ZB[R * W + j] : 0.0;
-        dmma(acc[s], a, b);
-      }
+    const int st = ks >> 1;
+    const int off = (8 * st + 4 * (ks & 1)) * W;              // physical row 8*stream + 4*(ks&1) (+ q, folded into the pointers)
+    double a;
+    if (L >= 2) {
+      a = ap[off];
+    } else if (L == 1) {
+      const double av = ap1[4 * (ks & 1) * W];
+      const double sd = fma(-av, av, 1.0);
+      const double v = st == 0 ? av : (st == 1 ? sd * w0x : (st == 2 ? sd * w0t : -2.0 * av * sd * w0x * w0x));
+      a = (i == W && st == 0) ? 1.0 : v;                      // i >= W: av = 0 and w0x = w0t = 0, so v = 0
+    } else {
+      // layer 0: inputs (x^, t^) on the value stream, (sc0, 0) on the x stream, (0, sc1) on the t stream; unit 2 = ones
+      const int pr = 4 * (ks & 1) + q;
+      const double xv = Aop[pr * 2 + 0], tv = Aop[pr * 2 + 1];
+      a = i == 0 ? (st == 0 ? xv : (st == 1 ? sc0 : 0.0))
+                 : (i == 1 ? (st == 0 ? tv : (st == 2 ? sc1 : 0.0)) : ((i == 2 && st == 0) ? 1.0 : 0.0));
     }
+    const double b0 = bp0[off], b1 = bp1[off], b2 = bp2[off];
+    dmma(acc[0], a, b0);
+    dmma(acc[1], a, b1);
+    dmma(acc[2], a, b2);
   }
 }
 
 template <int L>
-__device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it, int half, const double* sm, uint64_t* bars,
-                                            double sc0, double sc1, int lane) {
+__device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it, int half, int chains, const double* sm,
+                                            uint64_t* bars, double sc0, double sc1, int lane) {
   constexpr int J = 7 - L;                  // task index within a tile (layers 7..0)
   const int T = 8 * it + J;
   const int slot = T % RING;
-  const Own o = ownership(L, wg);
+  const int mt = owned_row(L, wg);
 #pragma unroll 1
   for (int c = 2 * half; c < 2 * half + 2; c++) {
+    if (c >= chains) break;                 // chain warps beyond `chains` have no tiles in this launch
     wait_produced(bars, c, T);
     const double* stash = sm + SM_STASH + c * STASH_PER_WARP;
     const double* Aop = L >= 2 ? stash + STASH0 + (L - 2) * STASHL : (L == 1 ? stash : sm + SM_XT + (c * 2 + (it & 1)) * 16);
     const double* ZB = sm + SM_RING + (c * RING + slot) * 640;
-    if (!PINN_ABL_NOWG && o.n > 0) wgrad_task<L>(acc, o, Aop, ZB, sm + SM_W, sc0, sc1, lane);
+    if (!PINN_ABL_NOWG && mt >= 0) wgrad_task<L>(acc, mt, Aop, ZB, sm, sc0, sc1, lane);
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty(bars, c, slot));
   }
@@ -336,22 +278,20 @@ __device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it,
 template <int L>
 __device__ __forceinline__ void wgrad_flush(const double (&acc)[3][2], int wg, double* outp, int lane) {
   const int g = lane >> 2, q = lane & 3;
-  const Own o = ownership(L, wg);
+  const int mt = owned_row(L, wg);
   const int in_dim = L == 0 ? 2 : W;
+  const int i = 8 * mt + g;
+  if (mt < 0) return;
 #pragma unroll
-  for (int s = 0; s < 3; s++) {
-    if (s < o.n) {
-      const int i = 8 * o.mt[s] + g;
+  for (int nt = 0; nt < 3; nt++)
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int j = 8 * o.nt[s] + 2 * q + e;
-        if (j < W) {
-          if (i < in_dim) outp[woff(L) + i * W + j] = acc[s][e];
-          else if (i == in_dim) outp[boff(L) + j] = acc[s][e];
-        }
+    for (int e = 0; e < 2; e++) {
+      const int j = 8 * nt + 2 * q + e;
+      if (j < W) {
+        if (i < in_dim) outp[woff(L) + i * W + j] = acc[nt][e];
+        else if (i == in_dim) outp[boff(L) + j] = acc[nt][e];
       }
     }
-  }
 }
 
 __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
@@ -362,15 +302,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
 
-  if (PINN_WG_FAST || PINN_WG_ROWS)
-    for (int i = threadIdx.x; i < 32 * W; i += THREADS) sm[SM_SPECIAL + i] = (i % W == 0 && i / W < 8) ? 1.0 : 0.0;
+  for (int i = threadIdx.x; i < 32 * W; i += THREADS) sm[SM_SPECIAL + i] = (i % W == 0 && i / W < 8) ? 1.0 : 0.0;
   if (threadIdx.x == 0) {
     mbar_init(bars, 1);
     for (int i = 0; i < CHAINS * RING; i++) {
       mbar_init(bars + 1 + 2 * i, 1);        // full: the producing chain warp's lane 0
       mbar_init(bars + 2 + 2 * i, 4);        // empty: lane 0 of each of the 4 wgrad warps
     }
-    mbar_init(bars + 1 + 2 * CHAINS * RING, 2);   // phase offset: the two chain warps of half A
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -380,17 +318,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   mbar_wait(bars, 0);
 
   const double sc0 = 2.0 / p.dx0, sc1 = 2.0 / p.dx1;
-  const long long n_rounds = (p.n_total + ROUND - 1) / ROUND;
+  const int chains = (p.chains >= 1 && p.chains <= CHAINS) ? p.chains : CHAINS;
+  const int round_pts = chains * TILE;
+  const long long n_rounds = (p.n_total + round_pts - 1) / round_pts;
   const int my_rounds = (int)((n_rounds - blockIdx.x + gridDim.x - 1) / gridDim.x);
   double* outp = p.partials + (size_t)blockIdx.x * PSTRIDE;
 
-  // Roles: chain warps 0-3, weight-gradient warps 4-7.  PINN_CHAIN_HIGH=1 swaps them (the issue arbiter is said to prefer
-  // the highest warp id); measured: no gain (0.452 vs 0.445 ms), so the plain order stays.
-#ifndef PINN_CHAIN_HIGH
-#define PINN_CHAIN_HIGH 0
-#endif
-  const bool is_wgrad = PINN_CHAIN_HIGH ? (warp < CHAINS) : (warp >= CHAINS);
-  if (is_wgrad) {
+  if (warp >= CHAINS) {
     // =========================================== wgrad warps ===========================================
     const int wg = warp & 3;
     double a0[3][2], a1[3][2], a2[3][2], a3[3][2], a4[3][2], a5[3][2], a6[3][2], a7[3][2];
@@ -403,16 +337,16 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     // The chain warps are consumed in two halves (chains 0,1 then chains 2,3).  Ring back-pressure then shifts the
     // halves by one phase: while one half runs its forward pass (which produces no weight-gradient work), the other
     // half runs its backward pass and keeps these warps -- and the FP64 pipe of every sub-partition -- busy.
-    for (int it2 = 0; it2 < (PINN_ABL_NOSTAGE ? 0 : 2 * my_rounds); it2++) {
+    for (int it2 = 0; it2 < 2 * my_rounds; it2++) {
       const int it = it2 >> 1, half = it2 & 1;
-      wgrad_layer<7>(a7, wg, it, half, sm, bars, sc0, sc1, lane);
-      wgrad_layer<6>(a6, wg, it, half, sm, bars, sc0, sc1, lane);
-      wgrad_layer<5>(a5, wg, it, half, sm, bars, sc0, sc1, lane);
-      wgrad_layer<4>(a4, wg, it, half, sm, bars, sc0, sc1, lane);
-      wgrad_layer<3>(a3, wg, it, half, sm, bars, sc0, sc1, lane);
-      wgrad_layer<2>(a2, wg, it, half, sm, bars, sc0, sc1, lane);
-      wgrad_layer<1>(a1, wg, it, half, sm, bars, sc0, sc1, lane);
-      wgrad_layer<0>(a0, wg, it, half, sm, bars, sc0, sc1, lane);
+      wgrad_layer<7>(a7, wg, it, half, chains, sm, bars, sc0, sc1, lane);
+      wgrad_layer<6>(a6, wg, it, half, chains, sm, bars, sc0, sc1, lane);
+      wgrad_layer<5>(a5, wg, it, half, chains, sm, bars, sc0, sc1, lane);
+      wgrad_layer<4>(a4, wg, it, half, chains, sm, bars, sc0, sc1, lane);
+      wgrad_layer<3>(a3, wg, it, half, chains, sm, bars, sc0, sc1, lane);
+      wgrad_layer<2>(a2, wg, it, half, chains, sm, bars, sc0, sc1, lane);
+      wgrad_layer<1>(a1, wg, it, half, chains, sm, bars, sc0, sc1, lane);
+      wgrad_layer<0>(a0, wg, it, half, chains, sm, bars, sc0, sc1, lane);
     }
     wgrad_flush<0>(a0, wg, outp, lane);
     wgrad_flush<1>(a1, wg, outp, lane);
@@ -424,21 +358,24 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     wgrad_flush<7>(a7, wg, outp, lane);
   } else {
     // =========================================== chain warps ===========================================
-    const int c = warp & 3;
+    const int c = warp;
+    const int n_tiles = c < chains ? my_rounds : 0;
     double* stash = sm + SM_STASH + c * STASH_PER_WARP;
     const double l1 = p.ide ? Wsm[P_NET] : 1.0;
     const double kap = p.ide ? exp(Wsm[P_NET + 1]) : p.nu;
     double loss_d = 0.0, loss_f = 0.0, gl1 = 0.0, gl2 = 0.0;
-    double g8[3][2], gb8 = 0.0;             // output-layer weight gradient: per-lane partials over this lane's points
+    double g8[5], gb8 = 0.0;                // output-layer weight gradient: per-lane partials over this lane's points
 #pragma unroll
-    for (int nt = 0; nt < 3; nt++) g8[nt][0] = g8[nt][1] = 0.0;
+    for (int j = 0; j < 5; j++) g8[j] = 0.0;
     const int pg = prow(g);
-    if (PINN_PHASE_OFFSET && c >= 2) mbar_wait(bars + 1 + 2 * CHAINS * RING, 0);   // start half a tile behind half A
+    int u5[5];                              // the five hidden units of this lane
+#pragma unroll
+    for (int j = 0; j < 5; j++) u5[j] = unit5(j, q);
     // coordinates of this lane's point in tile `it`; the next tile's pair is prefetched one tile ahead so that neither
     // the L2/HBM latency nor (zero-copy mode: p.xc in pinned host memory) the PCIe latency is exposed
     auto load_xt = [&](int it, double& xo, double& to) {
       const long long rnd = blockIdx.x + (long long)it * gridDim.x;
-      long long pt = rnd * ROUND + c * TILE + g;
+      long long pt = rnd * round_pts + c * TILE + g;
       if (pt >= p.n_total) pt = p.n_total - 1;
       if (p.xc && pt >= p.c0 && pt < p.c0 + p.n_c) {
         xo = __ldg(p.xc + (pt - p.c0)); to = __ldg(p.tc + (pt - p.c0));
@@ -447,16 +384,15 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       }
     };
     double xr_next = 0.0, tr_next = 0.0;
-    if (PINN_XT_PREFETCH && my_rounds > 0) load_xt(0, xr_next, tr_next);
+    if (n_tiles > 0) load_xt(0, xr_next, tr_next);
 
 #pragma unroll 1
-    for (int it = 0; it < my_rounds; it++) {
+    for (int it = 0; it < n_tiles; it++) {
       const long long rnd = blockIdx.x + (long long)it * gridDim.x;
-      const long long pt = rnd * ROUND + c * TILE + g;
+      const long long pt = rnd * round_pts + c * TILE + g;
       const bool in_set = pt < p.n_total;
-      if (!PINN_XT_PREFETCH) load_xt(it, xr_next, tr_next);
       const double xr = xr_next, tr = tr_next;
-      if (PINN_XT_PREFETCH && it + 1 < my_rounds) load_xt(it + 1, xr_next, tr_next);
+      if (it + 1 < n_tiles) load_xt(it + 1, xr_next, tr_next);
       const double wf = (in_set && pt >= p.c0 && pt < p.c0 + p.n_c) ? p.wf : 0.0;
       const bool has_d = in_set && pt >= p.d0 && pt < p.d0 + p.n_d;
       const double wd = has_d ? p.wd : 0.0;
@@ -466,29 +402,25 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       double* XT = sm + SM_XT + (c * 2 + (it & 1)) * 16;
       if (q == 0) { XT[pg * 2 + 0] = xh; XT[pg * 2 + 1] = th; }
 
-      double H[4][3][2];
+      double V[4][5];
       // ---------------- layer 0 (2 -> 20): direct
 #pragma unroll
-      for (int nt = 0; nt < 3; nt++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int col = 8 * nt + 2 * q + e;
-          const bool ok = col < W;
-          const double w0 = ok ? Wsm[col] : 0.0, w1 = ok ? Wsm[W + col] : 0.0, b = ok ? Wsm[2 * W + col] : 0.0;
-          H[0][nt][e] = fma(xh, w0, fma(th, w1, b));
-          H[1][nt][e] = sc0 * w0;
-          H[2][nt][e] = sc1 * w1;
-          H[3][nt][e] = 0.0;
-        }
-      act_forward(H);
-      // the a-only stash of layer 0 (and, with RING = 3, the layer-1 stash) is still the A operand of the previous
-      // tile's last tasks: wait until the layer-1 task (J = 6) has been consumed; consumers retire tasks in order
-      if (!PINN_ABL_NOSTAGE && it > 0) wait_consumed(bars, c, 8 * (it - 1) + 6);
-      if (!PINN_ABL_NOSTAGE) {
+      for (int j = 0; j < 5; j++) {
+        const double w0 = Wsm[u5[j]], w1 = Wsm[W + u5[j]], b = Wsm[2 * W + u5[j]];
+        V[0][j] = fma(xh, w0, fma(th, w1, b));
+        V[1][j] = sc0 * w0;
+        V[2][j] = sc1 * w1;
+        V[3][j] = 0.0;
+      }
+      act_forward5(V);
+      // the a-only stash of layer 0 is still the A operand of the previous tile's layer-1 task (J = 6): wait until it has
+      // been consumed; consumers retire tasks in order
+      if (it > 0) wait_consumed(bars, c, 8 * (it - 1) + 6);
+      {
         double* r0 = stash + pg * W;
-        *reinterpret_cast<double2*>(r0 + 2 * q) = make_double2(H[0][0][0], H[0][0][1]);
-        *reinterpret_cast<double2*>(r0 + 8 + 2 * q) = make_double2(H[0][1][0], H[0][1][1]);
-        if (q < 2) *reinterpret_cast<double2*>(r0 + 16 + 2 * q) = make_double2(H[0][2][0], H[0][2][1]);
+        *reinterpret_cast<double2*>(r0 + 2 * q) = make_double2(V[0][0], V[0][1]);
+        *reinterpret_cast<double2*>(r0 + 8 + 2 * q) = make_double2(V[0][2], V[0][3]);
+        r0[u5[4]] = V[0][4];
       }
       // ---------------- hidden layers 1..7: DMMA chain
 #pragma unroll 1
@@ -503,36 +435,24 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
             Z[0][nt][e] = (col < W) ? Wl[W * W + col] : 0.0;
             Z[1][nt][e] = Z[2][nt][e] = Z[3][nt][e] = 0.0;
           }
-        if (!PINN_ABL_NODMMA) burgers::mma_layer(Z, H, Wl, W, 1, lane);
-        act_forward(Z);
-#pragma unroll
-        for (int s = 0; s < 4; s++)
-#pragma unroll
-          for (int nt = 0; nt < 3; nt++) { H[s][nt][0] = Z[s][nt][0]; H[s][nt][1] = Z[s][nt][1]; }
-        if (!PINN_ABL_NOSTAGE && l < NHID - 1) burgers::stage_rows(stash + STASH0 + (l - 1) * STASHL, H, lane);
+        if (!PINN_ABL_NODMMA) mma_layer5(Z, V, Wl, W, 1, lane);
+        c_to_v5(V, Z, lane);
+        act_forward5(V);
+        if (l < NHID - 1) stage5(stash + STASH0 + (l - 1) * STASHL, V, lane);
       }
-      if (PINN_PHASE_OFFSET && it == 0 && c < 2) { __syncwarp(); if (lane == 0) mbar_arrive(bars + 1 + 2 * CHAINS * RING); }
       // ---------------- output layer (20 -> 1), residual, seeds
-      double seed[4];
-      double A[4][3][2];
+      double A[4][5];
       {
         const double* W8 = Wsm + woff(8);
-        double w8[3][2];
+        double w8[5];
 #pragma unroll
-        for (int nt = 0; nt < 3; nt++)
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int col = 8 * nt + 2 * q + e;
-            w8[nt][e] = (col < W) ? W8[col] : 0.0;
-          }
+        for (int j = 0; j < 5; j++) w8[j] = W8[u5[j]];
         double out[4];
 #pragma unroll
         for (int s = 0; s < 4; s++) {
           double acc = 0.0;
 #pragma unroll
-          for (int nt = 0; nt < 3; nt++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) acc = fma(H[s][nt][e], w8[nt][e], acc);
+          for (int j = 0; j < 5; j++) acc = fma(V[s][j], w8[j], acc);
           acc += shfl_xor_d(acc, 1);
           acc += shfl_xor_d(acc, 2);
           out[s] = acc;
@@ -542,6 +462,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         const double f = utt + l1 * u * ux - kap * uxx;      // inf_cont_burgers.py:90 / ide_cont_burgers.py:85
         const double r = u - ut;
         const double cc = 2.0 * wf * f;
+        double seed[4];
         seed[0] = fma(cc * l1, ux, 2.0 * wd * r);
         seed[1] = cc * l1 * u;
         seed[2] = cc;
@@ -555,30 +476,26 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         }
         // output-layer weight gradient (per-lane partial over this lane's point) and adjoint of layer-7 outputs
 #pragma unroll
-        for (int nt = 0; nt < 3; nt++)
+        for (int j = 0; j < 5; j++) {
+          double acc = g8[j];
 #pragma unroll
-          for (int e = 0; e < 2; e++) {
-            double acc = g8[nt][e];
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-              acc = fma(H[s][nt][e], seed[s], acc);
-              A[s][nt][e] = seed[s] * w8[nt][e];
-            }
-            g8[nt][e] = acc;
+          for (int s = 0; s < 4; s++) {
+            acc = fma(V[s][j], seed[s], acc);
+            A[s][j] = seed[s] * w8[j];
           }
+          g8[j] = acc;
+        }
       }
-      // ---------------- backward: layers 7..1 (task J = 7-l, ring slot J&1)
+      // ---------------- backward: layers 7..1 (task J = 7-l, ring slot J % RING)
 #pragma unroll 1
       for (int l = NHID - 1; l >= 1; l--) {
         const int T = 8 * it + (7 - l), slot = T % RING;
-        if (!PINN_ABL_NOSTAGE && l < NHID - 1) load_rows(H, stash + STASH0 + (l - 1) * STASHL, lane);   // outputs of layer l (l=7: registers)
-        act_backward_out(A, H);                                                      // A := Z-bar
-        if (!PINN_ABL_NOSTAGE) {
-          if (T >= RING) wait_consumed(bars, c, T - RING);                           // the slot's previous task is done
-          burgers::stage_rows(sm + SM_RING + (c * RING + slot) * 640, A, lane);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
-        }
+        if (l < NHID - 1) load5(V, stash + STASH0 + (l - 1) * STASHL, lane);        // outputs of layer l (l = 7: registers)
+        act_backward5(A, V);                                                         // A := Z-bar
+        if (T >= RING) wait_consumed(bars, c, T - RING);                             // the slot's previous task is done
+        stage5(sm + SM_RING + (c * RING + slot) * 640, A, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
         // adjoint of the layer inputs: A_new = Z-bar * W_l^T
         {
           const double* Wl = Wsm + woff(l);
@@ -587,42 +504,31 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           for (int s = 0; s < 4; s++)
 #pragma unroll
             for (int nt = 0; nt < 3; nt++) An[s][nt][0] = An[s][nt][1] = 0.0;
-          if (!PINN_ABL_NODMMA) burgers::mma_layer(An, A, Wl, 1, W, lane);
-#pragma unroll
-          for (int s = 0; s < 4; s++)
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) { A[s][nt][0] = An[s][nt][0]; A[s][nt][1] = An[s][nt][1]; }
+          if (!PINN_ABL_NODMMA) mma_layer5(An, A, Wl, 1, W, lane);
+          c_to_v5(A, An, lane);
         }
       }
-      // ---------------- backward: layer 0 (task 7, slot 1): outputs rebuilt from the a-only stash
+      // ---------------- backward: layer 0 (task 7): outputs rebuilt from the a-only stash
       {
         const double* r0 = stash + pg * W;
         const double2 c0 = *reinterpret_cast<const double2*>(r0 + 2 * q);
         const double2 c1 = *reinterpret_cast<const double2*>(r0 + 8 + 2 * q);
-        double2 c2 = make_double2(0.0, 0.0);
-        if (q < 2) c2 = *reinterpret_cast<const double2*>(r0 + 16 + 2 * q);
-        const double av[3][2] = {{c0.x, c0.y}, {c1.x, c1.y}, {c2.x, c2.y}};
+        const double av[5] = {c0.x, c0.y, c1.x, c1.y, r0[u5[4]]};
 #pragma unroll
-        for (int nt = 0; nt < 3; nt++)
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int col = 8 * nt + 2 * q + e;
-            const bool ok = col < W;
-            const double a = av[nt][e], s = fma(-a, a, 1.0);
-            const double zx = ok ? sc0 * Wsm[col] : 0.0, zt = ok ? sc1 * Wsm[W + col] : 0.0;
-            H[0][nt][e] = a;
-            H[1][nt][e] = s * zx;
-            H[2][nt][e] = s * zt;
-            H[3][nt][e] = -2.0 * a * s * zx * zx;
-          }
-        act_backward_out(A, H);
-        const int T = 8 * it + 7, slot = T % RING;
-        if (!PINN_ABL_NOSTAGE) {
-          if (T >= RING) wait_consumed(bars, c, T - RING);
-          burgers::stage_rows(sm + SM_RING + (c * RING + slot) * 640, A, lane);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
+        for (int j = 0; j < 5; j++) {
+          const double a = av[j], s = fma(-a, a, 1.0);
+          const double zx = sc0 * Wsm[u5[j]], zt = sc1 * Wsm[W + u5[j]];
+          V[0][j] = a;
+          V[1][j] = s * zx;
+          V[2][j] = s * zt;
+          V[3][j] = -2.0 * a * s * zx * zx;
         }
+        act_backward5(A, V);
+        const int T = 8 * it + 7, slot = T % RING;
+        if (T >= RING) wait_consumed(bars, c, T - RING);
+        stage5(sm + SM_RING + (c * RING + slot) * 640, A, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
       }
     }
 
@@ -630,14 +536,11 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     double* red = sm + SM_RED + c * 64;
     loss_d = warp_sum(loss_d); loss_f = warp_sum(loss_f); gl1 = warp_sum(gl1); gl2 = warp_sum(gl2); gb8 = warp_sum(gb8);
 #pragma unroll
-    for (int nt = 0; nt < 3; nt++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        double v = g8[nt][e];
-        v += shfl_xor_d(v, 4); v += shfl_xor_d(v, 8); v += shfl_xor_d(v, 16);   // sum over the 8 points (g)
-        const int col = 8 * nt + 2 * q + e;
-        if (g == 0 && col < W) red[8 + col] = v;
-      }
+    for (int j = 0; j < 5; j++) {
+      double v = g8[j];
+      v += shfl_xor_d(v, 4); v += shfl_xor_d(v, 8); v += shfl_xor_d(v, 16);   // sum over the 8 points (g)
+      if (g == 0) red[8 + u5[j]] = v;
+    }
     if (lane == 0) { red[0] = loss_d; red[1] = loss_f; red[2] = gl1; red[3] = gl2; red[4] = gb8; }
   }
 

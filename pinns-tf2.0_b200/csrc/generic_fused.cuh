@@ -31,9 +31,9 @@ struct Args {
   const double* t;
   const double* tgt;          // data targets [n_d][out]
   long long n_total;
-  int pde;                    // PINN_BURGERS_INF / PINN_BURGERS_IDE / PINN_NLS_INF / PINN_BURGERS_DISC (3)
+  int pde;                    // PINN_BURGERS_INF / PINN_BURGERS_IDE / PINN_NLS_INF / PINN_BURGERS_DISC (3) / PINN_BURGERS_IDE_DISC (4)
   int in_dim;                 // 2 (x,t), or 1 (x only: discrete-time models)
-  double dt;                  // DISC: time step;  irk: (q+1) x q stage matrix, q = out - 1
+  double dt;                  // DISC: time step;  irk: (q+1) x q stage matrix, q = out - 1;  IDE_DISC: [M_0 ; M_1], each q x q, q = out
   const double* irk;
   // Burgers: points [d0, d0+n_d) carry the data term, [c0, c0+n_c) the residual term
   long long c0, n_c, d0, n_d;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
   double* SEED = OUTV + (size_t)pts * 4 * out;
   double* outp = p.partials + (size_t)blockIdx.x * p.pstride;
   const double sc0 = 2.0 / nd.dx0, sc1 = 2.0 / nd.dx1;
-  const bool ide = p.pde == 1;
+  const bool ide = p.pde == 1 || p.pde == 4;
   const double l1 = ide ? p.w[p.p_net] : 1.0;
   const double kap = ide ? exp(p.w[p.p_net + 1]) : p.nu;
 
@@ -147,43 +147,52 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
   }
   __syncthreads();
   double part0 = 0.0, part1 = 0.0, part2 = 0.0, gl1 = 0.0, gl2 = 0.0;
-  if (p.pde == 3) {
-    // Discrete-time IRK head (1d-burgers/inf_disc_burgers.py:61-101).  OUTV[pt] = [U_1 (q+1) | U_x | (t: 0) | U_xx]
-    //   N_j = U_j U_x,j - nu U_xx,j (j < q);  U_0,k = U_1,k + dt sum_j N_j IRK[k][j];  loss = sum (U_0 - u_0)^2 on the
-    //   data points + sum U_1^2 on the boundary points.  Scratch: NB[pt][q] (N, then N-bar), RB[pt][q+1] (2 (U_0 - u_0)).
-    const int q = out - 1;
+  if (p.pde == 3 || p.pde == 4) {
+    // Discrete-time IRK heads.  OUTV[pt] = [U (out) | U_x | (t: 0) | U_xx].
+    // pde 3, inference (1d-burgers/inf_disc_burgers.py:61-101), out = q+1:
+    //   N_j = U_j U_x,j - nu U_xx,j (j < q);  U_0,k = U_k + dt sum_j N_j IRK[k][j];  loss = sum (U_0 - u_0)^2 on the data
+    //   points + sum U^2 on the boundary points.
+    // pde 4, identification (1d-burgers/ide_disc_burgers.py:81-115), out = q, two snapshots [x_0 (n_d) | x_1]:
+    //   N_j = l1 U_j U_x,j - e^{l2} U_xx,j;  snapshot s: pred_k = U_k + dt sum_j N_j M_s[k][j] with M_0 = alpha and
+    //   M_1 = -(beta - alpha) (the sign of N' = -N folded into the matrix);  loss = sum (pred - u_s)^2 over points and stages.
+    // Scratch: NB[pt][q] (N, then N-bar), RB[pt][out] (2 x residual).
+    const bool idd = p.pde == 4;
+    const int q = idd ? out : out - 1;
     double* NB = A0;
     double* RB = A1;
     for (int idx = tid; idx < npts * q; idx += THREADS) {
       const int pt = idx / q, j = idx - pt * q;
       const double* o = OUTV + (size_t)pt * 4 * out;
-      NB[idx] = o[j] * o[out + j] - p.nu * o[3 * out + j];
+      NB[idx] = l1 * o[j] * o[out + j] - kap * o[3 * out + j];       // inference: l1 = 1, kap = nu
     }
     __syncthreads();
     for (int idx = tid; idx < npts * out; idx += THREADS) {
       const int pt = idx / out, k = idx - pt * out;
       const long long gp = base + pt;
-      const double u1k = OUTV[(size_t)pt * 4 * out + k];
-      if (gp < p.n_d) {
+      const double uk = OUTV[(size_t)pt * 4 * out + k];
+      if (idd || gp < p.n_d) {
+        const bool second = idd && gp >= p.n_d;
         const double* nrow = NB + (size_t)pt * q;
-        const double* irow = p.irk + (size_t)k * q;
+        const double* irow = p.irk + (second ? (size_t)q * q : 0) + (size_t)k * q;
         double acc = 0.0;
         for (int j = 0; j < q; j++) acc = fma(nrow[j], __ldg(irow + j), acc);
-        const double r = fma(p.dt, acc, u1k) - __ldg(p.tgt + gp);
-        part0 = fma(r, r, part0);
+        const double r = fma(p.dt, acc, uk) - __ldg(p.tgt + gp);      // targets: [u_0 | u_1]
+        if (second) part1 = fma(r, r, part1); else part0 = fma(r, r, part0);
         RB[idx] = 2.0 * r;
       } else {
-        part1 = fma(u1k, u1k, part1);
-        RB[idx] = 2.0 * u1k;                 // boundary point: d/dU_1 of sum U_1^2
+        part1 = fma(uk, uk, part1);
+        RB[idx] = 2.0 * uk;                  // boundary point: d/dU of sum U^2
       }
     }
     __syncthreads();
     for (int idx = tid; idx < npts * q; idx += THREADS) {
       const int pt = idx / q, j = idx - pt * q;
+      const long long gp = base + pt;
       double acc = 0.0;
-      if (base + pt < p.n_d) {
+      if (idd || gp < p.n_d) {
         const double* rrow = RB + (size_t)pt * out;
-        for (int k = 0; k < out; k++) acc = fma(rrow[k], __ldg(p.irk + (size_t)k * q + j), acc);
+        const double* mcol = p.irk + ((idd && gp >= p.n_d) ? (size_t)q * q : 0) + j;
+        for (int k = 0; k < out; k++) acc = fma(rrow[k], __ldg(mcol + (size_t)k * q), acc);
         acc *= p.dt;
       }
       NB[idx] = acc;                          // N-bar (0 on boundary points)
@@ -194,10 +203,12 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
       const double* o = OUTV + (size_t)pt * 4 * out;
       const double nb_ = k < q ? NB[(size_t)pt * q + k] : 0.0;
       double* sdp = SEED + (size_t)pt * 4 * out;
-      sdp[k] = fma(nb_, o[out + k], RB[idx]);
-      sdp[out + k] = nb_ * o[k];
+      sdp[k] = fma(nb_ * l1, o[out + k], RB[idx]);
+      sdp[out + k] = nb_ * l1 * o[k];
       sdp[2 * out + k] = 0.0;
-      sdp[3 * out + k] = -p.nu * nb_;
+      sdp[3 * out + k] = -kap * nb_;
+      gl1 = fma(nb_ * o[k], o[out + k], gl1);                         // d/d lambda_1, d/d lambda_2 (raw); unused for pde 3
+      gl2 = fma(-kap * nb_, o[3 * out + k], gl2);
     }
     __syncthreads();
   } else

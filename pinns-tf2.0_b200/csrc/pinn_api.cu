@@ -73,7 +73,8 @@ struct pinn_handle {
   double nu = 0.0, dt = 0.0;
   double* d_irk = nullptr;          // DISC: (q+1) x q stage matrix
   int irk_q = 0;
-  std::vector<double> h_x0;         // DISC: data x positions (host copy for re-assembly)
+  std::vector<double> h_x0;         // DISC: data x positions (host copy for re-assembly); IDE_DISC: snapshot 0 (x_1 lives in h_tb)
+  std::vector<double> h_u0, h_u1;   // IDE_DISC: targets of the two snapshots
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_sm = 0;
@@ -289,7 +290,18 @@ int burgers_launch_eval(pinn_t* h, const int* run_flag) {
   a.nu = h->nu; a.ide = ide ? 1 : 0;
   a.partials = h->d_partials;
   a.run_flag = run_flag;
-  const long long rounds = (n_total + B::ROUND - 1) / B::ROUND;
+  // v2: few points -> fewer chain warps per CTA and more CTAs (a launch then lasts one tile on lightly loaded SMs)
+  int chains = 4;
+  if (h->burgers_kernel == 2) {
+    const long long n_tiles = (n_total + B::TILE - 1) / B::TILE;
+    if (n_tiles < 4LL * h->n_cta) {
+      chains = (int)((n_tiles + h->n_cta - 1) / h->n_cta);
+      if (chains < 1) chains = 1;
+    }
+  }
+  a.chains = chains;
+  const long long round_pts = (long long)chains * B::TILE;
+  const long long rounds = (n_total + round_pts - 1) / round_pts;
   int grid = (int)(rounds < h->n_cta ? rounds : h->n_cta);
   if (h->burgers_kernel == 2)
     pinn::burgers2::fused_loss_grad<<<grid, pinn::burgers2::THREADS, pinn::burgers2::SMEM_BYTES, h->stream>>>(a);
@@ -338,8 +350,9 @@ int disc_upload_points(pinn_t* h) {
 
 int generic_launch_eval(pinn_t* h, const int* run_flag) {
   namespace G = pinn::generic;
-  const bool disc = h->pde == PINN_BURGERS_DISC;
-  if (disc && (!h->d_irk || h->irk_q + 1 != h->layers.back())) return fail("discrete-time model: call pinn_set_irk first");
+  const bool idd = h->pde == PINN_BURGERS_IDE_DISC;
+  const bool disc = h->pde == PINN_BURGERS_DISC || idd;
+  if (disc && (!h->d_irk || h->irk_q + (idd ? 0 : 1) != h->layers.back())) return fail("discrete-time model: call pinn_set_irk first");
   const bool nls = h->pde == PINN_NLS_INF, ide = h->pde == PINN_BURGERS_IDE;
   const long long n_total = disc ? h->n_aux : (nls ? h->n_aux + h->n_c : (ide ? h->n_d : h->n_d + h->n_c));
   if (n_total <= 0) return fail("no points set (pinn_set_collocation / pinn_set_data)");
@@ -388,7 +401,7 @@ int generic_launch_eval(pinn_t* h, const int* run_flag) {
   pinn::ReduceMap map{};
   map.p_net = h->P_net;
   map.n_extra = 0;
-  if (ide) { map.extra_src[map.n_extra++] = h->P_net + 0; map.extra_src[map.n_extra++] = h->P_net + 1; }
+  if (ide || idd) { map.extra_src[map.n_extra++] = h->P_net + 0; map.extra_src[map.n_extra++] = h->P_net + 1; }
   map.extra_src[map.n_extra++] = h->P_net + 3;
   map.extra_src[map.n_extra++] = h->P_net + 4;
   map.extra_src[map.n_extra++] = h->P_net + 5;
@@ -543,7 +556,7 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
                 int device, int rank, int world, const void* nccl_uid) {
   if (!out || !layers || !lb || !ub) return fail("pinn_create: null argument");
   if (n_layers < 3 || n_layers > pinn::MAXL) return fail("pinn_create: need 3..16 layer sizes");
-  if (pde_id < 0 || pde_id > 3) return fail("pinn_create: unknown pde_id");
+  if (pde_id < 0 || pde_id > 4) return fail("pinn_create: unknown pde_id");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("pinn_create: no CUDA device -- this library has no CPU fallback");
@@ -551,7 +564,7 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
   pinn_t* h = new pinn_t();
   h->pde = pde_id; h->device = device; h->rank = rank; h->world = world < 1 ? 1 : world;
   h->layers.assign(layers, layers + n_layers);
-  const bool disc = pde_id == PINN_BURGERS_DISC;
+  const bool disc = pde_id == PINN_BURGERS_DISC || pde_id == PINN_BURGERS_IDE_DISC;
   for (int i = 0; i < n_layers; i++) {
     const int v = h->layers[i];
     const int cap = (disc && i == n_layers - 1) ? 512 : pinn::MAXW;     // the IRK head may be q+1 = 501 wide
@@ -565,7 +578,9 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
   h->lb[1] = disc ? 0.0 : lb[1]; h->ub[1] = disc ? 1.0 : ub[1];            // the t axis does not exist for 1-D nets
   if (!(h->ub[0] > h->lb[0]) || !(h->ub[1] > h->lb[1])) { delete h; return fail("pinn_create: need ub > lb"); }
   const int want_out = pde_id == PINN_NLS_INF ? 2 : 1;
-  if (disc) {
+  if (pde_id == PINN_BURGERS_IDE_DISC) {
+    if (h->layers.back() < 1) { delete h; return fail("pinn_create: the discrete-time identification model needs q >= 1 outputs"); }
+  } else if (disc) {
     if (h->layers.back() < 2) { delete h; return fail("pinn_create: the discrete-time model needs q+1 >= 2 outputs"); }
   } else if (h->layers.back() != want_out) {
     delete h;
@@ -581,7 +596,7 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
   }
   h->P_net = 0;
   for (int l = 0; l + 1 < n_layers; l++) h->P_net += layers[l] * layers[l + 1] + layers[l + 1];
-  h->P = h->P_net + (pde_id == PINN_BURGERS_IDE ? 2 : 0);
+  h->P = h->P_net + ((pde_id == PINN_BURGERS_IDE || pde_id == PINN_BURGERS_IDE_DISC) ? 2 : 0);
 
 #define CREATE_TRY(expr)                                                                          \
   do {                                                                                            \
@@ -689,6 +704,11 @@ int pinn_set_pde_params(pinn_t* h, const double* p, int n) {
     h->nu = p[0]; h->dt = p[1];
     return 0;
   }
+  if (h->pde == PINN_BURGERS_IDE_DISC) {
+    if (n != 1 || !p) return fail("pinn_set_pde_params: BURGERS_IDE_DISC takes [dt]");
+    h->dt = p[0];
+    return 0;
+  }
   if (n != 0) return fail("pinn_set_pde_params: this PDE takes no constants");
   return 0;
 }
@@ -700,13 +720,13 @@ int pinn_get_params(pinn_t* h, double* p, int n) {
     p[0] = h->nu;                                   // inf_cont_burgers.py:92-93
     return 0;
   }
-  if (h->pde == PINN_BURGERS_IDE) {
-    if (n != 2) return fail("pinn_get_params: BURGERS_IDE has two parameters (lambda_1, exp(lambda_2))");
+  if (h->pde == PINN_BURGERS_IDE || h->pde == PINN_BURGERS_IDE_DISC) {
+    if (n != 2) return fail("pinn_get_params: identification has two parameters (lambda_1, exp(lambda_2))");
     CUDA_TRY(cudaSetDevice(h->device));
     double lam[2];
     CUDA_TRY(cudaMemcpyAsync(lam, h->d_w + h->P_net, 16, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    p[0] = lam[0]; p[1] = std::exp(lam[1]);         // ide_cont_burgers.py:109-114
+    p[0] = lam[0]; p[1] = std::exp(lam[1]);         // ide_cont_burgers.py:109-114, ide_disc_burgers.py:138-143
     return 0;
   }
   if (h->pde == PINN_BURGERS_DISC) {
@@ -720,13 +740,16 @@ int pinn_get_params(pinn_t* h, double* p, int n) {
 
 int pinn_set_irk(pinn_t* h, const double* irk, int q) {
   if (!h || !irk) return fail("pinn_set_irk: null argument");
-  if (h->pde != PINN_BURGERS_DISC) return fail("pinn_set_irk: only the discrete-time model has a stage matrix");
-  if (q + 1 != h->layers.back()) return fail("pinn_set_irk: q+1 must equal the network's output width");
+  if (h->pde != PINN_BURGERS_DISC && h->pde != PINN_BURGERS_IDE_DISC) return fail("pinn_set_irk: only the discrete-time models have stage matrices");
+  const bool idd = h->pde == PINN_BURGERS_IDE_DISC;
+  if (!idd && q + 1 != h->layers.back()) return fail("pinn_set_irk: q+1 must equal the network's output width");
+  if (idd && q != h->layers.back()) return fail("pinn_set_irk: q must equal the network's output width");
+  const size_t n_rows = idd ? (size_t)2 * q : (size_t)q + 1;      // identification: [M_0 ; M_1], each q x q
   CUDA_TRY(cudaSetDevice(h->device));
   if (h->d_irk) cudaFree(h->d_irk);
   h->d_irk = nullptr;
-  CUDA_TRY(cudaMalloc((void**)&h->d_irk, (size_t)(q + 1) * q * 8));
-  CUDA_TRY(cudaMemcpy(h->d_irk, irk, (size_t)(q + 1) * q * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc((void**)&h->d_irk, n_rows * q * 8));
+  CUDA_TRY(cudaMemcpy(h->d_irk, irk, n_rows * q * 8, cudaMemcpyHostToDevice));
   h->irk_q = q;
   return 0;
 }
@@ -734,7 +757,8 @@ int pinn_set_irk(pinn_t* h, const double* irk, int q) {
 int pinn_set_collocation(pinn_t* h, const double* x, const double* t, int64_t n, int64_t n_global) {
   if (!h) return fail("null handle");
   if (h->pde == PINN_BURGERS_IDE) return fail("pinn_set_collocation: identification uses the data points as residual points");
-  if (h->pde == PINN_BURGERS_DISC) return fail("pinn_set_collocation: the discrete-time model has no collocation set (x_0 data + x_1 boundary)");
+  if (h->pde == PINN_BURGERS_DISC || h->pde == PINN_BURGERS_IDE_DISC)
+    return fail("pinn_set_collocation: the discrete-time models have no collocation set (snapshot / boundary points only)");
   if (n < 0 || (n > 0 && (!x || !t))) return fail("pinn_set_collocation: bad arguments");
   if (n_global < n) return fail("pinn_set_collocation: n_global < n");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -773,6 +797,7 @@ int pinn_set_data(pinn_t* h, const double* X, int64_t n, int in_dim, const doubl
   if (!h) return fail("null handle");
   if (n < 0 || (n > 0 && (!X || !u))) return fail("pinn_set_data: bad arguments");
   if (in_dim != 1 && in_dim != 2) return fail("pinn_set_data: in_dim must be 1 (broadcast quirk) or 2");
+  if (h->pde == PINN_BURGERS_IDE_DISC) return pinn_set_snapshot(h, 0, X, n, u);
   if (h->pde == PINN_BURGERS_DISC) {
     // x_0 (n,1) and u_0 (n,1): the snapshot the q stages are fitted to (inf_disc_burgers.py:98-101; u_0 broadcasts)
     if (in_dim != 1 || out_dim != 1) return fail("pinn_set_data: the discrete-time model takes x_0 (n,1) and u_0 (n,1)");
@@ -820,6 +845,27 @@ int pinn_set_data(pinn_t* h, const double* X, int64_t n, int in_dim, const doubl
   return 0;
 }
 
+int pinn_set_snapshot(pinn_t* h, int which, const double* x, int64_t n, const double* u) {
+  if (!h) return fail("null handle");
+  if (h->pde != PINN_BURGERS_IDE_DISC) return fail("pinn_set_snapshot: only the discrete-time identification model has two snapshots");
+  if ((which != 0 && which != 1) || n < 0 || (n > 0 && (!x || !u))) return fail("pinn_set_snapshot: bad arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  // host copies of both snapshots: the device blocks [x_0 | x_1] and [u_0 | u_1] are re-assembled whenever one changes
+  (which == 0 ? h->h_x0 : h->h_tb).assign(x, x + n);
+  (which == 0 ? h->h_u0 : h->h_u1).assign(u, u + n);
+  h->n_d = (long long)h->h_x0.size();
+  h->n_b = (long long)h->h_tb.size();
+  h->d_out_dim = 1; h->data_weight = 1.0;
+  const long long nu = h->n_d + h->n_b;
+  if (nu) {
+    if (ensure(&h->d_u, &h->u_cap, nu)) return -1;
+    if (h->n_d) CUDA_TRY(cudaMemcpyAsync(h->d_u, h->h_u0.data(), h->n_d * 8, cudaMemcpyHostToDevice, h->stream));
+    if (h->n_b) CUDA_TRY(cudaMemcpyAsync(h->d_u + h->n_d, h->h_u1.data(), h->n_b * 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  return disc_upload_points(h);
+}
+
 int pinn_set_boundary(pinn_t* h, const double* tb, int64_t n_b) {
   if (!h) return fail("null handle");
   if (h->pde == PINN_BURGERS_DISC) {
@@ -829,7 +875,7 @@ int pinn_set_boundary(pinn_t* h, const double* tb, int64_t n_b) {
     CUDA_TRY(cudaSetDevice(h->device));
     return disc_upload_points(h);
   }
-  if (h->pde != PINN_NLS_INF) return fail("pinn_set_boundary: only the NLS and discrete-time problems have a boundary term");
+  if (h->pde != PINN_NLS_INF) return fail("pinn_set_boundary: only the NLS and discrete-time inference problems have a boundary term");
   if (n_b < 0 || (n_b > 0 && !tb)) return fail("pinn_set_boundary: bad arguments");
   h->h_tb.assign(tb, tb + n_b);
   h->n_b = n_b;
@@ -1052,13 +1098,13 @@ int pinn_derivatives(pinn_t* h, const double* X, int64_t n, double* out) {
 
 int64_t pinn_num_residual_points(const pinn_t* h) {
   if (!h) return -1;
-  if (h->pde == PINN_BURGERS_DISC) return 0;
+  if (h->pde == PINN_BURGERS_DISC || h->pde == PINN_BURGERS_IDE_DISC) return 0;
   return h->pde == PINN_BURGERS_IDE ? h->n_d : h->n_c;
 }
 
 int pinn_residual(pinn_t* h, double* f_out, int64_t n_rows) {
   if (!h || !f_out) return fail("null argument");
-  if (h->pde == PINN_BURGERS_DISC) return fail("pinn_residual: not defined for the discrete-time model");
+  if (h->pde == PINN_BURGERS_DISC || h->pde == PINN_BURGERS_IDE_DISC) return fail("pinn_residual: not defined for the discrete-time models");
   const bool ide = h->pde == PINN_BURGERS_IDE;
   const int64_t n = ide ? h->n_d : h->n_c;
   if (n_rows != n)

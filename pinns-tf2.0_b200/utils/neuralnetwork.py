@@ -96,11 +96,18 @@ class NeuralNetwork(object):
     def __init_subclass__(cls, **kw):
         super().__init_subclass__(**kw)
         # TensorFlow tape bodies in the reference subclasses are replaced by the fused-kernel equivalents
-        for name in ("loss", "f_model", "uvx_model", "U_0_model", "grad", "get_loss_and_flat_grad", "get_params",
+        for name in ("loss", "f_model", "uvx_model", "U_0_model", "U_1_model", "autograd", "grad", "get_loss_and_flat_grad", "get_params",
                      "wrap_training_variables", "get_weights", "set_weights"):
             if name in cls.__dict__ and name in _NATIVE_OVERRIDES and not getattr(cls.__dict__[name], "_keep", False):
                 setattr(cls, "_script_" + name, cls.__dict__[name])
                 setattr(cls, name, _NATIVE_OVERRIDES[name])
+        # ide_disc_burgers.py writes its own training loop (fit(x_0,u_0,x_1,u_1) :149-194, predict :197-202) around tape code:
+        # four-argument fit / predict of a two-snapshot model go to the native loop, everything else stays the script's
+        for name in ("fit", "predict"):
+            if name in cls.__dict__ and not getattr(cls.__dict__[name], "_keep", False):
+                script_fn = cls.__dict__[name]
+                setattr(cls, "_script_" + name, script_fn)
+                setattr(cls, name, _two_snapshot_dispatch(name, script_fn))
 
     def __init__(self, hp, logger, ub, lb):
         layers = hp["layers"]
@@ -139,7 +146,9 @@ class NeuralNetwork(object):
     def _pde_id(self):
         tag = self.pde
         if tag is None:
-            if hasattr(self, "IRK_weights"):
+            if hasattr(self, "IRK_alpha"):
+                tag = "burgers_ide_disc"
+            elif hasattr(self, "IRK_weights"):
                 tag = "burgers_disc"
             elif hasattr(self, "lambda_1"):
                 tag = "burgers_ide"
@@ -150,7 +159,7 @@ class NeuralNetwork(object):
             else:
                 raise pinn_cabi.PinnError("cannot recognise the PDE of %s: set the class attribute `pde`" % type(self).__name__)
         return {"burgers_inf": pinn_cabi.BURGERS_INF, "burgers_ide": pinn_cabi.BURGERS_IDE, "nls_inf": pinn_cabi.NLS_INF,
-                "burgers_disc": pinn_cabi.BURGERS_DISC}[tag]
+                "burgers_disc": pinn_cabi.BURGERS_DISC, "burgers_ide_disc": pinn_cabi.BURGERS_IDE_DISC}[tag]
 
     def _native(self):
         if self._h is None:
@@ -166,6 +175,10 @@ class NeuralNetwork(object):
                 h.set_pde_params([float(self.nu), float(np.asarray(self.dt).reshape(-1)[0])])
                 h.set_irk(np.asarray(self.IRK_weights, dtype=np.float64))
                 h.set_boundary(np.asarray(self.x_1, dtype=np.float64).reshape(-1))
+            elif pde == pinn_cabi.BURGERS_IDE_DISC:                  # ide_disc_burgers.py:49-55, :151-152
+                h.set_pde_params([float(np.asarray(self.dt).reshape(-1)[0])])
+                h.set_irk(pinn_cabi.irk_ide_disc(self.IRK_alpha, self.IRK_beta))
+                w = np.concatenate([w, [0.0, -6.0]])
             elif pde == pinn_cabi.BURGERS_IDE:
                 l1 = float(np.asarray(self.lambda_1.numpy() if hasattr(self.lambda_1, "numpy") else self.lambda_1).reshape(-1)[0])
                 l2 = float(np.asarray(self.lambda_2.numpy() if hasattr(self.lambda_2, "numpy") else self.lambda_2).reshape(-1)[0])
@@ -177,14 +190,37 @@ class NeuralNetwork(object):
             self._h = h
         return self._h
 
+    @staticmethod
+    def _data_key(*arrays):
+        """Identity AND content of the bound arrays: an array mutated in place between calls is uploaded again.  The key holds
+        the object identity, the shape and a checksum of the bytes (whole array up to 1 MiB -- the data terms are at most a few
+        thousand rows -- else its first and last 64 KiB)."""
+        import zlib
+        key = []
+        for a in arrays:
+            b = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+            raw = b.reshape(-1).view(np.uint8)
+            crc = zlib.crc32(raw.tobytes()) if raw.size <= (1 << 20) else zlib.crc32(raw[:65536].tobytes() + raw[-65536:].tobytes())
+            key.append((id(a), b.shape, crc))
+        return tuple(key)
+
     def _bind(self, X, u):
-        """Upload the data term when (X,u) changes (fit/grad are always called with the same arrays)."""
-        key = (id(X), id(u))
+        """Upload the data term when (X,u) changes -- by identity or by content."""
+        key = self._data_key(X, u)
         if self._bound != key:
             Xa, ua = np.asarray(X, dtype=np.float64), np.asarray(u, dtype=np.float64)
             self._native().set_data(Xa, ua, getattr(self, "data_weight", 1.0))
             self._bound = key
             self._bound_refs = (X, u)
+
+    def _bind_snapshots(self, x_0, u_0, x_1, u_1):
+        key = self._data_key(x_0, u_0, x_1, u_1)
+        if self._bound != key:
+            n = self._native()
+            n.set_snapshot(0, np.asarray(x_0, dtype=np.float64), np.asarray(u_0, dtype=np.float64))
+            n.set_snapshot(1, np.asarray(x_1, dtype=np.float64), np.asarray(u_1, dtype=np.float64))
+            self._bound = key
+            self._bound_refs = (x_0, u_0, x_1, u_1)
 
     def _as_tensor(self, a):
         return _t(a)
@@ -213,7 +249,7 @@ class NeuralNetwork(object):
 
     def wrap_training_variables(self):
         var = self.model.trainable_variables
-        if self._pde_id() == pinn_cabi.BURGERS_IDE:       # ide_cont_burgers.py:93-96
+        if self._pde_id() in (pinn_cabi.BURGERS_IDE, pinn_cabi.BURGERS_IDE_DISC):       # ide_cont_burgers.py:93-96
             w = self._native().get_weights()
             var = var + [_t(w[-2:-1]), _t(w[-1:])]
         return var
@@ -230,7 +266,8 @@ class NeuralNetwork(object):
         self._native().set_weights(np.asarray(w, dtype=np.float64))
 
     def get_loss_and_flat_grad(self, X, u):
-        self._bind(X, u)
+        if X is not None:
+            self._bind(X, u)
 
         def loss_and_flat_grad(w):
             loss, g, _ = self._native().loss_grad(w=np.asarray(w, dtype=np.float64))
@@ -281,8 +318,10 @@ class NeuralNetwork(object):
 
 
 # ---------------------------------------------------------------------- native replacements for subclass overrides
-def _native_loss(self, u, u_pred=None):
+def _native_loss(self, *args):
     """Composite PDE loss of the recognised problem on the bound data (value only)."""
+    if len(args) == 4:                                   # ide_disc_burgers.py:111-115 loss(x_0, u_0, x_1, u_1)
+        self._bind_snapshots(*args)
     loss, _, _ = self._native().loss_grad(want_grad=False)
     return np.float64(loss)
 
@@ -305,12 +344,92 @@ def _native_f_model(self, *args):
     return _t(f)
 
 
-def _native_U_0_model(self, x):
+def _ide_disc_models(self, x):
+    """U_0 = U + dt N alpha^T and U_1 = U - dt N (beta - alpha)^T on arbitrary points (ide_disc_burgers.py:81-108, predict
+    :197-202): network value and x-derivatives from the device, the two small q x q products on the host (off the step path)."""
+    n = self._native()
+    U, Ux, _, Uxx = n.derivatives(np.asarray(x, dtype=np.float64).reshape(-1, 1))
+    w = n.get_weights()
+    N = w[-2] * U * Ux - np.exp(w[-1]) * Uxx
+    M = pinn_cabi.irk_ide_disc(self.IRK_alpha, self.IRK_beta)
+    q = M.shape[1]
+    dt = float(np.asarray(self.dt).reshape(-1)[0])
+    return _t(U + dt * N @ M[:q].T), _t(U + dt * N @ M[q:].T)
+
+
+def _native_U_0_model(self, x, customDummy=None):
+    if self._pde_id() == pinn_cabi.BURGERS_IDE_DISC:
+        return _ide_disc_models(self, x)[0]
     raise pinn_cabi.PinnError("U_0_model is evaluated inside the fused kernel; use grad()/fit()/predict()")
 
 
-def _native_grad(self, X, u):
-    return NeuralNetwork.grad(self, X, u)
+def _native_U_1_model(self, x, customDummy=None):
+    if self._pde_id() == pinn_cabi.BURGERS_IDE_DISC:
+        return _ide_disc_models(self, x)[1]
+    raise pinn_cabi.PinnError("U_1_model belongs to the discrete-time identification model")
+
+
+def _native_autograd(self, *args):
+    raise pinn_cabi.PinnError("autograd (the dummy-gradient tape trick) is replaced by the fused kernel's forward Taylor streams")
+
+
+def _native_fit_two_snapshots(self, x_0, u_0, x_1, u_1):
+    """fit(x_0, u_0, x_1, u_1) of ide_disc_burgers.py:149-194 on the device: lambda_1 = 0, lambda_2 = -6, tf_epochs Adam steps
+    (loss logged with the current lambdas), then the fixed-step L-BFGS, then the closing line."""
+    self.logger.log_train_start(self)
+    x_0, u_0, x_1, u_1 = (self.tensor(a) for a in (x_0, u_0, x_1, u_1))
+    self._bind_snapshots(x_0, u_0, x_1, u_1)
+    n = self._native()
+    w = n.get_weights()
+    w[-2:] = [0.0, -6.0]                                  # :151-152
+    n.set_weights(w)
+
+    def custom():
+        l1, l2 = self.get_params(numpy=True)
+        return f"l1 = {l1:5f}  l2 = {l2:8f}"
+
+    def log_train_epoch(epoch, loss, is_iter):
+        printed = epoch % self.logger.frequency == 0       # the lambdas are read back only for the lines that are printed
+        self.logger.log_train_epoch(epoch, loss, custom() if printed else "", is_iter)
+
+    self.logger.log_train_opt("Adam")
+    for epoch in range(self.tf_epochs):
+        n.adam_step(self.tf_lr, self.tf_b1, self.tf_b2, self.tf_eps, sync=False)
+        self._adam_serial = getattr(self, "_adam_serial", 0) + 1
+        # the reference logs (loss before the update, lambdas after it): :172-176
+        log_train_epoch(epoch, LazyLoss(n, self), False)
+    self.logger.log_train_opt("LBFGS")
+    closure = self.get_loss_and_flat_grad(None, None)
+    lbfgs(closure, self.get_weights(), self.nt_config, Struct(), True, log_train_epoch)
+    self.logger.log_train_end(self.tf_epochs, custom())
+
+
+def _two_snapshot_dispatch(name, script_fn):
+    def fit(self, *args):
+        if len(args) == 4 and self._pde_id() == pinn_cabi.BURGERS_IDE_DISC:
+            return _native_fit_two_snapshots(self, *args)
+        return script_fn(self, *args)
+
+    def predict(self, x_star, *rest):
+        try:
+            two = self._pde_id() == pinn_cabi.BURGERS_IDE_DISC
+        except pinn_cabi.PinnError:
+            two = False
+        if two:
+            return _ide_disc_models(self, x_star)
+        return script_fn(self, x_star, *rest)
+
+    fn = fit if name == "fit" else predict
+    fn.__name__ = name
+    return fn
+
+
+def _native_grad(self, *args):
+    if len(args) == 4:                                   # ide_disc_burgers.py:117-120 grad(x_0, u_0, x_1, u_1)
+        self._bind_snapshots(*args)
+        loss, g, _ = self._native().loss_grad()
+        return np.float64(loss), self._unflatten(g[: self._n_net_params()]) + [_t(g[-2:-1]), _t(g[-1:])]
+    return NeuralNetwork.grad(self, *args)
 
 
 def _native_get_loss_and_flat_grad(self, X, u):
@@ -326,9 +445,9 @@ def _native_get_params(self, numpy=False):
     pde = self._pde_id()
     if pde == pinn_cabi.BURGERS_INF:
         return self.nu
-    if pde == pinn_cabi.BURGERS_IDE:
+    if pde in (pinn_cabi.BURGERS_IDE, pinn_cabi.BURGERS_IDE_DISC):
         w = self._native().get_weights()
-        l1, l2 = w[-2], np.exp(w[-1])            # ide_cont_burgers.py:109-114
+        l1, l2 = w[-2], np.exp(w[-1])            # ide_cont_burgers.py:109-114, ide_disc_burgers.py:138-143
         return (l1, l2) if numpy else (_t([l1]), _t([l2]))
     return []
 
@@ -345,7 +464,8 @@ def _native_set_weights(self, w):
     return NeuralNetwork.set_weights(self, w)
 
 
-_NATIVE_OVERRIDES.update(U_0_model=_native_U_0_model, grad=_native_grad, get_loss_and_flat_grad=_native_get_loss_and_flat_grad)
+_NATIVE_OVERRIDES.update(U_0_model=_native_U_0_model, U_1_model=_native_U_1_model, autograd=_native_autograd, grad=_native_grad,
+                         get_loss_and_flat_grad=_native_get_loss_and_flat_grad)
 _NATIVE_OVERRIDES.update(loss=_native_loss, f_model=_native_f_model, uvx_model=_native_uvx_model,
                          get_params=_native_get_params, wrap_training_variables=_native_wrap_training_variables,
                          get_weights=_native_get_weights, set_weights=_native_set_weights)

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.realpath(__file__))
 # PINN_LIB: load another build of the same library (kernel experiments: profiles/kernel_variants.py)
 LIB_PATH = os.environ.get("PINN_LIB") or os.path.join(_HERE, "..", "lib", "libpinn_b200.so")
 
-BURGERS_INF, BURGERS_IDE, NLS_INF, BURGERS_DISC = 0, 1, 2, 3
+BURGERS_INF, BURGERS_IDE, NLS_INF, BURGERS_DISC, BURGERS_IDE_DISC = 0, 1, 2, 3, 4
 LBFGS_REASONS = {0: "running", 1: "max iterations", 2: "max evaluations", 3: "optimality", 4: "step below tolX",
                  5: "f change below tolX", 6: "no progress along direction", 7: "initial optimality"}
 
@@ -38,6 +38,7 @@ SIGNATURES = {
     "pinn_set_collocation": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64]),
     "pinn_set_collocation_mapped": (C.c_int, [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64]),
     "pinn_set_data": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int, _dp, C.c_int, C.c_double]),
+    "pinn_set_snapshot": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int64, _dp]),
     "pinn_set_boundary": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "pinn_set_weights": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "pinn_get_weights": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
@@ -154,15 +155,21 @@ class Pinn(object):
         self._ck(self.lib.pinn_set_pde_params(self.h, _p(a), a.size))
 
     def get_params(self):
-        n = {BURGERS_INF: 1, BURGERS_IDE: 2, NLS_INF: 0, BURGERS_DISC: 2}[self.pde]
+        n = {BURGERS_INF: 1, BURGERS_IDE: 2, NLS_INF: 0, BURGERS_DISC: 2, BURGERS_IDE_DISC: 2}[self.pde]
         out = np.zeros(max(n, 1))
         self._ck(self.lib.pinn_get_params(self.h, _p(out), n))
         return out[:n]
 
     def set_irk(self, irk):
+        """BURGERS_DISC: (q+1, q) stage matrix.  BURGERS_IDE_DISC: (2q, q) = [alpha ; -(beta - alpha)] (see irk_ide_disc)."""
         irk = _arr(irk)
-        assert irk.ndim == 2 and irk.shape[0] == irk.shape[1] + 1
+        assert irk.ndim == 2 and irk.shape[0] in (irk.shape[1] + 1, 2 * irk.shape[1])
         self._ck(self.lib.pinn_set_irk(self.h, _p(irk), irk.shape[1]))
+
+    def set_snapshot(self, which, x, u):
+        x, u = _arr(x).reshape(-1), _arr(u).reshape(-1)
+        assert x.size == u.size
+        self._ck(self.lib.pinn_set_snapshot(self.h, int(which), _p(x), x.size, _p(u)))
 
     def set_collocation(self, x, t, n_global=None):
         x, t = _arr(x).reshape(-1), _arr(t).reshape(-1)
@@ -297,6 +304,14 @@ class Pinn(object):
         buf = C.create_string_buffer(512)
         self._ck(self.lib.pinn_kernel_info(self.h, buf, 512))
         return json.loads(buf.value.decode())
+
+
+def irk_ide_disc(IRK_alpha, IRK_beta):
+    """Stage matrices of the discrete-time identification model for pinn_set_irk: [alpha ; -(beta - alpha)].  The difference is
+    formed in the arrays' OWN dtype (float32 tables in the reference, 1d-burgers/burgersutil.py:92, ide_disc_burgers.py:107)
+    before the conversion to float64 -- a float64 difference differs at the 1e-10 level."""
+    a, b = np.asarray(IRK_alpha), np.asarray(IRK_beta)
+    return np.concatenate([a.astype(np.float64), -(b - a).astype(np.float64)], 0)
 
 
 def device_tanh(x):
