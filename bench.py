@@ -215,6 +215,21 @@ def time_reference_port(n_f, steps, warmup, seed=1234, budget_s=110.0):
     return sec, threads, f, n_f
 
 
+def _port_baseline(kind, data, w, steps, warmup, n_pts, what, **adam):
+    """cpu_baseline of one of the extra configurations: the restated reference problem `kind` built from `data`, timed like
+    the headline arm (same fixed thread count)."""
+    import torch
+    from oracle import reference_port as rp
+    threads, ncpu = cpu_threads()
+    torch.set_num_threads(threads)
+    problem = {"burgers_inf": lambda: rp.BurgersInference(LAYERS, LB, UB, NU, *data),
+               "burgers_ide": lambda: rp.BurgersIdentification(LAYERS, LB, UB, *data),
+               "nls_inf": lambda: rp.SchrodingerInference(NLS_LAYERS, NLS_LB, NLS_UB, *data)}[kind]()
+    sec, _ = time_port_steps(problem, w, steps, warmup, **adam)
+    return {"value": n_pts / sec, "unit": "points/s", "ms_per_step": sec * 1e3, "cores": threads, "nproc": ncpu, "kind": "port",
+            "sample": "%d Adam steps after %d warm-up, %s (oracle/reference_port.py)" % (steps, warmup, what)}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -339,19 +354,9 @@ def cfg5_block(p, dist, rank, world, steps=20, iters=20):
             "lbfgs_iterations_timed": n_it, "timing": "CUDA events on the launching stream, L2 flushed between Adam steps, max over ranks"}
 
 
-def _port_baseline(make_problem, w, steps, warmup, n_pts, what, **adam):
-    import torch
-    threads, ncpu = cpu_threads()
-    torch.set_num_threads(threads)
-    sec, _ = time_port_steps(make_problem(), w, steps, warmup, **adam)
-    return {"value": n_pts / sec, "unit": "points/s", "ms_per_step": sec * 1e3, "cores": threads, "nproc": ncpu, "kind": "port",
-            "sample": "%d Adam steps after %d warm-up, %s (oracle/reference_port.py)" % (steps, warmup, what)}
-
-
 def measure_extras(pinn_cabi, n_f, with_cpu=True):
     """Other SURVEY section-8 configurations, measured briefly on the same box (not the headline metric), each with the
     restated reference timed on the host cores beside it."""
-    from oracle import reference_port as rp
     out = {}
     peak = fp64_peak()[0]
     eps = float(np.finfo(float).eps)
@@ -387,8 +392,7 @@ def measure_extras(pinn_cabi, n_f, with_cpu=True):
              "timing": "CUDA events, 200 back-to-back asynchronous steps (inputs 160 KB: L2-resident by nature)"}
         p.close()
         if with_cpu:
-            d["cpu_baseline"] = _port_baseline(lambda: rp.BurgersInference(LAYERS, LB, UB, NU, X_f, X_u, u), init_weights(), 8, 2, n1,
-                                               "N_f=10000 (the whole configuration)")
+            d["cpu_baseline"] = _port_baseline("burgers_inf", (X_f, X_u, u), init_weights(), 8, 2, n1, "N_f=10000 (the whole configuration)")
             d["speedup_vs_cpu_baseline"] = d["adam_points_per_s"] / d["cpu_baseline"]["value"]
         out["burgers_cfg1_10k"] = d
     except Exception as e:  # pragma: no cover
@@ -409,8 +413,7 @@ def measure_extras(pinn_cabi, n_f, with_cpu=True):
              "ms_per_step": ms, "points_per_s": 2000 / (ms * 1e-3), "lbfgs_ms_per_iteration": lb_ms, "lbfgs_iterations": n_it}
         p.close()
         if with_cpu:
-            d["cpu_baseline"] = _port_baseline(lambda: rp.BurgersIdentification(LAYERS, LB, UB, X_u, u), w_ide, 10, 2, 2000,
-                                               "N=2000 (the whole configuration)")
+            d["cpu_baseline"] = _port_baseline("burgers_ide", (X_u, u), w_ide, 10, 2, 2000, "N=2000 (the whole configuration)")
             d["speedup_vs_cpu_baseline"] = d["points_per_s"] / d["cpu_baseline"]["value"]
         out["burgers_identification"] = d
     except Exception as e:  # pragma: no cover
@@ -443,8 +446,8 @@ def measure_extras(pinn_cabi, n_f, with_cpu=True):
              "roofline_frac_fp64": flops / (k_ms * 1e-3) / 1e12 / peak}
         p.close()
         if with_cpu:
-            d["cpu_baseline"] = _port_baseline(lambda: rp.SchrodingerInference(NLS_LAYERS, NLS_LB, NLS_UB, X_f[:5000], tb, x0, uv0), w_nls,
-                                               4, 1, 5000, "bounded sample: N_f=5000 of the 20000 points", lr=0.05, b1=0.99, eps=0.1)
+            d["cpu_baseline"] = _port_baseline("nls_inf", (X_f[:5000], tb, x0, uv0), w_nls, 4, 1, 5000,
+                                               "bounded sample: N_f=5000 of the 20000 points", lr=0.05, b1=0.99, eps=0.1)
             d["speedup_vs_cpu_baseline"] = d["points_per_s"] / d["cpu_baseline"]["value"]
         out["schrodinger"] = d
     except Exception as e:  # pragma: no cover

@@ -154,6 +154,21 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
  * query the count. */
 int pinn_lbfgs_history(pinn_t* h, double* f_hist_out, int capacity, int* n_out);
 
+/* lbfgs() for an ARBITRARY opfunc (utils/custom_lbfgs.py:39-236 takes any closure x -> (f, g)): a stand-alone device-resident
+ * optimiser object.  The caller evaluates its objective wherever it likes; the iterate, the (s, y) history ring and the
+ * two-loop recursion live on the device and run through the same kernel as pinn_lbfgs, with the reference's control flow
+ * and quirks.  Protocol:  create(x0) -> f,g = opfunc(x0) -> feed(f, g) -> while status == PINN_LBFGS_RUNNING:
+ * f,g = opfunc(x_next); feed(f, g).  feed() returns in x_next the point to evaluate next or, once status != 0, the vector
+ * lbfgs() returns; logged_iter >= 1 names the iteration the reference would have logged after this evaluation (with its f),
+ * -1 none.  max_eval == 0 selects the reference default 1.25 * max_iter; n <= 32768. */
+typedef struct pinn_lbfgs_handle pinn_lbfgs_t;
+int pinn_lbfgs_create(pinn_lbfgs_t** out, int device, int64_t n, const double* x0, int max_iter, double learning_rate,
+                      int n_correction, double tol_fun, double tol_x, double max_eval);
+int pinn_lbfgs_feed(pinn_lbfgs_t* s, double f, const double* g, double* x_next, int* status_out, int* n_iter_out, int* n_eval_out,
+                    int* logged_iter_out, double* logged_f_out);
+int pinn_lbfgs_f_hist(pinn_lbfgs_t* s, double* f_hist_out, int capacity, int* n_out);
+int pinn_lbfgs_destroy(pinn_lbfgs_t* s);
+
 /* predict (utils/neuralnetwork.py:151-153): forward only on (n,in_dim) points -> (n,out_dim). */
 int pinn_predict(pinn_t* h, const double* X, int64_t n, int in_dim, double* out);
 /* f_model on the stored residual points (inf_cont_burgers.py:65-90,95-98): the collocation set, or the data points for

@@ -38,7 +38,10 @@
 //
 // Measured and dropped (profiles/kernel_variants_r02.md): 3-slot ring, per-tile-pair ownership 3/2/2/2 (0.451 -> 0.416 ms
 // with row ownership), holding the weight-gradient DMMAs back while the co-resident chain warp is in a DMMA phase
-// (slower: the weight-gradient warps starve), publishing Z-bar after the chain warp's own input-adjoint GEMM (no change).
+// (slower: the weight-gradient warps starve), publishing Z-bar after the chain warp's own input-adjoint GEMM (no change),
+// output units 16..19 of the chain GEMMs as 80 FMAs + a quad reduce-scatter instead of the half-padded third DMMA tile
+// (fewer pipe cycles on paper, 0.389 -> 0.416 ms in practice: DFMA interleaved with DMMA costs more than it saves); the same
+// for columns 16..19 of the weight-gradient tile rows (0.390 -> 0.410 ms).
 #pragma once
 #include "burgers_fused.cuh"
 
@@ -85,9 +88,9 @@ constexpr int STASH_PER_WARP = STASH0 + 6 * STASHL;   // 4000
 constexpr int SM_W = 0;
 constexpr int SM_STASH = SM_W + WPAD;
 constexpr int SM_RING = SM_STASH + CHAINS * STASH_PER_WARP;
-constexpr int SM_XT = SM_RING + CHAINS * RING * 640;
-constexpr int SM_RED = SM_XT + CHAINS * 2 * 16;
-constexpr int SM_BAR = SM_RED + 256;      // 1 + 2*CHAINS*RING mbarriers
+constexpr int RED_PER_WARP = 128;         // chain-warp partials: [0..4] scalars, [8..27] dW8, [32..91] dW0 (x row, t row), db0
+constexpr int SM_RED = SM_RING + CHAINS * RING * 640;
+constexpr int SM_BAR = SM_RED + CHAINS * RED_PER_WARP;      // 1 + 2*CHAINS*RING mbarriers
 constexpr int SM_SPECIAL = SM_BAR + 1 + 2 * CHAINS * RING + 1;   // [32 rows][W] page: column 0 = the bias ones-row (1 on the value
                                                                  // stream's rows 0..7), column 1 = 0
 constexpr int SM_DOUBLES = SM_SPECIAL + 32 * W;
@@ -96,7 +99,8 @@ constexpr int SMEM_BYTES = SM_DOUBLES * 8;   // ~201 KB
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Ring bookkeeping: chain warp c numbers its weight-gradient tasks T = 8*tile + J (J = 7 - layer).  Task T lives in ring
+// Ring bookkeeping: chain warp c numbers its weight-gradient tasks T = 7*tile + J (J = 7 - layer, layers 7..1; the
+// gradients of layer 0 and of the output layer are plain FMAs in the chain warp itself).  Task T lives in ring
 // slot T % RING; it is the (T / RING)-th use of that slot, i.e. phase T / RING of the slot's full and empty barriers.
 __device__ __forceinline__ uint64_t* bar_full(uint64_t* bars, int c, int slot) { return bars + 1 + (c * RING + slot) * 2; }
 __device__ __forceinline__ uint64_t* bar_empty(uint64_t* bars, int c, int slot) { return bars + 2 + (c * RING + slot) * 2; }
@@ -203,10 +207,8 @@ __device__ __forceinline__ void load5(double (&V)[4][5], const double* T, int la
 // ---------------------------------------------------------------------------------------------------
 // wgrad warps
 // ---------------------------------------------------------------------------------------------------
-// tile-row ownership: hidden layer l: position k = (wg - l) & 3; k < 3 owns (mt = k; nt = 0,1,2).  Layer 0 has one tile row
-// (inputs x^, t^ and the bias unit): warp 0.
+// tile-row ownership, hidden layers 1..7: position k = (wg - l) & 3; k < 3 owns (mt = k; nt = 0,1,2), k == 3 rests.
 __device__ __forceinline__ int owned_row(int l, int wg) {
-  if (l == 0) return wg == 0 ? 0 : -1;
   const int k = (wg - l) & 3;
   return k < 3 ? k : -1;
 }
@@ -236,17 +238,11 @@ __device__ __forceinline__ void wgrad_task(double (&acc)[3][2], int mt, const do
     double a;
     if (L >= 2) {
       a = ap[off];
-    } else if (L == 1) {
+    } else {
       const double av = ap1[4 * (ks & 1) * W];
       const double sd = fma(-av, av, 1.0);
       const double v = st == 0 ? av : (st == 1 ? sd * w0x : (st == 2 ? sd * w0t : -2.0 * av * sd * w0x * w0x));
       a = (i == W && st == 0) ? 1.0 : v;                      // i >= W: av = 0 and w0x = w0t = 0, so v = 0
-    } else {
-      // layer 0: inputs (x^, t^) on the value stream, (sc0, 0) on the x stream, (0, sc1) on the t stream; unit 2 = ones
-      const int pr = 4 * (ks & 1) + q;
-      const double xv = Aop[pr * 2 + 0], tv = Aop[pr * 2 + 1];
-      a = i == 0 ? (st == 0 ? xv : (st == 1 ? sc0 : 0.0))
-                 : (i == 1 ? (st == 0 ? tv : (st == 2 ? sc1 : 0.0)) : ((i == 2 && st == 0) ? 1.0 : 0.0));
     }
     const double b0 = bp0[off], b1 = bp1[off], b2 = bp2[off];
     dmma(acc[0], a, b0);
@@ -258,8 +254,8 @@ __device__ __forceinline__ void wgrad_task(double (&acc)[3][2], int mt, const do
 template <int L>
 __device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it, int half, int chains, const double* sm,
                                             uint64_t* bars, double sc0, double sc1, int lane) {
-  constexpr int J = 7 - L;                  // task index within a tile (layers 7..0)
-  const int T = 8 * it + J;
+  constexpr int J = 7 - L;                  // task index within a tile (layers 7..1)
+  const int T = 7 * it + J;
   const int slot = T % RING;
   const int mt = owned_row(L, wg);
 #pragma unroll 1
@@ -267,7 +263,7 @@ __device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it,
     if (c >= chains) break;                 // chain warps beyond `chains` have no tiles in this launch
     wait_produced(bars, c, T);
     const double* stash = sm + SM_STASH + c * STASH_PER_WARP;
-    const double* Aop = L >= 2 ? stash + STASH0 + (L - 2) * STASHL : (L == 1 ? stash : sm + SM_XT + (c * 2 + (it & 1)) * 16);
+    const double* Aop = L >= 2 ? stash + STASH0 + (L - 2) * STASHL : stash;
     const double* ZB = sm + SM_RING + (c * RING + slot) * 640;
     if (!PINN_ABL_NOWG && mt >= 0) wgrad_task<L>(acc, mt, Aop, ZB, sm, sc0, sc1, lane);
     __syncwarp();
@@ -279,7 +275,7 @@ template <int L>
 __device__ __forceinline__ void wgrad_flush(const double (&acc)[3][2], int wg, double* outp, int lane) {
   const int g = lane >> 2, q = lane & 3;
   const int mt = owned_row(L, wg);
-  const int in_dim = L == 0 ? 2 : W;
+  const int in_dim = W;
   const int i = 8 * mt + g;
   if (mt < 0) return;
 #pragma unroll
@@ -327,12 +323,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   if (warp >= CHAINS) {
     // =========================================== wgrad warps ===========================================
     const int wg = warp & 3;
-    double a0[3][2], a1[3][2], a2[3][2], a3[3][2], a4[3][2], a5[3][2], a6[3][2], a7[3][2];
+    double a1[3][2], a2[3][2], a3[3][2], a4[3][2], a5[3][2], a6[3][2], a7[3][2];
 #pragma unroll
     for (int s = 0; s < 3; s++)
 #pragma unroll
       for (int e = 0; e < 2; e++)
-        a0[s][e] = a1[s][e] = a2[s][e] = a3[s][e] = a4[s][e] = a5[s][e] = a6[s][e] = a7[s][e] = 0.0;
+        a1[s][e] = a2[s][e] = a3[s][e] = a4[s][e] = a5[s][e] = a6[s][e] = a7[s][e] = 0.0;
 #pragma unroll 1
     // The chain warps are consumed in two halves (chains 0,1 then chains 2,3).  Ring back-pressure then shifts the
     // halves by one phase: while one half runs its forward pass (which produces no weight-gradient work), the other
@@ -346,9 +342,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       wgrad_layer<3>(a3, wg, it, half, chains, sm, bars, sc0, sc1, lane);
       wgrad_layer<2>(a2, wg, it, half, chains, sm, bars, sc0, sc1, lane);
       wgrad_layer<1>(a1, wg, it, half, chains, sm, bars, sc0, sc1, lane);
-      wgrad_layer<0>(a0, wg, it, half, chains, sm, bars, sc0, sc1, lane);
     }
-    wgrad_flush<0>(a0, wg, outp, lane);
     wgrad_flush<1>(a1, wg, outp, lane);
     wgrad_flush<2>(a2, wg, outp, lane);
     wgrad_flush<3>(a3, wg, outp, lane);
@@ -365,8 +359,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     const double kap = p.ide ? exp(Wsm[P_NET + 1]) : p.nu;
     double loss_d = 0.0, loss_f = 0.0, gl1 = 0.0, gl2 = 0.0;
     double g8[5], gb8 = 0.0;                // output-layer weight gradient: per-lane partials over this lane's points
+    double g0x[5], g0t[5], g0b[5];          // layer-0 weight gradient (rows x^, t^ of W_0 and b_0): likewise
 #pragma unroll
-    for (int j = 0; j < 5; j++) g8[j] = 0.0;
+    for (int j = 0; j < 5; j++) g8[j] = g0x[j] = g0t[j] = g0b[j] = 0.0;
     const int pg = prow(g);
     int u5[5];                              // the five hidden units of this lane
 #pragma unroll
@@ -399,8 +394,6 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       const double ut = has_d ? __ldg(p.utgt + (pt - p.d0)) : 0.0;
       const double xh = 2.0 * (xr - p.lb0) / p.dx0 - 1.0;   // utils/neuralnetwork.py:29-30
       const double th = 2.0 * (tr - p.lb1) / p.dx1 - 1.0;
-      double* XT = sm + SM_XT + (c * 2 + (it & 1)) * 16;
-      if (q == 0) { XT[pg * 2 + 0] = xh; XT[pg * 2 + 1] = th; }
 
       double V[4][5];
       // ---------------- layer 0 (2 -> 20): direct
@@ -415,7 +408,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       act_forward5(V);
       // the a-only stash of layer 0 is still the A operand of the previous tile's layer-1 task (J = 6): wait until it has
       // been consumed; consumers retire tasks in order
-      if (it > 0) wait_consumed(bars, c, 8 * (it - 1) + 6);
+      if (it > 0) wait_consumed(bars, c, 7 * (it - 1) + 6);
       {
         double* r0 = stash + pg * W;
         *reinterpret_cast<double2*>(r0 + 2 * q) = make_double2(V[0][0], V[0][1]);
@@ -489,7 +482,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       // ---------------- backward: layers 7..1 (task J = 7-l, ring slot J % RING)
 #pragma unroll 1
       for (int l = NHID - 1; l >= 1; l--) {
-        const int T = 8 * it + (7 - l), slot = T % RING;
+        const int T = 7 * it + (7 - l), slot = T % RING;
         if (l < NHID - 1) load5(V, stash + STASH0 + (l - 1) * STASHL, lane);        // outputs of layer l (l = 7: registers)
         act_backward5(A, V);                                                         // A := Z-bar
         if (T >= RING) wait_consumed(bars, c, T - RING);                             // the slot's previous task is done
@@ -508,7 +501,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           c_to_v5(A, An, lane);
         }
       }
-      // ---------------- backward: layer 0 (task 7): outputs rebuilt from the a-only stash
+      // ---------------- backward: layer 0: outputs rebuilt from the a-only stash; its weight gradient is 3 rows (x^, t^, bias)
+      // -- 25 FMAs per lane here instead of 24 DMMAs in a weight-gradient warp
       {
         const double* r0 = stash + pg * W;
         const double2 c0 = *reinterpret_cast<const double2*>(r0 + 2 * q);
@@ -524,22 +518,26 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           V[3][j] = -2.0 * a * s * zx * zx;
         }
         act_backward5(A, V);
-        const int T = 8 * it + 7, slot = T % RING;
-        if (T >= RING) wait_consumed(bars, c, T - RING);
-        stage5(sm + SM_RING + (c * RING + slot) * 640, A, lane);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full(bars, c, slot));
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          g0x[j] = fma(xh, A[0][j], fma(sc0, A[1][j], g0x[j]));   // inputs: (x^, t^) on the value stream, (sc0, 0) on the x
+          g0t[j] = fma(th, A[0][j], fma(sc1, A[2][j], g0t[j]));   // stream, (0, sc1) on the t stream, 0 on the xx stream
+          g0b[j] += A[0][j];
+        }
       }
     }
 
     // ---------------- chain-warp partials: losses, identification gradients, output-layer gradient
-    double* red = sm + SM_RED + c * 64;
+    double* red = sm + SM_RED + c * RED_PER_WARP;
     loss_d = warp_sum(loss_d); loss_f = warp_sum(loss_f); gl1 = warp_sum(gl1); gl2 = warp_sum(gl2); gb8 = warp_sum(gb8);
 #pragma unroll
     for (int j = 0; j < 5; j++) {
-      double v = g8[j];
+      double v = g8[j], vx = g0x[j], vt = g0t[j], vb = g0b[j];
       v += shfl_xor_d(v, 4); v += shfl_xor_d(v, 8); v += shfl_xor_d(v, 16);   // sum over the 8 points (g)
-      if (g == 0) red[8 + u5[j]] = v;
+      vx += shfl_xor_d(vx, 4); vx += shfl_xor_d(vx, 8); vx += shfl_xor_d(vx, 16);
+      vt += shfl_xor_d(vt, 4); vt += shfl_xor_d(vt, 8); vt += shfl_xor_d(vt, 16);
+      vb += shfl_xor_d(vb, 4); vb += shfl_xor_d(vb, 8); vb += shfl_xor_d(vb, 16);
+      if (g == 0) { red[8 + u5[j]] = v; red[32 + u5[j]] = vx; red[32 + W + u5[j]] = vt; red[32 + 2 * W + u5[j]] = vb; }
     }
     if (lane == 0) { red[0] = loss_d; red[1] = loss_f; red[2] = gl1; red[3] = gl2; red[4] = gb8; }
   }
@@ -547,13 +545,16 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   __syncthreads();
   {
     const double* red = sm + SM_RED;
+    constexpr int R = RED_PER_WARP;
     const int t = threadIdx.x;
-    if (t < W) outp[woff(8) + t] = red[8 + t] + red[64 + 8 + t] + red[128 + 8 + t] + red[192 + 8 + t];
-    if (t == 32) outp[boff(8)] = red[4] + red[64 + 4] + red[128 + 4] + red[192 + 4];
-    if (t == 33) outp[IDX_LD] = red[0] + red[64] + red[128] + red[192];
-    if (t == 34) outp[IDX_LF] = red[1] + red[65] + red[129] + red[193];
-    if (t == 35) outp[IDX_DL1] = red[2] + red[66] + red[130] + red[194];
-    if (t == 36) outp[IDX_DL2] = red[3] + red[67] + red[131] + red[195];
+    auto sum4 = [&](int i) { return red[i] + red[R + i] + red[2 * R + i] + red[3 * R + i]; };   // fixed order: chains 0..3
+    if (t < W) outp[woff(8) + t] = sum4(8 + t);
+    if (t >= 64 && t < 64 + 3 * W) outp[woff(0) + (t - 64)] = sum4(32 + (t - 64));   // W_0 (2 x 20, row-major) then b_0: flat 0..59
+    if (t == 32) outp[boff(8)] = sum4(4);
+    if (t == 33) outp[IDX_LD] = sum4(0);
+    if (t == 34) outp[IDX_LF] = sum4(1);
+    if (t == 35) outp[IDX_DL1] = sum4(2);
+    if (t == 36) outp[IDX_DL2] = sum4(3);
     if (t == 37) outp[3023] = 0.0;
   }
 }

@@ -22,6 +22,12 @@ struct LbfgsState {
   double h_diag, t, f, f_old;
   double ro[128];   // 1 / (y_i . s_i) per ring slot, cached when the pair is pushed (same dot product the reference
                     // recomputes every iteration, utils/custom_lbfgs.py:121-123)
+  // ---- Gram-matrix formulation (lbfgs_dots / lbfgs_solve / lbfgs_apply): physical history slots 0..n_corr (one spare)
+  int free_slot;    // physical slot that receives the candidate pair of the next iteration
+  int apply;        // what lbfgs_apply has to do: 0 nothing, 1 move the model weights, 2 write x_final (last iteration)
+  int slot[129];    // physical slot of the pair of age i (0 = oldest), i < k
+  double c_g, step; // direction d = c_g g + sum_m ca[m] s_m + cb[m] y_m  (m = age), step length t
+  double ca[128], cb[128];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -462,6 +468,248 @@ lbfgs_iterate(LbfgsState* __restrict__ st, double* __restrict__ w, const double*
     if (last) st->status = 1;                                            // :192
     else st->pending = 1;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// L-BFGS, Gram-matrix formulation: the same iteration as lbfgs_iterate (utils/custom_lbfgs.py:81-221, same stop tests, same
+// quirks), re-associated so that nothing sequential touches a P-vector.  lbfgs_iterate is one CTA whose 2 x n_corr dependent
+// dot products each stream an (s, y) pair through ONE SM (4.8 MB of history per iteration at n_corr = 50, P = 3021:
+// ~55 us, SM<->L2 bandwidth bound).  Here
+//   lbfgs_dots   (P/256 CTAs): y = g - g_old, s = d t into the spare history slot; per-CTA partial sums of ALL dot products
+//                the iteration needs -- s_m.y, y_m.y, s_m.g, y_m.g for every stored pair m, y.s, y.y, s.g, y.g, g.g, |g|_1,
+//                |s|_1 -- the history is read once, by all SMs in parallel;
+//   lbfgs_solve  (1 CTA): fixed-order sum of the partials, the stop tests, the curvature test and history bookkeeping, the
+//                Gram matrices SY[a][b] = s_a.y_b, YY[a][b] = y_a.y_b (one new row/column per accepted pair), and the two-loop
+//                recursion in COEFFICIENT space:  al_i = ro_i (-s_i.g - sum_{m>i} al_m SY[i][m]);
+//                y_i.q = -y_i.g - sum_m al_m YY[i][m];  be_i = ro_i (H y_i.q + sum_{m<i} (al_m - be_m) SY[m][i]);
+//                d = -H g - H sum al_m y_m + sum (al_m - be_m) s_m;  g.d from the same numbers;
+//   lbfgs_apply  (P/256 CTAs): d as that linear combination (history read once more, in parallel), g_old = g, x += t d.
+// Mathematically identical to the reference's loop; rounding differs at the 1e-16 level (different association), which a
+// fixed-step L-BFGS amplifies about tenfold per ten iterations -- as between any two fp64 implementations.
+// ------------------------------------------------------------------------------------------------
+constexpr int LB_CHUNK = 256;       // entries per CTA of lbfgs_dots / lbfgs_apply
+constexpr int LB_NSCAL = 7;         // scalar dots: |g|_1, g.g, |s|_1, y.s, y.y, s.g, y.g;  then 4 per stored pair
+
+__global__ void __launch_bounds__(LB_CHUNK)
+lbfgs_dots(const LbfgsState* __restrict__ st, const double* __restrict__ R, int P, const double* __restrict__ g_old,
+           const double* __restrict__ d, double* __restrict__ S, double* __restrict__ Y, double* __restrict__ part, int part_stride) {
+  __shared__ double sg[LB_CHUNK], sy[LB_CHUNK], ss[LB_CHUNK];
+  if (st->status != 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = blockIdx.x * LB_CHUNK + tid;
+  const bool have_step = st->n_iter > 0;             // false: this is the initial evaluation, there is no pair to form
+  const int k = st->k;
+  const double gi = i < P ? R[i] : 0.0;
+  double yi = 0.0, si = 0.0;
+  if (have_step && i < P) {
+    yi = gi - g_old[i];                               // custom_lbfgs.py:98
+    si = d[i] * st->t;                                // :99
+    const size_t o = (size_t)st->free_slot * P + i;
+    S[o] = si; Y[o] = yi;
+  }
+  sg[tid] = gi; sy[tid] = yi; ss[tid] = si;
+  __syncthreads();
+  double* out = part + (size_t)blockIdx.x * part_stride;
+  const int ndots = LB_NSCAL + (have_step ? 4 * k : 0);
+  // dot j: warps take j = warp, warp + 8, ...; lanes stride the chunk; fixed shuffle tree -> deterministic
+  for (int j = warp; j < ndots; j += LB_CHUNK / 32) {
+    double acc = 0.0;
+    if (j < LB_NSCAL) {
+#pragma unroll
+      for (int e = 0; e < LB_CHUNK / 32; e++) {
+        const int t = lane + 32 * e;
+        const double gg = sg[t], yy = sy[t], sv = ss[t];
+        acc += j == 0 ? fabs(gg) : j == 1 ? gg * gg : j == 2 ? fabs(sv) : j == 3 ? yy * sv : j == 4 ? yy * yy : j == 5 ? sv * gg : yy * gg;
+      }
+    } else {
+      const int m = (j - LB_NSCAL) >> 2, which = (j - LB_NSCAL) & 3;
+      const double* hist = ((which & 1) ? Y : S) + (size_t)st->slot[m] * P + (size_t)blockIdx.x * LB_CHUNK;
+      const double* other = which < 2 ? sy : sg;      // 0: s_m.y  1: y_m.y  2: s_m.g  3: y_m.g
+#pragma unroll
+      for (int e = 0; e < LB_CHUNK / 32; e++) {
+        const int t = lane + 32 * e;
+        acc = fma(blockIdx.x * LB_CHUNK + t < P ? hist[t] : 0.0, other[t], acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[j] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+lbfgs_solve(LbfgsState* __restrict__ st, const double* __restrict__ R, int P, const double* __restrict__ part, int n_blocks,
+            int part_stride, double* __restrict__ SY, double* __restrict__ YY, double* __restrict__ f_hist, int* __restrict__ logged) {
+  extern __shared__ double sy_s[];          // SY of the live pairs in AGE order, [k][k]: the recurrences below walk it serially
+  __shared__ double dots[LB_NSCAL + 4 * 128];
+  __shared__ double al[128], dl[128], sgv[128], ygv[128], yq[128], rov[128];
+  __shared__ int pslot[128];
+  if (st->status != 0) return;
+  const int tid = threadIdx.x;
+  const bool have_step = st->n_iter > 0;
+  int k = st->k;
+  const int ndots = LB_NSCAL + (have_step ? 4 * k : 0);
+  for (int j = tid; j < ndots; j += blockDim.x) {
+    double sacc = 0.0;
+    for (int b = 0; b < n_blocks; b++) sacc += part[(size_t)b * part_stride + j];
+    dots[j] = sacc;
+  }
+  for (int m = tid; m < k; m += blockDim.x) pslot[m] = st->slot[m];
+  __syncthreads();
+  const double f_new = R[P] + R[P + 1] + R[P + 2];
+  const double a1 = dots[0];
+  const int NS = st->n_corr + 1;
+  // ---- (a) bookkeeping + stop tests of the evaluation that has just completed (custom_lbfgs.py:65-76, 186-218)
+  if (st->pending) {
+    const int n_iter = st->n_iter, n_eval = st->n_eval + 1;
+    int status = 0;
+    if (n_iter == 0) {
+      if (a1 <= st->tol_fun) status = 7;
+    } else {
+      if ((double)n_eval >= st->max_eval) status = 2;                    // :195
+      else if (a1 <= st->tol_fun) status = 3;                            // :200-204
+      else if (dots[2] <= st->tol_x) status = 4;                         // :206-210
+      else if (fabs(f_new - st->f_old) < st->tol_x) status = 5;          // :212-215
+    }
+    __syncthreads();
+    if (tid == 0) {
+      st->n_eval = n_eval; st->f = f_new; st->pending = 0;
+      f_hist[n_eval - 1] = f_new;
+      if (n_iter > 0 && status == 0) logged[n_iter] = 1;                 // :217-218 (log after the stop tests)
+      st->status = status;
+      if (status != 0) st->apply = 0;
+    }
+    if (status != 0) return;
+  }
+  // ---- (b) history update and direction coefficients
+  const int n_iter = st->n_iter + 1;
+  const int n_corr = st->n_corr;
+  double h_diag = st->h_diag;
+  double gtd;
+  if (n_iter == 1) {                                                     // :91-95  d = -g
+    gtd = -dots[1];
+    if (tid == 0) { st->c_g = -1.0; }
+  } else {
+    const double ys = dots[3];
+    const int p_new = st->free_slot;
+    int shift = 0;                           // ages move down by one when the oldest pair is dropped
+    int k_new = k, free_next = p_new;
+    const bool accept = ys > 1e-10;                                      // :102-114
+    if (accept) {
+      if (k == n_corr) { shift = 1; free_next = pslot[0]; k_new = k; }
+      else { k_new = k + 1; free_next = k_new <= n_corr ? k_new : n_corr; }
+      h_diag = ys / dots[4];
+    }
+    __syncthreads();
+    // Gram entries of the new pair against the stored ones (read at their OLD ages), then the age tables in their NEW order
+    if (accept) {
+      for (int m = tid; m < k; m += blockDim.x) {
+        const int pm = pslot[m];
+        SY[(size_t)pm * NS + p_new] = dots[LB_NSCAL + 4 * m + 0];        // s_m . y_new
+        YY[(size_t)pm * NS + p_new] = dots[LB_NSCAL + 4 * m + 1];        // y_m . y_new (symmetric)
+        YY[(size_t)p_new * NS + pm] = dots[LB_NSCAL + 4 * m + 1];
+      }
+      if (tid == 0) { SY[(size_t)p_new * NS + p_new] = ys; YY[(size_t)p_new * NS + p_new] = dots[4]; }
+    }
+    for (int m = tid; m < k; m += blockDim.x) {
+      if (m >= shift) { sgv[m - shift] = dots[LB_NSCAL + 4 * m + 2]; ygv[m - shift] = dots[LB_NSCAL + 4 * m + 3]; }
+    }
+    __syncthreads();
+    int my_slot = -1;
+    if (tid < k_new) {
+      if (accept && tid == k_new - 1) { my_slot = p_new; sgv[tid] = dots[5]; ygv[tid] = dots[6]; }
+      else my_slot = pslot[tid + shift];
+    }
+    __syncthreads();
+    if (tid < k_new) pslot[tid] = my_slot;
+    __threadfence_block();
+    __syncthreads();
+    k = k_new;
+    // stage SY[age a][age b] (only a <= b is ever used: s of the older pair against y of the newer one) -- all loads in flight
+    // together instead of one dependent global load per step of the serial recurrences
+    for (int e = tid; e < k * k; e += blockDim.x) {
+      const int a = e / k, b = e - a * k;
+      sy_s[e] = a <= b ? SY[(size_t)pslot[a] * NS + pslot[b]] : 0.0;
+    }
+    __syncthreads();
+    if (tid < k) rov[tid] = 1.0 / sy_s[tid * k + tid];                        // ro_i = 1 / (y_i . s_i)   (:121-123)
+    __syncthreads();
+    // first loop (:131-133), newest to oldest.  Thread m accumulates  -s_m.g - sum_{j>m} al_j SY[m][j]  as the al_j appear.
+    double accm = tid < k ? -sgv[tid] : 0.0;
+    for (int j = k - 1; j >= 0; j--) {
+      if (tid == j) al[j] = accm * rov[j];
+      __syncthreads();
+      if (tid < j) accm = fma(-al[j], sy_s[tid * k + j], accm);
+    }
+    // y_i . q  with q = -g - sum_m al_m y_m
+    if (tid < k) {
+      double v = -ygv[tid];
+      const double* yrow = YY + (size_t)pslot[tid] * NS;
+#pragma unroll 8
+      for (int m = 0; m < k; m++) v = fma(-al[m], yrow[pslot[m]], v);      // independent loads, in flight together
+      yq[tid] = v;
+    }
+    __syncthreads();
+    // second loop (:137-139), oldest to newest.  Thread i accumulates  H y_i.q + sum_{m<i} (al_m - be_m) SY[m][i].
+    double acci = tid < k ? h_diag * yq[tid] : 0.0;
+    for (int m = 0; m < k; m++) {
+      if (tid == m) dl[m] = al[m] - acci * rov[m];                       // al_m - be_m
+      __syncthreads();
+      if (tid > m && tid < k) acci = fma(dl[m], sy_s[m * k + tid], acci);
+    }
+    // g . d = -H g.g - H sum al_m y_m.g + sum (al_m - be_m) s_m.g       (:151)
+    double gsum = 0.0;
+    if (tid == 0) {
+      gsum = -h_diag * dots[1];
+      for (int m = 0; m < k; m++) gsum = fma(-h_diag * al[m], ygv[m], gsum);
+      for (int m = 0; m < k; m++) gsum = fma(dl[m], sgv[m], gsum);
+      dots[0] = gsum;                      // broadcast through shared memory (a1 was copied out above)
+    }
+    __syncthreads();
+    gtd = dots[0];
+    if (tid < k) { st->ca[tid] = dl[tid]; st->cb[tid] = -h_diag * al[tid]; st->slot[tid] = pslot[tid]; }
+    if (tid == 0) { st->c_g = -h_diag; st->k = k; st->h_diag = h_diag; st->free_slot = free_next; }
+  }
+  if (n_iter == 1 && tid == 0) { st->k = 0; st->free_slot = 0; }
+  // ---- (c) step (:144-182)
+  __syncthreads();
+  if (tid == 0) {
+    const double f_cur = st->f;
+    if (gtd > -st->tol_x) {                                              // :154-156
+      st->n_iter = n_iter; st->f_old = f_cur; st->status = 6; st->apply = 0;
+    } else {
+      const double t = (n_iter == 1) ? fmin(1.0, 1.0 / a1) : st->lr;     // :159-163
+      const bool last = (n_iter == st->max_iter);
+      st->step = t; st->t = t; st->n_iter = n_iter; st->f_old = f_cur;
+      st->apply = last ? 2 : 1;
+      if (last) st->status = 1;                                          // :192
+      else st->pending = 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LB_CHUNK)
+lbfgs_apply(LbfgsState* __restrict__ st, double* __restrict__ w, const double* __restrict__ R, int P, double* __restrict__ g_old,
+            double* __restrict__ d, const double* __restrict__ S, const double* __restrict__ Y, double* __restrict__ x_final) {
+  __shared__ double ca[128], cb[128];
+  __shared__ int ps[128];
+  const int apply = st->apply;
+  if (apply == 0) return;                  // a stop test fired (or the optimiser was already stopped): nothing moves
+  const int k = st->k;
+  for (int m = threadIdx.x; m < k; m += blockDim.x) { ca[m] = st->ca[m]; cb[m] = st->cb[m]; ps[m] = st->slot[m]; }
+  __syncthreads();
+  const int i = blockIdx.x * LB_CHUNK + threadIdx.x;
+  if (i >= P) return;
+  const double gi = R[i];
+  double dv = st->c_g * gi;
+  for (int m = 0; m < k; m++) {
+    const size_t o = (size_t)ps[m] * P + i;
+    dv = fma(ca[m], S[o], dv);
+    dv = fma(cb[m], Y[o], dv);
+  }
+  g_old[i] = gi; d[i] = dv;                // :144, the direction of this step (s of the next iteration = d t)
+  const double xn = fma(st->step, dv, w[i]);                             // :174
+  if (apply == 2) x_final[i] = xn;         // no evaluation follows (:176-182): the model keeps the previous weights
+  else w[i] = xn;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -63,6 +63,9 @@ constexpr int NCCL_SUM = 0;       // ncclSum
 
 constexpr int LOSS_RING = 4096;
 
+// buffers of the Gram-matrix L-BFGS formulation (optim_kernels.cuh: lbfgs_dots / lbfgs_solve / lbfgs_apply)
+struct LbfgsGram { double *SY = nullptr, *YY = nullptr, *part = nullptr; int n_corr_cap = 0, n_blocks = 0, stride = 0; };
+
 }  // namespace
 
 struct pinn_handle {
@@ -123,6 +126,7 @@ struct pinn_handle {
   double *d_gold = nullptr, *d_d = nullptr, *d_S = nullptr, *d_Y = nullptr, *d_xfinal = nullptr, *d_fhist = nullptr;
   int* d_logged = nullptr;
   int lb_corr_cap = 0, lb_iter_cap = 0;
+  LbfgsGram lb_gram;
   std::vector<double> lb_fhist;             // f of every evaluation of the last pinn_lbfgs run (custom_lbfgs.py f_hist)
 
   // scratch for predict / derivatives
@@ -156,6 +160,60 @@ int nls_upload_points(pinn_t* h);
 int nls_launch_eval(pinn_t* h, const int* run_flag);
 int generic_launch_eval(pinn_t* h, const int* run_flag);
 int disc_upload_points(pinn_t* h);
+
+// One L-BFGS iteration on the device (stop tests of the pending evaluation, history update, direction, step).
+// Default: the Gram-matrix formulation (lbfgs_dots -> lbfgs_solve -> lbfgs_apply: every SM reads its slice of the history).
+// PINN_LBFGS=serial selects the single-CTA kernel that follows the reference's loop literally (cross-check).
+bool lbfgs_serial() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PINN_LBFGS"); v = (e && !strcmp(e, "serial")) ? 1 : 0; }
+  return v == 1;
+}
+int lbfgs_gram_ensure(LbfgsGram* gm, int n_corr, int P) {
+  const int nb = (P + pinn::LB_CHUNK - 1) / pinn::LB_CHUNK;
+  if (n_corr <= gm->n_corr_cap && nb <= gm->n_blocks) return 0;
+  if (gm->SY) cudaFree(gm->SY);
+  if (gm->YY) cudaFree(gm->YY);
+  if (gm->part) cudaFree(gm->part);
+  gm->SY = gm->YY = gm->part = nullptr;
+  const size_t NS = (size_t)n_corr + 1;
+  gm->stride = pinn::LB_NSCAL + 4 * n_corr + 1;
+  if (cudaMalloc((void**)&gm->SY, NS * NS * 8) != cudaSuccess || cudaMalloc((void**)&gm->YY, NS * NS * 8) != cudaSuccess ||
+      cudaMalloc((void**)&gm->part, (size_t)nb * gm->stride * 8) != cudaSuccess)
+    return fail("cudaMalloc failed (L-BFGS Gram buffers)");
+  gm->n_corr_cap = n_corr; gm->n_blocks = nb;
+  if ((size_t)n_corr * n_corr * 8 > 48 * 1024 &&
+      cudaFuncSetAttribute(pinn::lbfgs_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, n_corr * n_corr * 8) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(lbfgs_solve) failed");
+  return 0;
+}
+void lbfgs_gram_free(LbfgsGram* gm) {
+  if (gm->SY) cudaFree(gm->SY);
+  if (gm->YY) cudaFree(gm->YY);
+  if (gm->part) cudaFree(gm->part);
+  *gm = LbfgsGram{};
+}
+int lbfgs_launch_iteration(cudaStream_t stream, pinn::LbfgsState* st, double* w, const double* R, int P, double* gold, double* d,
+                           double* S, double* Y, double* xfinal, double* fhist, int* logged, const LbfgsGram& gm, long long* launches) {
+  if (lbfgs_serial()) {
+#define LB_LAUNCH(E, NT) pinn::lbfgs_iterate<E, NT><<<1, NT, 0, stream>>>(st, w, R, P, gold, d, S, Y, xfinal, fhist, logged)
+    if (P <= 12 * 256) LB_LAUNCH(12, 256);        // Burgers-size vectors: 8 warps, 12 entries per thread
+    else if (P <= 8 * 1024) LB_LAUNCH(8, 1024);
+    else LB_LAUNCH(32, 1024);
+#undef LB_LAUNCH
+    if (cudaGetLastError() != cudaSuccess) return fail("lbfgs_iterate launch failed");
+    if (launches) *launches += 1;
+    return 0;
+  }
+  const int nb = (P + pinn::LB_CHUNK - 1) / pinn::LB_CHUNK;
+  pinn::lbfgs_dots<<<nb, pinn::LB_CHUNK, 0, stream>>>(st, R, P, gold, d, S, Y, gm.part, gm.stride);
+  pinn::lbfgs_solve<<<1, 128, (size_t)gm.n_corr_cap * gm.n_corr_cap * 8, stream>>>(st, R, P, gm.part, nb, gm.stride, gm.SY, gm.YY, fhist,
+                                                                                   logged);
+  pinn::lbfgs_apply<<<nb, pinn::LB_CHUNK, 0, stream>>>(st, w, R, P, gold, d, S, Y, xfinal);
+  if (cudaGetLastError() != cudaSuccess) return fail("L-BFGS iteration launch failed");
+  if (launches) *launches += 3;
+  return 0;
+}
 
 // after a stream synchronisation: has the fused P2P exchange reported a peer that never published?
 int check_p2p(pinn_t* h) {
@@ -358,7 +416,9 @@ int generic_launch_eval(pinn_t* h, const int* run_flag) {
   if (n_total <= 0) return fail("no points set (pinn_set_collocation / pinn_set_data)");
   const int grid = h->n_cta;
   const long long per = (n_total + grid - 1) / grid;
-  const long long pts = (per + 15) / 16 * 16;
+  // points per CTA: a multiple of 16 for large sets; small sets (the discrete-time models have ~250 points) are spread over as
+  // many CTAs as possible -- an even count, because NLS boundary pairs (lb_k, ub_k) are adjacent and must not straddle a CTA
+  const long long pts = per >= 16 ? (per + 15) / 16 * 16 : (per + 1) / 2 * 2;
   pinn::NetDesc nd = net_desc(h);
   int maxw = 0; long long hsum = 0;
   for (int l = 0; l < nd.n_layers - 1; l++) { hsum += 4 * pts * nd.dims[l + 1]; if (nd.dims[l + 1] > maxw) maxw = nd.dims[l + 1]; }
@@ -681,6 +741,7 @@ int pinn_destroy(pinn_t* h) {
   if (h->d_step) cudaFree(h->d_step);
   if (h->d_lb) cudaFree(h->d_lb);
   if (h->d_logged) cudaFree(h->d_logged);
+  lbfgs_gram_free(&h->lb_gram);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   if (h->d_flush) cudaFree(h->d_flush);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -969,7 +1030,7 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
   if (tol_x == 0.0) tol_x = 1e-19;                                  // :51
   if (sync_every < 1) sync_every = 1;
   const int P = h->P;
-  if (P > 32 * 1024) return fail("pinn_lbfgs: parameter vector too large for the single-CTA L-BFGS kernel");
+  if (lbfgs_serial() && P > 32 * 1024) return fail("pinn_lbfgs: parameter vector too large for the single-CTA L-BFGS kernel");
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->d_gold) {
     CUDA_TRY(cudaMalloc((void**)&h->d_gold, h->w_cap * 8));
@@ -980,10 +1041,11 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
     if (h->d_S) cudaFree(h->d_S);
     if (h->d_Y) cudaFree(h->d_Y);
     h->d_S = h->d_Y = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&h->d_S, (size_t)n_correction * P * 8));
-    CUDA_TRY(cudaMalloc((void**)&h->d_Y, (size_t)n_correction * P * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_S, (size_t)(n_correction + 1) * P * 8));     // + the spare slot of the Gram formulation
+    CUDA_TRY(cudaMalloc((void**)&h->d_Y, (size_t)(n_correction + 1) * P * 8));
     h->lb_corr_cap = n_correction;
   }
+  if (lbfgs_gram_ensure(&h->lb_gram, n_correction, P)) return -1;
   if (max_iter + 2 > h->lb_iter_cap) {
     if (h->d_fhist) cudaFree(h->d_fhist);
     if (h->d_logged) cudaFree(h->d_logged);
@@ -1009,16 +1071,8 @@ int pinn_lbfgs(pinn_t* h, int max_iter, double learning_rate, int n_correction, 
   std::vector<int> lg(max_iter + 2);
   int reported = 0;
   auto iterate = [&]() -> int {
-#define LB_LAUNCH(E, NT)                                                                                       \
-  pinn::lbfgs_iterate<E, NT><<<1, NT, 0, h->stream>>>(h->d_lb, h->d_w, h->d_R, P, h->d_gold, h->d_d, h->d_S, h->d_Y, \
-                                                      h->d_xfinal, h->d_fhist, h->d_logged)
-    if (P <= 12 * 256) LB_LAUNCH(12, 256);        // Burgers-size vectors: 8 warps, 12 entries per thread
-    else if (P <= 8 * 1024) LB_LAUNCH(8, 1024);
-    else LB_LAUNCH(32, 1024);
-#undef LB_LAUNCH
-    if (cudaGetLastError() != cudaSuccess) return fail("lbfgs_iterate launch failed");
-    h->launches++;
-    return 0;
+    return lbfgs_launch_iteration(h->stream, h->d_lb, h->d_w, h->d_R, P, h->d_gold, h->d_d, h->d_S, h->d_Y, h->d_xfinal, h->d_fhist,
+                                  h->d_logged, h->lb_gram, &h->launches);
   };
   while (true) {
     for (int b = 0; b < sync_every; b++) {
@@ -1239,6 +1293,135 @@ int pinn_kernel_info(pinn_t* h, char* buf, int buflen) {
   }
   snprintf(buf, buflen, "{\"grid\": %d, \"block\": %d, \"dyn_smem\": %d, \"regs\": %d, \"local_bytes\": %zu, \"sms\": %d}",
            h->n_cta, threads, smem, fa.numRegs, fa.localSizeBytes, h->n_sm);
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// Stand-alone device-resident L-BFGS for ANY objective (utils/custom_lbfgs.py:39 takes an arbitrary `opfunc`): the caller
+// evaluates f and g wherever it likes and feeds them in; the vectors, the (s, y) history ring and the two-loop recursion
+// stay on the device and run through the SAME kernel (lbfgs_iterate) the PINN handles use.
+// -----------------------------------------------------------------------------------------------------------------
+struct pinn_lbfgs_handle {
+  int device = 0, n = 0, max_iter = 0, n_corr = 0;
+  cudaStream_t stream = nullptr;
+  pinn::LbfgsState* d_st = nullptr;
+  double *d_x = nullptr, *d_R = nullptr, *d_gold = nullptr, *d_d = nullptr, *d_S = nullptr, *d_Y = nullptr, *d_xfinal = nullptr,
+         *d_fhist = nullptr;
+  int* d_logged = nullptr;
+  LbfgsGram gram;
+  int reported = 0;
+};
+
+int pinn_lbfgs_destroy(pinn_lbfgs_t* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  double* bufs[] = {s->d_x, s->d_R, s->d_gold, s->d_d, s->d_S, s->d_Y, s->d_xfinal, s->d_fhist};
+  for (double* b : bufs) if (b) cudaFree(b);
+  if (s->d_logged) cudaFree(s->d_logged);
+  lbfgs_gram_free(&s->gram);
+  if (s->d_st) cudaFree(s->d_st);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return 0;
+}
+
+int pinn_lbfgs_create(pinn_lbfgs_t** out, int device, int64_t n, const double* x0, int max_iter, double learning_rate,
+                      int n_correction, double tol_fun, double tol_x, double max_eval) {
+  if (!out || !x0 || n < 1) return fail("pinn_lbfgs_create: bad arguments");
+  if (max_iter < 1) return fail("pinn_lbfgs_create: max_iter must be >= 1 (lbfgs() returns before anything for maxIter == 0)");
+  if (lbfgs_serial() && n > 32 * 1024) return fail("pinn_lbfgs_create: vector too large for the single-CTA L-BFGS kernel (32768 entries)");
+  if (n > (1 << 30)) return fail("pinn_lbfgs_create: vector too large");
+  if (n_correction <= 0) n_correction = 100;                        // custom_lbfgs.py:52
+  if (n_correction > 128) return fail("pinn_lbfgs_create: n_correction > 128 not supported");
+  if (learning_rate == 0.0) learning_rate = 1.0;                    // :55
+  if (tol_fun == 0.0) tol_fun = 1e-5;                               // :50
+  if (tol_x == 0.0) tol_x = 1e-19;                                  // :51
+  if (max_eval == 0.0) max_eval = max_iter * 1.25;                  // :49
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("pinn_lbfgs_create: no CUDA device -- this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail("pinn_lbfgs_create: bad device index");
+  pinn_lbfgs_t* s = new pinn_lbfgs_t();
+  s->device = device; s->n = (int)n; s->max_iter = max_iter; s->n_corr = n_correction;
+#define LB_TRY(expr)                                                                                     \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) { fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); pinn_lbfgs_destroy(s); return -1; } \
+  } while (0)
+  LB_TRY(cudaSetDevice(device));
+  LB_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  const size_t nb = ((size_t)n + 8) * 8;
+  LB_TRY(cudaMalloc((void**)&s->d_x, nb));
+  LB_TRY(cudaMalloc((void**)&s->d_R, nb));
+  LB_TRY(cudaMalloc((void**)&s->d_gold, nb));
+  LB_TRY(cudaMalloc((void**)&s->d_d, nb));
+  LB_TRY(cudaMalloc((void**)&s->d_xfinal, nb));
+  LB_TRY(cudaMalloc((void**)&s->d_S, (size_t)(n_correction + 1) * n * 8));
+  LB_TRY(cudaMalloc((void**)&s->d_Y, (size_t)(n_correction + 1) * n * 8));
+  if (lbfgs_gram_ensure(&s->gram, n_correction, (int)n)) { pinn_lbfgs_destroy(s); return -1; }
+  LB_TRY(cudaMalloc((void**)&s->d_fhist, (size_t)(max_iter + 2) * 8));
+  LB_TRY(cudaMalloc((void**)&s->d_logged, (size_t)(max_iter + 2) * 4));
+  LB_TRY(cudaMalloc((void**)&s->d_st, sizeof(pinn::LbfgsState)));
+  LB_TRY(cudaMemsetAsync(s->d_fhist, 0, (size_t)(max_iter + 2) * 8, s->stream));
+  LB_TRY(cudaMemsetAsync(s->d_logged, 0, (size_t)(max_iter + 2) * 4, s->stream));
+  LB_TRY(cudaMemsetAsync(s->d_R, 0, nb, s->stream));
+  LB_TRY(cudaMemcpyAsync(s->d_x, x0, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+  pinn::LbfgsState st{};
+  st.pending = 1; st.max_iter = max_iter; st.n_corr = n_correction; st.max_eval = max_eval;
+  st.lr = learning_rate; st.tol_fun = tol_fun; st.tol_x = tol_x; st.h_diag = 1.0;
+  LB_TRY(cudaMemcpyAsync(s->d_st, &st, sizeof(st), cudaMemcpyHostToDevice, s->stream));
+  LB_TRY(cudaStreamSynchronize(s->stream));
+#undef LB_TRY
+  *out = s;
+  return 0;
+}
+
+int pinn_lbfgs_feed(pinn_lbfgs_t* s, double f, const double* g, double* x_next, int* status_out, int* n_iter_out, int* n_eval_out,
+                    int* logged_iter_out, double* logged_f_out) {
+  if (!s || !g || !x_next || !status_out) return fail("pinn_lbfgs_feed: null argument");
+  CUDA_TRY(cudaSetDevice(s->device));
+  const int n = s->n;
+  const double tail[3] = {f, 0.0, 0.0};          // the kernel reads f as the sum of three loss parts behind the gradient
+  CUDA_TRY(cudaMemcpyAsync(s->d_R, g, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->d_R + n, tail, 24, cudaMemcpyHostToDevice, s->stream));
+  if (lbfgs_launch_iteration(s->stream, s->d_st, s->d_x, s->d_R, n, s->d_gold, s->d_d, s->d_S, s->d_Y, s->d_xfinal, s->d_fhist,
+                             s->d_logged, s->gram, nullptr)) return -1;
+  pinn::LbfgsState st{};
+  CUDA_TRY(cudaMemcpyAsync(&st, s->d_st, sizeof(st), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  *status_out = st.status;
+  if (n_iter_out) *n_iter_out = st.n_iter;
+  if (n_eval_out) *n_eval_out = st.n_eval;
+  // the iteration whose stop tests have just run (custom_lbfgs.py:217-218 logs it only if none of them fired)
+  const int tested = st.pending ? st.n_iter - 1 : st.n_iter;
+  int logged_it = -1;
+  double logged_f = 0.0;
+  // (at most one iteration is newly logged per evaluation; when the loop ends on max_iter, `tested` also covers the final,
+  // never-evaluated and never-logged iteration)
+  for (int it = s->reported + 1; it <= tested && it >= 1; it++) {
+    int flag = 0;
+    CUDA_TRY(cudaMemcpy(&flag, s->d_logged + it, 4, cudaMemcpyDeviceToHost));
+    if (flag) { logged_it = it; logged_f = f; }
+  }
+  if (tested > s->reported) s->reported = tested;
+  if (logged_iter_out) *logged_iter_out = logged_it;
+  if (logged_f_out) *logged_f_out = logged_f;
+  // where to evaluate next (status 0), or the vector lbfgs() returns: the last update when the loop ended on max_iter
+  const double* src = (st.status == PINN_LBFGS_MAX_ITER) ? s->d_xfinal : s->d_x;
+  CUDA_TRY(cudaMemcpy(x_next, src, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int pinn_lbfgs_f_hist(pinn_lbfgs_t* s, double* f_hist_out, int capacity, int* n_out) {
+  if (!s || !n_out) return fail("pinn_lbfgs_f_hist: null argument");
+  CUDA_TRY(cudaSetDevice(s->device));
+  pinn::LbfgsState st{};
+  CUDA_TRY(cudaMemcpy(&st, s->d_st, sizeof(st), cudaMemcpyDeviceToHost));
+  *n_out = st.n_eval;
+  if (f_hist_out) {
+    if (capacity < st.n_eval) return fail("pinn_lbfgs_f_hist: buffer too small");
+    if (st.n_eval) CUDA_TRY(cudaMemcpy(f_hist_out, s->d_fhist, (size_t)st.n_eval * 8, cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 

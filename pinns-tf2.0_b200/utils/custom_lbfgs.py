@@ -2,10 +2,11 @@
 two-loop kernel (pinn_lbfgs in include/pinn_b200.h).
 
 ``lbfgs(opfunc, x, config, state, do_verbose, log_fn)`` keeps the reference signature and return values
-(custom_lbfgs.py:39-44,76,236).  ``opfunc`` must be the closure returned by
-``NeuralNetwork.get_loss_and_flat_grad`` -- the whole iteration (history update, two-loop recursion, fixed step,
-stop tests) then runs on the GPU with one status read-back per ``sync_every`` iterations instead of the
-reference's >= 6 host syncs per iteration.  There is deliberately no host (CPU) implementation.
+(custom_lbfgs.py:39-44,76,236).  When ``opfunc`` is the closure returned by ``NeuralNetwork.get_loss_and_flat_grad`` the
+whole iteration (evaluation, history update, two-loop recursion, fixed step, stop tests) runs on the GPU with one status
+read-back per ``sync_every`` iterations instead of the reference's >= 6 host syncs per iteration.  Any OTHER closure is
+called once per iteration, as in the reference, while the optimiser state stays on the device (``_lbfgs_foreign``).
+There is deliberately no host (CPU) implementation of the optimiser arithmetic.
 """
 import time
 
@@ -56,6 +57,48 @@ class Struct(dummy):
         return self.__dict__.get(key, 0)
 
 
+def _lbfgs_foreign(opfunc, x, config, state, do_verbose, log_fn):
+    """Any closure x -> (f, g) (custom_lbfgs.py:39): the objective is evaluated by the caller's code, one call per iteration
+    exactly where the reference calls it (:65, :178), while the iterate, the (s, y) history and the two-loop recursion stay
+    on the device (pinn_lbfgs_create / pinn_lbfgs_feed -- the same kernel as the fused training path).  x is handed to opfunc
+    as a float64 array with .numpy(); f and g may be anything np.asarray() understands."""
+    global final_loss, times
+    import pinn_cabi
+    from neuralnetwork import _t
+    max_iter = int(config.maxIter)
+    if config.lineSearch:
+        raise NotImplementedError("lineSearch is dead code in the reference (custom_lbfgs.py:168-171) and is not provided")
+    x0 = np.asarray(x.numpy() if hasattr(x, "numpy") else x, dtype=np.float64).reshape(-1)
+    opt = pinn_cabi.Lbfgs(x0, max_iter, learning_rate=float(config.learningRate or 1), n_correction=int(config.nCorrection or 100),
+                          tol_fun=float(config.tolFun or 1e-5), tol_x=float(config.tolX or 1e-19), max_eval=float(config.maxEval or 0.0))
+    times = []
+    try:
+        xk = x0
+        while True:
+            f, g = opfunc(_t(xk))
+            f = float(np.asarray(f.numpy() if hasattr(f, "numpy") else f).reshape(-1)[0])
+            g = np.asarray(g.numpy() if hasattr(g, "numpy") else g, dtype=np.float64).reshape(-1)
+            xk, status, n_iter, n_eval, logged_it, logged_f = opt.feed(f, g)
+            if logged_it is not None:
+                if do_verbose:
+                    log_fn(logged_it, np.float64(logged_f), True)
+                    record_time()
+                    times.append(last_time())
+                if logged_it == max_iter - 1:
+                    final_loss = np.float64(logged_f)
+            if status != 0:
+                break
+        f_hist = opt.f_hist()
+    finally:
+        opt.close()
+    state.funcEval = state.funcEval + n_eval
+    state.nIter = state.nIter + n_iter
+    state.stop_reason = pinn_cabi.LBFGS_REASONS.get(status, "?")
+    if status == 7:             # initial optimality (custom_lbfgs.py:73-76)
+        return _t(xk), f_hist
+    return _t(xk), f_hist, n_eval
+
+
 def lbfgs(opfunc, x, config, state, do_verbose, log_fn):
     """Device-resident port of the reference control flow.  Returns None when maxIter == 0, ``(x, f_hist)`` when
     the initial point is already optimal, else ``(x, f_hist, currentFuncEval)``."""
@@ -64,8 +107,7 @@ def lbfgs(opfunc, x, config, state, do_verbose, log_fn):
         return
     net = getattr(opfunc, "_pinn_net", None)
     if net is None:
-        raise TypeError("lbfgs: opfunc must be the closure returned by NeuralNetwork.get_loss_and_flat_grad(); "
-                        "the optimiser is device-resident and has no host fallback for arbitrary Python closures")
+        return _lbfgs_foreign(opfunc, x, config, state, do_verbose, log_fn)
     max_iter = int(config.maxIter)
     tol_fun = config.tolFun or 1e-5
     tol_x = config.tolX or 1e-19

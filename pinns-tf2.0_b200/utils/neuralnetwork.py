@@ -255,6 +255,12 @@ class NeuralNetwork(object):
         return var
 
     def get_params(self, numpy=False):
+        """Base class: no PDE parameters (neuralnetwork.py:64-65); the identification models return (lambda_1, exp(lambda_2))."""
+        try:
+            if self._pde_id() in (pinn_cabi.BURGERS_IDE, pinn_cabi.BURGERS_IDE_DISC):
+                return _native_get_params(self, numpy)
+        except pinn_cabi.PinnError:
+            pass
         return []
 
     def get_weights(self, convert_to_tensor=True):
@@ -370,7 +376,7 @@ def _native_U_1_model(self, x, customDummy=None):
 
 
 def _native_autograd(self, *args):
-    raise pinn_cabi.PinnError("autograd (the dummy-gradient tape trick) is replaced by the fused kernel's forward Taylor streams")
+    raise pinn_cabi.PinnError("autograd (the dummy-gradient tape trick) is replaced by the fused kernel's forward derivative streams")
 
 
 def _native_fit_two_snapshots(self, x_0, u_0, x_1, u_1):

@@ -49,6 +49,12 @@ SIGNATURES = {
     "pinn_lbfgs": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, LOG_CB, C.c_void_p,
                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _dp]),
     "pinn_lbfgs_history": (C.c_int, [C.c_void_p, _dp, C.c_int, C.POINTER(C.c_int)]),
+    "pinn_lbfgs_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, _dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double,
+                                    C.c_double]),
+    "pinn_lbfgs_feed": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), _dp]),
+    "pinn_lbfgs_f_hist": (C.c_int, [C.c_void_p, _dp, C.c_int, C.POINTER(C.c_int)]),
+    "pinn_lbfgs_destroy": (C.c_int, [C.c_void_p]),
     "pinn_predict": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_int, _dp]),
     "pinn_num_residual_points": (C.c_int64, [C.c_void_p]),
     "pinn_residual": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
@@ -304,6 +310,52 @@ class Pinn(object):
         buf = C.create_string_buffer(512)
         self._ck(self.lib.pinn_kernel_info(self.h, buf, 512))
         return json.loads(buf.value.decode())
+
+
+class Lbfgs(object):
+    """Stand-alone device-resident L-BFGS (pinn_lbfgs_create / _feed): any objective, evaluated by the caller."""
+
+    def __init__(self, x0, max_iter, learning_rate=1.0, n_correction=100, tol_fun=1e-5, tol_x=1e-19, max_eval=0.0, device=0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        x0 = _arr(x0).reshape(-1)
+        self.n = x0.size
+        if self.lib.pinn_lbfgs_create(C.byref(self.h), int(device), self.n, _p(x0), int(max_iter), float(learning_rate),
+                                      int(n_correction), float(tol_fun), float(tol_x), float(max_eval)) != 0:
+            raise PinnError(self.lib.pinn_last_error().decode())
+
+    def feed(self, f, g):
+        """-> (x_next, status, n_iter, n_eval, logged_iter or None, logged_f)."""
+        g = _arr(g).reshape(-1)
+        if g.size != self.n:
+            raise PinnError(f"lbfgs: gradient has {g.size} entries, x has {self.n}")
+        x = np.empty(self.n)
+        st, it, ev, li = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        lf = C.c_double()
+        if self.lib.pinn_lbfgs_feed(self.h, float(f), _p(g), _p(x), C.byref(st), C.byref(it), C.byref(ev), C.byref(li),
+                                    C.byref(lf)) != 0:
+            raise PinnError(self.lib.pinn_last_error().decode())
+        return x, st.value, it.value, ev.value, (li.value if li.value >= 0 else None), lf.value
+
+    def f_hist(self):
+        n = C.c_int()
+        if self.lib.pinn_lbfgs_f_hist(self.h, None, 0, C.byref(n)) != 0:
+            raise PinnError(self.lib.pinn_last_error().decode())
+        out = np.empty(max(n.value, 1))
+        if self.lib.pinn_lbfgs_f_hist(self.h, _p(out), out.size, C.byref(n)) != 0:
+            raise PinnError(self.lib.pinn_last_error().decode())
+        return [float(v) for v in out[:n.value]]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pinn_lbfgs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def irk_ide_disc(IRK_alpha, IRK_beta):

@@ -69,7 +69,7 @@ def test_bench_gpu_arm_control_flow_with_fake_backend(monkeypatch):
     monkeypatch.setattr(pinn_cabi, "host_alloc", lambda n: (np.zeros(n), C.c_void_p(0)))
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(bench, "time_reference_port", lambda n_f, steps, warmup, seed=1234, budget_s=0: (0.4, 8, 0.1, n_f))
-    monkeypatch.setattr(bench, "_port_baseline", lambda make, w, steps, warmup, n, what, **kw: {"value": 1e5, "unit": "points/s", "cores": 8,
+    monkeypatch.setattr(bench, "_port_baseline", lambda kind, data, w, steps, warmup, n, what, **kw: {"value": 1e5, "unit": "points/s", "cores": 8,
                                                                                                   "kind": "port", "sample": what})
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "4", "--warmup", "1"])
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):

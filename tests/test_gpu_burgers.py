@@ -217,3 +217,89 @@ def test_zero_copy_collocation_matches_copied_and_sees_host_updates(cabi):
     p.set_collocation(g["X_f"][:, 0], g["X_f"][:, 1])
     assert p.loss_grad()[0] == l_copy
     p.close(); q.close()
+
+
+def test_mapped_collocation_first_then_growing_data_block(cabi):
+    """Regression: a fresh handle whose ONLY collocation set is a zero-copy mapping has no device collocation
+    region (capacity 0); growing the data block afterwards must not copy n_c doubles out of it."""
+    import ctypes as C
+    rng = np.random.default_rng(21)
+    lb, ub = np.array([-1.0, 0.0]), np.array([1.0, 0.99])
+    n = 100000
+    Xf = lb + (ub - lb) * rng.random((n, 2))
+    Xu = lb + (ub - lb) * rng.random((2000, 2)); u = rng.uniform(-1, 1, (2000, 1))
+    w = load_golden("burgers_inf")["w"]
+    hx, hx_ptr = cabi.host_alloc(n); ht, ht_ptr = cabi.host_alloc(n)
+    hx[:] = Xf[:, 0]; ht[:] = Xf[:, 1]
+    dp = C.POINTER(C.c_double)
+    p = cabi.Pinn(cabi.BURGERS_INF, LAYERS, lb, ub)
+    p.set_pde_params([0.01 / np.pi])
+    p.set_collocation_mapped(C.cast(hx_ptr, dp), C.cast(ht_ptr, dp), n)     # before any device-resident set exists
+    p.set_data(Xu, u)                                                       # 2000 rows > the initial data capacity: regrow
+    l_map, g_map, _ = p.loss_grad(w=w)
+    q = cabi.Pinn(cabi.BURGERS_INF, LAYERS, lb, ub)
+    q.set_pde_params([0.01 / np.pi]); q.set_data(Xu, u); q.set_collocation(Xf[:, 0], Xf[:, 1])
+    l_ref, g_ref, _ = q.loss_grad(w=w)
+    assert l_map == l_ref and np.array_equal(g_map, g_ref)
+    # ... and the reverse order of growth: a larger copied set after the mapping was dropped
+    p.set_collocation(Xf[:50000, 0], Xf[:50000, 1])
+    q.set_collocation(Xf[:50000, 0], Xf[:50000, 1])
+    assert p.loss_grad(w=w)[0] == q.loss_grad(w=w)[0]
+    p.close(); q.close()
+
+
+def test_residual_buffer_is_sized_by_the_library(cabi):
+    """pinn_residual takes the row count of the caller's buffer and refuses a mismatch (it used to write n_c rows
+    into whatever it was given)."""
+    import ctypes as C
+    g = load_golden("burgers_inf")
+    p = make_inf(cabi, g)
+    n = g["X_f"].shape[0]
+    assert p.residual().shape == (n, 1) and p.residual(n).shape == (n, 1)
+    with pytest.raises(cabi.PinnError, match="residual points are stored"):
+        p.residual(n - 1)
+    small = np.empty(n - 1)
+    rc = p.lib.pinn_residual(p.h, small.ctypes.data_as(C.POINTER(C.c_double)), n - 1)
+    assert rc != 0 and b"rows" in p.lib.pinn_last_error()
+    p.close()
+
+
+def test_small_sets_use_fewer_chain_warps_per_cta(cabi):
+    """N = 2000 identification (BASELINE configs[3] size): 250 tiles run as 125 CTAs x 2 chain warps; results are those of the
+    Taylor oracle, and of the same points evaluated inside a large launch (different tile -> CTA mapping)."""
+    from oracle import taylor as ty
+    rng = np.random.default_rng(17)
+    lb, ub = np.array([-1.0, 0.0]), np.array([1.0, 0.99])
+    X = lb + (ub - lb) * rng.random((2000, 2)); u = rng.uniform(-1, 1, (2000, 1))
+    w = np.concatenate([load_golden("burgers_inf")["w"], [0.3, -5.0]])
+    p = cabi.Pinn(cabi.BURGERS_IDE, LAYERS, lb, ub)
+    p.set_data(X, u)
+    loss, grad, _ = p.loss_grad(w=w)
+    f2, g2, _ = ty.burgers_loss_grad(w, LAYERS, lb, ub, None, X, u, identification=True)
+    assert abs(loss - f2) <= 1e-10 * abs(f2) and rel(grad, g2) < 1e-10
+    X3, u3 = np.vstack([X, 0.9 * X, 0.8 * X]), np.vstack([u, u, u])
+    for n in (8, 9, 300, 1184, 1185, 4735, 4737):          # around the chains-per-CTA switch points (148 and 592 tiles)
+        p.set_data(X3[:n], u3[:n])
+        l, gr, _ = p.loss_grad(w=w)
+        f2, g2, _ = ty.burgers_loss_grad(w, LAYERS, lb, ub, None, X3[:n], u3[:n], identification=True)
+        assert abs(l - f2) <= 1e-10 * abs(f2) and rel(gr, g2) < 1e-10, n
+    p.close()
+
+
+def test_quarter_million_point_shard(cabi):
+    """BASELINE configs[4] per-GPU share (2 000 000 points over 8 GPUs = 250 000 per rank, MSE_f weighted by the GLOBAL count)
+    against the numpy Taylor oracle."""
+    from oracle import taylor as ty
+    rng = np.random.default_rng(250)
+    lb, ub = np.array([-1.0, 0.0]), np.array([1.0, 0.99])
+    n = 250000
+    X_f = lb + (ub - lb) * rng.random((n, 2))
+    X_u = lb + (ub - lb) * rng.random((100, 2)); u = rng.uniform(-1, 1, (100, 1))
+    w = load_golden("burgers_inf")["w"]
+    p = cabi.Pinn(cabi.BURGERS_INF, LAYERS, lb, ub)
+    p.set_pde_params([0.01 / np.pi]); p.set_data(X_u, u, weight=0.0)
+    p.set_collocation(X_f[:, 0], X_f[:, 1], n_global=2000000)
+    loss, grad, parts = p.loss_grad(w=w)
+    f2, g2, _ = ty.burgers_loss_grad(w, LAYERS, lb, ub, X_f, X_u, u, nu=0.01 / np.pi, n_f_global=2000000, data_weight=0.0)
+    assert abs(loss - f2) <= 1e-10 * abs(f2) and rel(grad, g2) < 1e-10 and parts[0] == 0.0
+    p.close()

@@ -130,3 +130,24 @@ def test_lbfgs_short_run(cabi):
     assert r["n_iter"] == tr.n_iter and r["n_eval"] == tr.n_eval
     assert rel(r["x_final"], tr.x_final) < 1e-8
     assert rel(p.get_weights(), tr.x_eval[-1]) < 1e-8
+
+
+def test_lbfgs_twenty_iterations_at_full_size(cabi):
+    """BASELINE configs[2] size (N_f = 20 000, the lbfgs_iterate<32,1024> instantiation with P = 30 802): twenty device
+    iterations against the oracle's control flow driven by the numpy Taylor oracle.  Rounding differences between two fp64
+    implementations of a fixed-step L-BFGS grow about tenfold per ten iterations, hence 1e-6 on the trajectory."""
+    from oracle import reference_port as rp, taylor as ty
+    g = load_golden("nls_inf")
+    rng = np.random.default_rng(20)
+    X_f = g["lb"] + (g["ub"] - g["lb"]) * rng.random((20000, 2))
+    p = cabi.Pinn(cabi.NLS_INF, LAYERS, g["lb"], g["ub"])
+    p.set_collocation(X_f[:, 0], X_f[:, 1]); p.set_boundary(g["tb"]); p.set_data(g["x0"], g["uv0"]); p.set_weights(g["w"])
+    op = lambda x: ty.schrodinger_loss_grad(x, LAYERS, g["lb"], g["ub"], X_f, g["tb"], g["x0"], g["uv0"])[:2]
+    tr = rp.lbfgs_fixed_step(op, g["w"], max_iter=20, learning_rate=0.8, n_correction=50, tol_fun=np.finfo(float).eps)
+    logged = []
+    r = p.lbfgs(20, learning_rate=0.8, n_correction=50, tol_fun=np.finfo(float).eps, sync_every=7, want_x_final=True,
+                log_fn=lambda it, f: logged.append((it, f)))
+    assert r["n_iter"] == tr.n_iter == 20 and r["n_eval"] == tr.n_eval
+    assert rel(r["f_hist"], tr.f_hist) < 1e-6
+    assert [it for it, _ in logged] == [it for it, _ in tr.logged]
+    assert rel(r["x_final"], tr.x_final) < 1e-6 and rel(p.get_weights(), tr.x_eval[-1]) < 1e-6

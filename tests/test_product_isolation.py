@@ -53,12 +53,13 @@ def test_native_sources_have_no_host_arithmetic_fallback():
 
 def test_bench_and_smoke_use_the_oracle_only_as_checker():
     bench = open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read()
-    # the only oracle entry point in bench.py is the CPU timing helper shared by cpu_baseline and --impl reference
+    # the only oracle entry points in bench.py are the CPU timing helpers (one contiguous section: cpu_threads ... _port_baseline)
+    # shared by cpu_baseline, the extras' cpu_baselines and --impl reference
     users = [m.start() for m in re.finditer(r"from oracle|import oracle", bench)]
     assert users, "bench.py must time the oracle for cpu_baseline"
-    body = bench[bench.index("def time_reference_port"):bench.index("def run_reference_arm")]
-    assert all(bench.index("def time_reference_port") < u < bench.index("def run_reference_arm") for u in users), \
-        "oracle imported outside time_reference_port"
+    lo, hi = bench.index("def cpu_threads"), bench.index("def run_reference_arm")
+    body = bench[lo:hi]
+    assert all(lo < u < hi for u in users), "oracle imported outside the CPU timing section"
     assert "pinn_cabi" not in body                      # the CPU leg never touches the product, and vice versa
     entry = open(os.path.join(ROOT, "__graft_entry__.py"), encoding="utf-8").read()
     build_body = entry[entry.index("def build"):entry.index("def smoke")]

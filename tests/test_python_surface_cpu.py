@@ -36,7 +36,9 @@ def test_struct_and_lbfgs_contract():
     assert s.anything == 0 and s.maxIter == 0
     assert lbfgs(lambda x: (0.0, x), np.zeros(3), s, Struct(), True, None) is None      # custom_lbfgs.py:43-44
     s.maxIter = 5
-    with pytest.raises(TypeError, match="no host fallback"):
+    # a foreign closure runs on the stand-alone DEVICE optimiser: without a GPU that fails loudly (no host fallback)
+    import pinn_cabi
+    with pytest.raises(pinn_cabi.PinnError, match="no CPU fallback"):
         lbfgs(lambda x: (0.0, x), np.zeros(3), s, Struct(), True, None)
 
 
