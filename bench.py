@@ -452,6 +452,26 @@ def measure_extras(pinn_cabi, n_f, with_cpu=True):
         out["schrodinger"] = d
     except Exception as e:  # pragma: no cover
         out["schrodinger"] = {"error": str(e)}
+    # ---- a net the specialised DMMA kernel does not cover: upstream's 8 x 40 table (Burgers_systematic.py:187-202) on the
+    # generic fused kernel (plain DFMA) -- reported so that the cliff next to the [2,20x8,1] path has a number
+    try:
+        L40 = [2] + [40] * 8 + [1]
+        n40 = 20000
+        S40 = 2 * 40 + 7 * 1600 + 40
+        X_f, X_u, u = synthetic_problem(40, n40)
+        p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, L40, LB, UB)
+        p.set_pde_params([NU]); p.set_data(X_u, u); p.set_collocation(X_f[:, 0], X_f[:, 1]); p.set_weights(init_weights(L40))
+        for _ in range(3):
+            p.adam_step(ADAM_LR, sync=False)
+        p.sync()
+        ms = float(np.mean(timed_adam_steps(p, 10, flush=False)))
+        k_ms = p.time_kernel_ms(5) / 5
+        out["burgers_8x40_generic"] = {"config": "[2,40x8,1] tanh (upstream's systematic table), N_f=%d, generic fused kernel (DFMA, no tensor cores)" % n40,
+                                       "ms_per_step": ms, "points_per_s": n40 / (ms * 1e-3), "kernel_ms": k_ms,
+                                       "roofline_frac_fp64": (n40 * 24.0 * S40 + N_U * 6.0 * S40) / (k_ms * 1e-3) / 1e12 / peak}
+        p.close()
+    except Exception as e:  # pragma: no cover
+        out["burgers_8x40_generic"] = {"error": str(e)}
     # ---- discrete time
     try:
         q = 500

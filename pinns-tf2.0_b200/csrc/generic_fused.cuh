@@ -87,12 +87,13 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
   const double l1 = ide ? p.w[p.p_net] : 1.0;
   const double kap = ide ? exp(p.w[p.p_net + 1]) : p.nu;
 
-  // layer-l output slab: [4][pts][w_l]
-  size_t hoff[MAXL];
-  {
+  // layer-l output slab: [4][pts][w_l]  (offsets in shared memory: a dynamically indexed per-thread array would live on the stack)
+  __shared__ size_t hoff[MAXL];
+  if (tid == 0) {
     size_t o = 0;
     for (int l = 0; l < L - 1; l++) { hoff[l] = o; o += (size_t)4 * pts * nd.dims[l + 1]; }
   }
+  __syncthreads();
 
   // ======================================= forward: hidden layers =======================================
   for (int l = 0; l < L - 1; l++) {
@@ -268,7 +269,9 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
         sd[6] = -0.5 * cv; sd[7] = 0.5 * cu;
       }
     }
-    for (int c = 0; c < 4 * out; c++) SEED[(size_t)pt * 4 * out + c] = sd[c];
+#pragma unroll
+    for (int c = 0; c < 4 * MAXOUT; c++)
+      if (c < 4 * out) SEED[(size_t)pt * 4 * out + c] = sd[c];
   }
   block_reduce_store(part0, red, outp + p.p_net + 3);
   block_reduce_store(part1, red, outp + p.p_net + 4);

@@ -47,7 +47,8 @@ constexpr int SM_W = 0;
 constexpr int SM_S0 = SM_W + W * W;
 constexpr int SM_S1 = SM_S0 + SLAB;
 constexpr int SM_RED = SM_S1 + SLAB;
-constexpr int SM_BAR = SM_RED + 64;
+constexpr int SM_W4 = SM_RED + 64;        // head weights W_4 (100 x 2): read per element by the layer-3 adjoint epilogue
+constexpr int SM_BAR = SM_W4 + 2 * W;
 constexpr int SM_DOUBLES = SM_BAR + 2;
 constexpr int SMEM_BYTES = SM_DOUBLES * 8;     // 182,928 B
 
@@ -359,13 +360,14 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   const int n_first = wide ? 0 : 7;
   const int sn0 = 3 * wb;                        // strip: first N tile
   const int snn = wide ? 0 : (wb == 3 ? 4 : 3);  // strip: number of N tiles
+  for (int i = tid; i < 2 * W; i += THREADS) sm[SM_W4 + i] = __ldg(p.w + woff(4) + i);
   for (int l = 3; l >= 1; l--) {
     load_weights_tma(Wsm, p.w + woff(l), bar, wphase);
     const double* Hl = H + (size_t)l * LSZ;              // outputs of layer l (for the activation adjoint)
     const double* Hin = H + (size_t)(l - 1) * LSZ;       // inputs of layer l (A operand of the weight gradient)
     const double* Ain = A + (size_t)((l & 1) ? 0 : 1) * 4 * SSZ;    // adjoint of layer-l outputs (l < 3)
     double* Aout = A + (size_t)((l & 1) ? 1 : 0) * 4 * SSZ;         // adjoint of layer-(l-1) outputs
-    const double* W4 = p.w + woff(4);
+    const double* W4 = sm + SM_W4;
     double G[3][7][2], GS[4][2];
 #pragma unroll
     for (int m = 0; m < 3; m++)
@@ -397,8 +399,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
               if (l == 3) {
                 // adjoint of the last hidden layer's outputs straight from the seeds: A[s][u] = sum_o seed[s][o] W4[u][o]
                 const double s0 = SEED[pt * 8 + 2 * s], s1 = SEED[pt * 8 + 2 * s + 1];
-                a2.x = fma(s0, __ldg(W4 + 2 * u), s1 * __ldg(W4 + 2 * u + 1));
-                a2.y = fma(s0, __ldg(W4 + 2 * u + 2), s1 * __ldg(W4 + 2 * u + 3));
+                a2.x = fma(s0, W4[2 * u], s1 * W4[2 * u + 1]);
+                a2.y = fma(s0, W4[2 * u + 2], s1 * W4[2 * u + 3]);
               } else {
                 a2 = *reinterpret_cast<const double2*>(Ain + s * SSZ + (size_t)pt * W + u);
               }

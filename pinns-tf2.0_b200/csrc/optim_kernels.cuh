@@ -170,7 +170,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// xseq[0] = published evaluations so far, xseq[1] = blocks finished in the current launch
+// xseq[0] = published evaluations so far, xseq[1] = blocks finished in the current launch.
+// The grid is capped at a size that is certainly co-resident (the host passes min(n_vblocks, 2 x SMs)); every block walks
+// the 32-entry "virtual blocks" vb = blockIdx.x, blockIdx.x + gridDim.x, ... in increasing order.  A block waiting for the
+// peers' copy of vb therefore only depends on peers' blocks that wait for SMALLER virtual blocks: no cycle, whatever the order in
+// which the hardware dispatches blocks on the different GPUs.
 __global__ void __launch_bounds__(256)
 reduce_exchange(const double* __restrict__ partials, int n_cta, int stride, ReduceMap map, const int* __restrict__ run_flag,
                 XchgPeers peers, int* __restrict__ xseq, double* __restrict__ R, int* __restrict__ err, int adam,
@@ -180,44 +184,47 @@ reduce_exchange(const double* __restrict__ partials, int n_cta, int stride, Redu
   const unsigned long long seq = (unsigned long long)(*(volatile int*)xseq) + 1;
   const int parity = (int)(seq & 1);
   const int sub = threadIdx.x & 7;
-  const int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
-  const bool ok = i < map.n_out;
-  const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
-  double s = 0.0;
-  if (ok)
-    for (int b = sub; b < n_cta; b += 8) s += partials[(size_t)b * stride + src];
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 4);          // every sub-lane holds the entry's local sum
-  // ---- push: sub-lane k stores the entry into rank k's buffer, slot [parity][my rank]
-  const size_t slot = ((size_t)parity * peers.world + peers.rank) * peers.slot_len;
-  if (ok && sub < peers.world) peers.data[sub][slot + i] = s;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < peers.world)
-    st_release_sys(peers.flag[threadIdx.x] + ((size_t)parity * peers.world + peers.rank) * peers.n_blocks + blockIdx.x, seq);
-  // ---- wait for every rank's copy of this block's entries (local flags)
-  if (threadIdx.x < peers.world) {
-    const unsigned long long* f = peers.flag[peers.rank] + ((size_t)parity * peers.world + threadIdx.x) * peers.n_blocks + blockIdx.x;
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(f) < seq) {
-      if (globaltimer_ns() - t0 > 20000000000ULL) { atomicExch(err, 1); break; }
-      __nanosleep(32);
-    }
-  }
-  __syncthreads();
-  const bool dead = *(volatile int*)err != 0;       // a peer never published: leave R, weights and optimiser state untouched
-  // ---- sum over ranks: sub-lane k loads rank k's value from the LOCAL buffer, butterfly in a fixed order
-  double tot = 0.0;
-  if (ok && sub < peers.world)
-    tot = __ldcv(peers.data[peers.rank] + ((size_t)parity * peers.world + sub) * peers.slot_len + i);
-  tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-  tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-  tot += __shfl_xor_sync(0xffffffffu, tot, 4);
   const int t = adam ? step[0] + 1 : 0;
-  if (ok && sub == 0 && !dead) {
-    R[i] = tot;
-    if (adam && i < P) adam_entry(w, m, v, tot, i, t, lr, b1, b2, eps);
+  bool dead = false;
+  for (int vb = blockIdx.x; vb < peers.n_blocks; vb += gridDim.x) {
+    const int i = vb * (blockDim.x >> 3) + (threadIdx.x >> 3);
+    const bool ok = i < map.n_out;
+    const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
+    double s = 0.0;
+    if (ok)
+      for (int b = sub; b < n_cta; b += 8) s += partials[(size_t)b * stride + src];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);          // every sub-lane holds the entry's local sum
+    // ---- push: sub-lane k stores the entry into rank k's buffer, slot [parity][my rank]
+    const size_t slot = ((size_t)parity * peers.world + peers.rank) * peers.slot_len;
+    if (ok && sub < peers.world) peers.data[sub][slot + i] = s;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < peers.world)
+      st_release_sys(peers.flag[threadIdx.x] + ((size_t)parity * peers.world + peers.rank) * peers.n_blocks + vb, seq);
+    // ---- wait for every rank's copy of this virtual block's entries (local flags)
+    if (threadIdx.x < peers.world) {
+      const unsigned long long* f = peers.flag[peers.rank] + ((size_t)parity * peers.world + threadIdx.x) * peers.n_blocks + vb;
+      const unsigned long long t0 = globaltimer_ns();
+      while (ld_acquire_sys(f) < seq) {
+        if (globaltimer_ns() - t0 > 20000000000ULL) { atomicExch(err, 1); break; }
+        __nanosleep(32);
+      }
+    }
+    __syncthreads();
+    dead = dead || *(volatile int*)err != 0;        // a peer never published: leave R, weights and optimiser state untouched
+    // ---- sum over ranks: sub-lane k loads rank k's value from the LOCAL buffer, butterfly in a fixed order
+    double tot = 0.0;
+    if (ok && sub < peers.world)
+      tot = __ldcv(peers.data[peers.rank] + ((size_t)parity * peers.world + sub) * peers.slot_len + i);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+    if (ok && sub == 0 && !dead) {
+      R[i] = tot;
+      if (adam && i < P) adam_entry(w, m, v, tot, i, t, lr, b1, b2, eps);
+    }
   }
   __threadfence();
   __syncthreads();
@@ -490,49 +497,69 @@ lbfgs_iterate(LbfgsState* __restrict__ st, double* __restrict__ w, const double*
 constexpr int LB_CHUNK = 256;       // entries per CTA of lbfgs_dots / lbfgs_apply
 constexpr int LB_NSCAL = 7;         // scalar dots: |g|_1, g.g, |s|_1, y.s, y.y, s.g, y.g;  then 4 per stored pair
 
-__global__ void __launch_bounds__(LB_CHUNK)
+constexpr int LB_DOT_THREADS = 512;  // lbfgs_dots: 16 warps share a 256-entry chunk (the dot products are latency-bound)
+
+__global__ void __launch_bounds__(LB_DOT_THREADS)
 lbfgs_dots(const LbfgsState* __restrict__ st, const double* __restrict__ R, int P, const double* __restrict__ g_old,
            const double* __restrict__ d, double* __restrict__ S, double* __restrict__ Y, double* __restrict__ part, int part_stride) {
   __shared__ double sg[LB_CHUNK], sy[LB_CHUNK], ss[LB_CHUNK];
   if (st->status != 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int i = blockIdx.x * LB_CHUNK + tid;
   const bool have_step = st->n_iter > 0;             // false: this is the initial evaluation, there is no pair to form
   const int k = st->k;
-  const double gi = i < P ? R[i] : 0.0;
-  double yi = 0.0, si = 0.0;
-  if (have_step && i < P) {
-    yi = gi - g_old[i];                               // custom_lbfgs.py:98
-    si = d[i] * st->t;                                // :99
-    const size_t o = (size_t)st->free_slot * P + i;
-    S[o] = si; Y[o] = yi;
+  if (tid < LB_CHUNK) {
+    const int i = blockIdx.x * LB_CHUNK + tid;
+    const double gi = i < P ? R[i] : 0.0;
+    double yi = 0.0, si = 0.0;
+    if (have_step && i < P) {
+      yi = gi - g_old[i];                             // custom_lbfgs.py:98
+      si = d[i] * st->t;                              // :99
+      const size_t o = (size_t)st->free_slot * P + i;
+      S[o] = si; Y[o] = yi;
+    }
+    sg[tid] = gi; sy[tid] = yi; ss[tid] = si;
   }
-  sg[tid] = gi; sy[tid] = yi; ss[tid] = si;
   __syncthreads();
   double* out = part + (size_t)blockIdx.x * part_stride;
-  const int ndots = LB_NSCAL + (have_step ? 4 * k : 0);
-  // dot j: warps take j = warp, warp + 8, ...; lanes stride the chunk; fixed shuffle tree -> deterministic
-  for (int j = warp; j < ndots; j += LB_CHUNK / 32) {
+  constexpr int NW = LB_DOT_THREADS / 32, EPL = LB_CHUNK / 32;
+  // scalar dots: warps 0..6, one each; lanes stride the chunk; fixed shuffle tree -> deterministic
+  if (warp < LB_NSCAL) {
     double acc = 0.0;
-    if (j < LB_NSCAL) {
 #pragma unroll
-      for (int e = 0; e < LB_CHUNK / 32; e++) {
-        const int t = lane + 32 * e;
-        const double gg = sg[t], yy = sy[t], sv = ss[t];
-        acc += j == 0 ? fabs(gg) : j == 1 ? gg * gg : j == 2 ? fabs(sv) : j == 3 ? yy * sv : j == 4 ? yy * yy : j == 5 ? sv * gg : yy * gg;
-      }
-    } else {
-      const int m = (j - LB_NSCAL) >> 2, which = (j - LB_NSCAL) & 3;
-      const double* hist = ((which & 1) ? Y : S) + (size_t)st->slot[m] * P + (size_t)blockIdx.x * LB_CHUNK;
-      const double* other = which < 2 ? sy : sg;      // 0: s_m.y  1: y_m.y  2: s_m.g  3: y_m.g
-#pragma unroll
-      for (int e = 0; e < LB_CHUNK / 32; e++) {
-        const int t = lane + 32 * e;
-        acc = fma(blockIdx.x * LB_CHUNK + t < P ? hist[t] : 0.0, other[t], acc);
-      }
+    for (int e = 0; e < EPL; e++) {
+      const int t = lane + 32 * e;
+      const double gg = sg[t], yy = sy[t], sv = ss[t];
+      acc += warp == 0 ? fabs(gg) : warp == 1 ? gg * gg : warp == 2 ? fabs(sv) : warp == 3 ? yy * sv : warp == 4 ? yy * yy
+                                                                                   : warp == 5 ? sv * gg : yy * gg;
     }
     acc = warp_sum(acc);
-    if (lane == 0) out[j] = acc;
+    if (lane == 0) out[warp] = acc;
+  }
+  if (!have_step) return;
+  // stored pairs: warp takes ages m = warp, warp + 16, ...; the four dot products of a pair (s_m.y, y_m.y, s_m.g, y_m.g) share
+  // their 2 x 8 loads per lane, all in flight together
+  for (int m = warp; m < k; m += NW) {
+    const size_t base = (size_t)st->slot[m] * P + (size_t)blockIdx.x * LB_CHUNK;
+    double sv[EPL], yv[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int t = lane + 32 * e;
+      const bool in = blockIdx.x * LB_CHUNK + t < P;
+      sv[e] = in ? S[base + t] : 0.0;
+      yv[e] = in ? Y[base + t] : 0.0;
+    }
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPL; e++) {
+      const int t = lane + 32 * e;
+      a0 = fma(sv[e], sy[t], a0); a1 = fma(yv[e], sy[t], a1);
+      a2 = fma(sv[e], sg[t], a2); a3 = fma(yv[e], sg[t], a3);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    if (lane == 0) {
+      double* o = out + LB_NSCAL + 4 * m;
+      o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
+    }
   }
 }
 
@@ -701,7 +728,8 @@ lbfgs_apply(LbfgsState* __restrict__ st, double* __restrict__ w, const double* _
   if (i >= P) return;
   const double gi = R[i];
   double dv = st->c_g * gi;
-  for (int m = 0; m < k; m++) {
+#pragma unroll 8
+  for (int m = 0; m < k; m++) {            // 2k independent loads per entry; the fixed order of the FMAs keeps d reproducible
     const size_t o = (size_t)ps[m] * P + i;
     dv = fma(ca[m], S[o], dv);
     dv = fma(cb[m], Y[o], dv);

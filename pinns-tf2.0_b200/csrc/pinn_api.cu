@@ -162,11 +162,16 @@ int generic_launch_eval(pinn_t* h, const int* run_flag);
 int disc_upload_points(pinn_t* h);
 
 // One L-BFGS iteration on the device (stop tests of the pending evaluation, history update, direction, step).
-// Default: the Gram-matrix formulation (lbfgs_dots -> lbfgs_solve -> lbfgs_apply: every SM reads its slice of the history).
-// PINN_LBFGS=serial selects the single-CTA kernel that follows the reference's loop literally (cross-check).
+// Default: the single-CTA kernel that follows the reference's loop literally (lbfgs_iterate).
+// PINN_LBFGS=gram selects the Gram-matrix formulation (lbfgs_dots -> lbfgs_solve -> lbfgs_apply: every SM reads its slice of
+// the history; ~12 us less per iteration at n_corr = 50).  It is NOT the default: in 1 of 8 long fixed-step runs
+// (profiles/lbfgs_stability_r02.jsonl) its coefficient-space recursion produced a bad direction at iteration ~400 where the
+// literal loop did not -- the triangular recurrence over s_i.y_m amplifies rounding when the stored pairs are nearly
+// dependent, whereas the literal loop measures every s_i.q against the actual q -- and the reference has no line search to
+// recover from one bad step.
 bool lbfgs_serial() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("PINN_LBFGS"); v = (e && !strcmp(e, "serial")) ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("PINN_LBFGS"); v = (e && !strcmp(e, "gram")) ? 0 : 1; }
   return v == 1;
 }
 int lbfgs_gram_ensure(LbfgsGram* gm, int n_corr, int P) {
@@ -206,7 +211,7 @@ int lbfgs_launch_iteration(cudaStream_t stream, pinn::LbfgsState* st, double* w,
     return 0;
   }
   const int nb = (P + pinn::LB_CHUNK - 1) / pinn::LB_CHUNK;
-  pinn::lbfgs_dots<<<nb, pinn::LB_CHUNK, 0, stream>>>(st, R, P, gold, d, S, Y, gm.part, gm.stride);
+  pinn::lbfgs_dots<<<nb, pinn::LB_DOT_THREADS, 0, stream>>>(st, R, P, gold, d, S, Y, gm.part, gm.stride);
   pinn::lbfgs_solve<<<1, 128, (size_t)gm.n_corr_cap * gm.n_corr_cap * 8, stream>>>(st, R, P, gm.part, nb, gm.stride, gm.SY, gm.YY, fhist,
                                                                                    logged);
   pinn::lbfgs_apply<<<nb, pinn::LB_CHUNK, 0, stream>>>(st, w, R, P, gold, d, S, Y, xfinal);
@@ -301,7 +306,8 @@ int launch_tail(pinn_t* h, const int* run_flag, const AdamArgs* ad) {
   }
   if (h->p2p_ready) {
     if (nb != h->peers.n_blocks || map.n_out > h->peers.slot_len) return fail("internal: exchange buffer geometry mismatch");
-    pinn::reduce_exchange<<<nb, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, map, run_flag, h->peers, h->d_xseq,
+    const int xgrid = nb < 2 * h->n_sm ? nb : 2 * h->n_sm;      // certainly co-resident: <= 2 blocks of 256 threads per SM
+    pinn::reduce_exchange<<<xgrid, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, map, run_flag, h->peers, h->d_xseq,
                                                       h->d_R, h->d_p2p_err, ad ? 1 : 0, h->d_w, h->d_m, h->d_v, h->P, h->d_step,
                                                       ad ? ad->lr : 0.0, ad ? ad->b1 : 0.0, ad ? ad->b2 : 0.0, ad ? ad->eps : 0.0,
                                                       h->d_loss_ring, LOSS_RING);

@@ -37,6 +37,15 @@ def run(tf_epochs, nt_epochs):
             "log_tail": buf.getvalue().strip().split("\n")[-3:]}
 
 
-out = {"oracle_cpu_default_schedule": {"final_loss": float(g["oracle_lbfgs_f"][-1]), "rel_l2_error_u": float(g["oracle_error"])},
+# one-time process costs (CUDA context, module load, first cudaMalloc) are paid here, outside the training times below
+_t0 = time.perf_counter()
+import pinn_cabi
+_warm = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, [2] + [20] * 8 + [1], g["lb"], g["ub"])
+_warm.set_pde_params([0.01 / np.pi]); _warm.set_collocation(g["X_f"][:64, 0], g["X_f"][:64, 1]); _warm.set_data(g["X_u"], g["u"])
+_warm.adam_step(1e-3); _warm.lbfgs(2, learning_rate=0.8, n_correction=50, tol_fun=1e-300); _warm.close()
+process_start_seconds = time.perf_counter() - _t0
+
+out = {"process_start_seconds (CUDA context + module load, once per process)": process_start_seconds,
+       "oracle_cpu_default_schedule": {"final_loss": float(g["oracle_lbfgs_f"][-1]), "rel_l2_error_u": float(g["oracle_error"])},
        "b200_default_schedule": run(100, 200), "b200_long_schedule": run(2000, 5000)}
 print(json.dumps(out, indent=1))

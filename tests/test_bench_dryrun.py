@@ -94,7 +94,8 @@ def test_bench_gpu_arm_control_flow_with_fake_backend(monkeypatch):
     assert d["e2e"]["h2d_bytes_per_step"] == 1600000 and d["e2e"]["d2h_bytes_per_step"] == 8
     r = d["roofline"]
     assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["traffic"] > 1e6
-    assert set(d["extras"]) == {"burgers_lbfgs", "burgers_cfg1_10k", "burgers_identification", "schrodinger", "burgers_discrete_time"}
+    assert set(d["extras"]) == {"burgers_lbfgs", "burgers_cfg1_10k", "burgers_identification", "schrodinger", "burgers_8x40_generic",
+                                "burgers_discrete_time"}
     assert all("error" not in v for v in d["extras"].values()), d["extras"]
     for k in ("burgers_cfg1_10k", "burgers_identification", "schrodinger"):
         assert d["extras"][k]["cpu_baseline"]["kind"] == "port"
