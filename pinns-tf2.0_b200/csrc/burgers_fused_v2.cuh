@@ -79,6 +79,9 @@ constexpr int ROUND = CHAINS * TILE;      // 32 points per full CTA round
 #ifndef PINN_ABL_NODMMA
 #define PINN_ABL_NODMMA 0                 // no chain DMMAs
 #endif
+#ifndef PINN_G_SLEEP
+#define PINN_G_SLEEP 0                    // experiment: nanoseconds a weight-gradient warp sleeps after each k-step (spreads its DMMAs)
+#endif
 constexpr int RING = PINN_RING;           // Z-bar ring slots per chain warp
 
 // shared memory carve-up (doubles)
@@ -248,6 +251,7 @@ __device__ __forceinline__ void wgrad_task(double (&acc)[3][2], int mt, const do
     dmma(acc[0], a, b0);
     dmma(acc[1], a, b1);
     dmma(acc[2], a, b2);
+    if (PINN_G_SLEEP > 0) __nanosleep(PINN_G_SLEEP);
   }
 }
 

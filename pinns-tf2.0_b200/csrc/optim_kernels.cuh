@@ -199,10 +199,14 @@ reduce_exchange(const double* __restrict__ partials, int n_cta, int stride, Redu
     // ---- push: sub-lane k stores the entry into rank k's buffer, slot [parity][my rank]
     const size_t slot = ((size_t)parity * peers.world + peers.rank) * peers.slot_len;
     if (ok && sub < peers.world) peers.data[sub][slot + i] = s;
-    __threadfence_system();
+    // publication: the block barrier orders every thread's data stores before the flag writers, whose release at system
+    // scope (fence + store) is cumulative over what they have observed through the barrier -- ONE system-scope fence per
+    // block and peer instead of one per thread
     __syncthreads();
-    if (threadIdx.x < peers.world)
+    if (threadIdx.x < peers.world) {
+      __threadfence_system();
       st_release_sys(peers.flag[threadIdx.x] + ((size_t)parity * peers.world + peers.rank) * peers.n_blocks + vb, seq);
+    }
     // ---- wait for every rank's copy of this virtual block's entries (local flags)
     if (threadIdx.x < peers.world) {
       const unsigned long long* f = peers.flag[peers.rank] + ((size_t)parity * peers.world + threadIdx.x) * peers.n_blocks + vb;
