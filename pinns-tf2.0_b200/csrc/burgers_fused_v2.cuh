@@ -41,7 +41,11 @@
 // (slower: the weight-gradient warps starve), publishing Z-bar after the chain warp's own input-adjoint GEMM (no change),
 // output units 16..19 of the chain GEMMs as 80 FMAs + a quad reduce-scatter instead of the half-padded third DMMA tile
 // (fewer pipe cycles on paper, 0.389 -> 0.416 ms in practice: DFMA interleaved with DMMA costs more than it saves); the same
-// for columns 16..19 of the weight-gradient tile rows (0.390 -> 0.410 ms).
+// for columns 16..19 of the weight-gradient tile rows (0.390 -> 0.410 ms); spreading the weight-gradient DMMAs with __nanosleep
+// between k-steps (0.443 ms at 20 ns and worse); and a THREE-warps-per-sub-partition variant that splits every tile's chain
+// between two half-warps (N tiles {0,2} / {1}, A operands from shared memory, roles alternating per layer; 384 threads x 168
+// registers): correct on the first run, but 0.439 ms -- the FP64 pipe was 70 % busy against 75 % here (pair barriers and the
+// A-operand LDS cost more than the added latency hiding bought).
 #pragma once
 #include "burgers_fused.cuh"
 
@@ -78,9 +82,6 @@ constexpr int ROUND = CHAINS * TILE;      // 32 points per full CTA round
 #endif
 #ifndef PINN_ABL_NODMMA
 #define PINN_ABL_NODMMA 0                 // no chain DMMAs
-#endif
-#ifndef PINN_G_SLEEP
-#define PINN_G_SLEEP 0                    // experiment: nanoseconds a weight-gradient warp sleeps after each k-step (spreads its DMMAs)
 #endif
 constexpr int RING = PINN_RING;           // Z-bar ring slots per chain warp
 
@@ -251,7 +252,6 @@ __device__ __forceinline__ void wgrad_task(double (&acc)[3][2], int mt, const do
     dmma(acc[0], a, b0);
     dmma(acc[1], a, b1);
     dmma(acc[2], a, b2);
-    if (PINN_G_SLEEP > 0) __nanosleep(PINN_G_SLEEP);
   }
 }
 

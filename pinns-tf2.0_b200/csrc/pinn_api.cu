@@ -356,7 +356,7 @@ int burgers_launch_eval(pinn_t* h, const int* run_flag) {
   a.run_flag = run_flag;
   // v2: few points -> fewer chain warps per CTA and more CTAs (a launch then lasts one tile on lightly loaded SMs)
   int chains = 4;
-  if (h->burgers_kernel == 2) {
+  if (h->burgers_kernel >= 2) {
     const long long n_tiles = (n_total + B::TILE - 1) / B::TILE;
     if (n_tiles < 4LL * h->n_cta) {
       chains = (int)((n_tiles + h->n_cta - 1) / h->n_cta);
