@@ -296,6 +296,7 @@ __device__ __forceinline__ void wgrad_flush(const double (&acc)[3][2], int wg, d
 
 __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   extern __shared__ __align__(16) double sm[];
+  pdl_launch_dependents();                 // the tail kernel's blocks may be placed as SMs free up; they park in pdl_wait()
   if (p.run_flag && *p.run_flag != 0) return;
   double* Wsm = sm + SM_W;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BAR);   // [0] weights TMA; then (full, empty) per (chain, slot)

@@ -45,6 +45,7 @@ struct ReduceMap {
 // (deterministic).  blockDim = 256 -> 32 entries per block.
 __global__ void reduce_partials(const double* __restrict__ partials, int n_cta, int stride, double* __restrict__ R,
                                 ReduceMap map, const int* __restrict__ run_flag) {
+  pdl_wait();                                       // the fused kernel that wrote the partials has completed
   if (run_flag && *run_flag != 0) return;
   const int sub = threadIdx.x & 7;
   const int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
@@ -99,6 +100,7 @@ __global__ void reduce_adam(const double* __restrict__ partials, int n_cta, int 
                             double* __restrict__ w, double* __restrict__ m, double* __restrict__ v, int P,
                             int* __restrict__ step, double lr, double b1, double b2, double eps,
                             double* __restrict__ loss_ring, int ring) {
+  pdl_wait();                                       // the fused kernel that wrote the partials has completed
   const int t = step[0] + 1;
   const int sub = threadIdx.x & 7;
   const int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
@@ -180,6 +182,7 @@ reduce_exchange(const double* __restrict__ partials, int n_cta, int stride, Redu
                 XchgPeers peers, int* __restrict__ xseq, double* __restrict__ R, int* __restrict__ err, int adam,
                 double* __restrict__ w, double* __restrict__ m, double* __restrict__ v, int P, int* __restrict__ step,
                 double lr, double b1, double b2, double eps, double* __restrict__ loss_ring, int ring) {
+  pdl_wait();                                       // the fused kernel that wrote the partials has completed
   if (run_flag && *run_flag != 0) return;          // identical on every rank (replicated L-BFGS state)
   const unsigned long long seq = (unsigned long long)(*(volatile int*)xseq) + 1;
   const int parity = (int)(seq & 1);

@@ -286,6 +286,26 @@ int ensure_points(pinn_t* h, long long need_d, long long need_c) {
 
 struct AdamArgs { double lr, b1, b2, eps; };
 
+// Launch a tail kernel, optionally with programmatic stream serialization (PDL, PINN_PDL=1): its blocks may then be placed while
+// the fused kernel that precedes it in the stream drains, and wait in pdl_wait() for its completion.  OFF by default: measured
+// on 1xB200 the step got 5 us SLOWER with it (0.4094 vs 0.4044 ms: the early-placed tail blocks sit on the SMs whose fused CTA
+// finished first and the launch latency they were meant to hide is smaller than what their parking costs).
+bool use_pdl() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PINN_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_tail_kernel(void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // The tail of an evaluation: fixed-order reduction of the per-CTA partials into R = [grad | loss parts] on every rank,
 // optionally fused with the Adam update.
 //   world == 1      : reduce_partials, or reduce_adam (one kernel)
@@ -296,10 +316,11 @@ int launch_tail(pinn_t* h, const int* run_flag, const AdamArgs* ad) {
   const int nb = (map.n_out + 31) / 32;
   if (h->world == 1) {
     if (ad)
-      pinn::reduce_adam<<<nb, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, h->d_R, map, h->d_w, h->d_m, h->d_v,
-                                                    h->P, h->d_step, ad->lr, ad->b1, ad->b2, ad->eps, h->d_loss_ring, LOSS_RING);
+      CUDA_TRY(launch_tail_kernel(pinn::reduce_adam, nb, 256, h->stream, h->d_partials, h->last_grid, h->last_stride, h->d_R, map, h->d_w,
+                                  h->d_m, h->d_v, h->P, h->d_step, ad->lr, ad->b1, ad->b2, ad->eps, h->d_loss_ring, LOSS_RING));
     else
-      pinn::reduce_partials<<<nb, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, h->d_R, map, run_flag);
+      CUDA_TRY(launch_tail_kernel(pinn::reduce_partials, nb, 256, h->stream, h->d_partials, h->last_grid, h->last_stride, h->d_R, map,
+                                  run_flag));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return 0;
@@ -307,15 +328,15 @@ int launch_tail(pinn_t* h, const int* run_flag, const AdamArgs* ad) {
   if (h->p2p_ready) {
     if (nb != h->peers.n_blocks || map.n_out > h->peers.slot_len) return fail("internal: exchange buffer geometry mismatch");
     const int xgrid = nb < 2 * h->n_sm ? nb : 2 * h->n_sm;      // certainly co-resident: <= 2 blocks of 256 threads per SM
-    pinn::reduce_exchange<<<xgrid, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, map, run_flag, h->peers, h->d_xseq,
-                                                      h->d_R, h->d_p2p_err, ad ? 1 : 0, h->d_w, h->d_m, h->d_v, h->P, h->d_step,
-                                                      ad ? ad->lr : 0.0, ad ? ad->b1 : 0.0, ad ? ad->b2 : 0.0, ad ? ad->eps : 0.0,
-                                                      h->d_loss_ring, LOSS_RING);
+    CUDA_TRY(launch_tail_kernel(pinn::reduce_exchange, xgrid, 256, h->stream, h->d_partials, h->last_grid, h->last_stride, map, run_flag,
+                                h->peers, h->d_xseq, h->d_R, h->d_p2p_err, ad ? 1 : 0, h->d_w, h->d_m, h->d_v, h->P, h->d_step,
+                                ad ? ad->lr : 0.0, ad ? ad->b1 : 0.0, ad ? ad->b2 : 0.0, ad ? ad->eps : 0.0, h->d_loss_ring,
+                                LOSS_RING));
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return 0;
   }
-  pinn::reduce_partials<<<nb, 256, 0, h->stream>>>(h->d_partials, h->last_grid, h->last_stride, h->d_R, map, run_flag);
+  CUDA_TRY(launch_tail_kernel(pinn::reduce_partials, nb, 256, h->stream, h->d_partials, h->last_grid, h->last_stride, h->d_R, map, run_flag));
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   // one exchange over [gradient | loss parts].  A skipped evaluation (L-BFGS stopped) still takes part with
@@ -420,11 +441,12 @@ int generic_launch_eval(pinn_t* h, const int* run_flag) {
   const bool nls = h->pde == PINN_NLS_INF, ide = h->pde == PINN_BURGERS_IDE;
   const long long n_total = disc ? h->n_aux : (nls ? h->n_aux + h->n_c : (ide ? h->n_d : h->n_d + h->n_c));
   if (n_total <= 0) return fail("no points set (pinn_set_collocation / pinn_set_data)");
-  const int grid = h->n_cta;
-  const long long per = (n_total + grid - 1) / grid;
+  const long long per = (n_total + h->n_cta - 1) / h->n_cta;
   // points per CTA: a multiple of 16 for large sets; small sets (the discrete-time models have ~250 points) are spread over as
   // many CTAs as possible -- an even count, because NLS boundary pairs (lb_k, ub_k) are adjacent and must not straddle a CTA
   const long long pts = per >= 16 ? (per + 15) / 16 * 16 : (per + 1) / 2 * 2;
+  // only CTAs that own points are launched: every CTA writes (and the tail kernel reads) a full partial vector
+  const int grid = (int)((n_total + pts - 1) / pts);
   pinn::NetDesc nd = net_desc(h);
   int maxw = 0; long long hsum = 0;
   for (int l = 0; l < nd.n_layers - 1; l++) { hsum += 4 * pts * nd.dims[l + 1]; if (nd.dims[l + 1] > maxw) maxw = nd.dims[l + 1]; }
@@ -436,9 +458,9 @@ int generic_launch_eval(pinn_t* h, const int* run_flag) {
     if (h->d_gA) cudaFree(h->d_gA);
     if (h->d_gS) cudaFree(h->d_gS);
     h->d_gH = h->d_gA = h->d_gS = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&h->d_gH, (size_t)grid * hsum * 8));
-    CUDA_TRY(cudaMalloc((void**)&h->d_gA, (size_t)grid * 2 * a_per * 8));
-    CUDA_TRY(cudaMalloc((void**)&h->d_gS, (size_t)grid * 2 * pts * 4 * out_w * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_gH, (size_t)h->n_cta * hsum * 8));          // sized for the largest grid (all CTAs)
+    CUDA_TRY(cudaMalloc((void**)&h->d_gA, (size_t)h->n_cta * 2 * a_per * 8));
+    CUDA_TRY(cudaMalloc((void**)&h->d_gS, (size_t)h->n_cta * 2 * pts * 4 * out_w * 8));
     h->g_pts = pts;
   }
   G::Args a{};
