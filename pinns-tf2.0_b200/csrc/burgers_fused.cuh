@@ -68,7 +68,7 @@ struct Args {
   int ide;                // identification: l1 = w[P_NET], kappa = exp(w[P_NET+1])
   double* partials;       // [gridDim.x][PSTRIDE]
   const int* run_flag;    // optional: skip the whole launch when *run_flag != 0 (L-BFGS stopped on device)
-  int chains;             // v2 only: chain warps (8-point tiles) per CTA round, 1..4 (small point sets use fewer per CTA)
+  int chains;             // unused (kept for ABI stability of the launch struct within this library)
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -33,8 +33,8 @@
 //   Z    = s A - 2 a (a_x A_x + a_t A_t) - 2 A_xx (a a_xx + a_x^2)
 // (algebraically identical to SURVEY Appendix A; no division by s, so saturated units are safe).
 //
-// Small point sets: `chains` (1..4) chain warps per CTA are used, so that e.g. 2000 points (250 tiles) run as 125 CTAs x 2
-// tiles instead of 63 CTAs x 4 -- the latency of a launch is one tile either way, but the sub-partitions are less loaded.
+// Work distribution is tile-granular (8 points): the tiles are dealt evenly to the CTAs and round-robin to a CTA's four chain
+// warps, so the slowest CTA carries at most one tile more than the others and small sets spread over all SMs.
 //
 // Measured and dropped (profiles/kernel_variants_r02.md): 3-slot ring, per-tile-pair ownership 3/2/2/2 (0.451 -> 0.416 ms
 // with row ownership), holding the weight-gradient DMMAs back while the co-resident chain warp is in a DMMA phase
@@ -86,9 +86,9 @@ constexpr int ROUND = CHAINS * TILE;      // 32 points per full CTA round
 constexpr int RING = PINN_RING;           // Z-bar ring slots per chain warp
 
 // shared memory carve-up (doubles)
-constexpr int STASH0 = 160;               // layer 0: a only, [8 rows][20]
+constexpr int STASH0 = 640;               // layer 0: outputs (a, a_x, a_t, a_xx) as [32 rows][20], like the other layers
 constexpr int STASHL = 640;               // layers 1..6: outputs (a, a_x, a_t, a_xx) as [32 rows][20]
-constexpr int STASH_PER_WARP = STASH0 + 6 * STASHL;   // 4000
+constexpr int STASH_PER_WARP = STASH0 + 6 * STASHL;   // 4480
 constexpr int SM_W = 0;
 constexpr int SM_STASH = SM_W + WPAD;
 constexpr int SM_RING = SM_STASH + CHAINS * STASH_PER_WARP;
@@ -98,7 +98,7 @@ constexpr int SM_BAR = SM_RED + CHAINS * RED_PER_WARP;      // 1 + 2*CHAINS*RING
 constexpr int SM_SPECIAL = SM_BAR + 1 + 2 * CHAINS * RING + 1;   // [32 rows][W] page: column 0 = the bias ones-row (1 on the value
                                                                  // stream's rows 0..7), column 1 = 0
 constexpr int SM_DOUBLES = SM_SPECIAL + 32 * W;
-constexpr int SMEM_BYTES = SM_DOUBLES * 8;   // ~201 KB
+constexpr int SMEM_BYTES = SM_DOUBLES * 8;   // ~217 KB
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -211,16 +211,24 @@ __device__ __forceinline__ void load5(double (&V)[4][5], const double* T, int la
 // ---------------------------------------------------------------------------------------------------
 // wgrad warps
 // ---------------------------------------------------------------------------------------------------
-// tile-row ownership, hidden layers 1..7: position k = (wg - l) & 3; k < 3 owns (mt = k; nt = 0,1,2), k == 3 rests.
-__device__ __forceinline__ int owned_row(int l, int wg) {
+// tile-row ownership, hidden layers 1..7: position k = (wg - l) & 3; k < 3 owns row mt = k, k == 3 rests.  7 layers x 3 rows over
+// 4 warps is 6/5/5/5 rows (warp 3 rests only at layer 4); to level that, warp 3 hands the third N tile of its row at layers
+// 1, 2, 3 to the warp that rests there (warps 0, 1, 2): 120/128/128/128 DMMA per chain tile instead of 120/120/120/144.
+// mask: bit nt set = this warp accumulates tile (mt, nt).
+struct Own { int mt, mask; };
+__device__ __forceinline__ Own ownership(int l, int wg) {
   const int k = (wg - l) & 3;
-  return k < 3 ? k : -1;
+  Own o;
+  if (k < 3) { o.mt = k; o.mask = (wg == 3 && l <= 3) ? 3 : 7; }
+  else if (l <= 3) { o.mt = (3 - l) & 3; o.mask = 4; }
+  else { o.mt = 0; o.mask = 0; }
+  return o;
 }
 
 // one weight-gradient task: accumulate this warp's tile row of layer L for one chain warp's 8-point tile.
 // Rows of the staged operands: R = 8*stream + 4*(ks&1) + q for k-step ks (K = 32 rows = 8 k-steps); A[row][i] = input unit i
 // of layer L (i == 20: the bias ones-row on the value stream), B[row][j] = Z-bar.
-template <int L>
+template <int L, int MASK>
 __device__ __forceinline__ void wgrad_task(double (&acc)[3][2], int mt, const double* Aop, const double* ZB, const double* sm,
                                            double sc0, double sc1, int lane) {
   const int g = lane >> 2, q = lane & 3;
@@ -230,46 +238,37 @@ __device__ __forceinline__ void wgrad_task(double (&acc)[3][2], int mt, const do
   const double* bp0 = ZB + g + q * W;
   const double* bp1 = ZB + 8 + g + q * W;
   const double* bp2 = (16 + g < W ? ZB + 16 + g : SP + 1) + q * W;
-  const double* ap = (i < W ? Aop + i : (i == W ? SP : SP + 1)) + q * W;          // L >= 2: [32 rows][W] outputs of layer L-1
-  const double* ap1 = (i < W ? Aop + i : SP + 1) + q * W;                          // L == 1: a-only stash [8 rows][W]
-  // layer-1 inputs are synthesised from the a-only stash of layer 0: per-lane constants of the unit this lane reads
-  const double w0x = (L == 1 && i < W) ? sc0 * Wsm[i] : 0.0;
-  const double w0t = (L == 1 && i < W) ? sc1 * Wsm[W + i] : 0.0;
+  const double* ap = (i < W ? Aop + i : (i == W ? SP : SP + 1)) + q * W;          // [32 rows][W] outputs of layer L-1
 #pragma unroll
   for (int ks = 0; ks < 8; ks++) {
     const int st = ks >> 1;
     const int off = (8 * st + 4 * (ks & 1)) * W;              // physical row 8*stream + 4*(ks&1) (+ q, folded into the pointers)
-    double a;
-    if (L >= 2) {
-      a = ap[off];
-    } else {
-      const double av = ap1[4 * (ks & 1) * W];
-      const double sd = fma(-av, av, 1.0);
-      const double v = st == 0 ? av : (st == 1 ? sd * w0x : (st == 2 ? sd * w0t : -2.0 * av * sd * w0x * w0x));
-      a = (i == W && st == 0) ? 1.0 : v;                      // i >= W: av = 0 and w0x = w0t = 0, so v = 0
-    }
-    const double b0 = bp0[off], b1 = bp1[off], b2 = bp2[off];
-    dmma(acc[0], a, b0);
-    dmma(acc[1], a, b1);
-    dmma(acc[2], a, b2);
+    const double a = ap[off];
+    if (MASK & 1) dmma(acc[0], a, bp0[off]);
+    if (MASK & 2) dmma(acc[1], a, bp1[off]);
+    if (MASK & 4) dmma(acc[2], a, bp2[off]);
   }
 }
 
 template <int L>
-__device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it, int half, int chains, const double* sm,
+__device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it, int half, int cnt, const double* sm,
                                             uint64_t* bars, double sc0, double sc1, int lane) {
   constexpr int J = 7 - L;                  // task index within a tile (layers 7..1)
   const int T = 7 * it + J;
   const int slot = T % RING;
-  const int mt = owned_row(L, wg);
+  const Own o = ownership(L, wg);
 #pragma unroll 1
   for (int c = 2 * half; c < 2 * half + 2; c++) {
-    if (c >= chains) break;                 // chain warps beyond `chains` have no tiles in this launch
+    if (4 * it + c >= cnt) break;           // chain warp c has no tile in this round (the CTA's last round may be partial)
     wait_produced(bars, c, T);
     const double* stash = sm + SM_STASH + c * STASH_PER_WARP;
-    const double* Aop = L >= 2 ? stash + STASH0 + (L - 2) * STASHL : stash;
+    const double* Aop = stash + (L - 1) * STASHL;         // outputs of layer L-1 (STASH0 == STASHL)
     const double* ZB = sm + SM_RING + (c * RING + slot) * 640;
-    if (!PINN_ABL_NOWG && mt >= 0) wgrad_task<L>(acc, mt, Aop, ZB, sm, sc0, sc1, lane);
+    if (!PINN_ABL_NOWG) {                   // warp-uniform: the mask is a function of (layer, warp)
+      if (o.mask == 7) wgrad_task<L, 7>(acc, o.mt, Aop, ZB, sm, sc0, sc1, lane);
+      else if (o.mask == 3) wgrad_task<L, 3>(acc, o.mt, Aop, ZB, sm, sc0, sc1, lane);
+      else if (o.mask == 4) wgrad_task<L, 4>(acc, o.mt, Aop, ZB, sm, sc0, sc1, lane);
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty(bars, c, slot));
   }
@@ -278,16 +277,15 @@ __device__ __forceinline__ void wgrad_layer(double (&acc)[3][2], int wg, int it,
 template <int L>
 __device__ __forceinline__ void wgrad_flush(const double (&acc)[3][2], int wg, double* outp, int lane) {
   const int g = lane >> 2, q = lane & 3;
-  const int mt = owned_row(L, wg);
+  const Own o = ownership(L, wg);
   const int in_dim = W;
-  const int i = 8 * mt + g;
-  if (mt < 0) return;
+  const int i = 8 * o.mt + g;
 #pragma unroll
   for (int nt = 0; nt < 3; nt++)
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const int j = 8 * nt + 2 * q + e;
-      if (j < W) {
+      if (j < W && ((o.mask >> nt) & 1)) {
         if (i < in_dim) outp[woff(L) + i * W + j] = acc[nt][e];
         else if (i == in_dim) outp[boff(L) + j] = acc[nt][e];
       }
@@ -319,10 +317,15 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   mbar_wait(bars, 0);
 
   const double sc0 = 2.0 / p.dx0, sc1 = 2.0 / p.dx1;
-  const int chains = (p.chains >= 1 && p.chains <= CHAINS) ? p.chains : CHAINS;
-  const int round_pts = chains * TILE;
-  const long long n_rounds = (p.n_total + round_pts - 1) / round_pts;
-  const int my_rounds = (int)((n_rounds - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  // Tile-granular distribution: the ceil(n/8) tiles are dealt to the CTAs as evenly as possible (the first `rem` CTAs take one
+  // more), a CTA's tiles j = 0..cnt-1 go to chain warp j & 3 in round j >> 2.  No CTA runs a whole extra round for a few left-over
+  // tiles (N_f = 100 000: 84.5 tiles per CTA = 21.1 rounds instead of 22 for the slowest CTA), and small sets spread over all SMs
+  // (2000 points: 1-2 tiles per CTA).
+  const long long tiles_total = (p.n_total + TILE - 1) / TILE;
+  const long long tbase = tiles_total / gridDim.x, trem = tiles_total - tbase * gridDim.x;
+  const int cnt = (int)(tbase + (blockIdx.x < trem ? 1 : 0));                                  // tiles of this CTA
+  const long long first_tile = tbase * blockIdx.x + (blockIdx.x < trem ? blockIdx.x : trem);
+  const int my_rounds = (cnt + CHAINS - 1) / CHAINS;
   double* outp = p.partials + (size_t)blockIdx.x * PSTRIDE;
 
   if (warp >= CHAINS) {
@@ -340,13 +343,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     // half runs its backward pass and keeps these warps -- and the FP64 pipe of every sub-partition -- busy.
     for (int it2 = 0; it2 < 2 * my_rounds; it2++) {
       const int it = it2 >> 1, half = it2 & 1;
-      wgrad_layer<7>(a7, wg, it, half, chains, sm, bars, sc0, sc1, lane);
-      wgrad_layer<6>(a6, wg, it, half, chains, sm, bars, sc0, sc1, lane);
-      wgrad_layer<5>(a5, wg, it, half, chains, sm, bars, sc0, sc1, lane);
-      wgrad_layer<4>(a4, wg, it, half, chains, sm, bars, sc0, sc1, lane);
-      wgrad_layer<3>(a3, wg, it, half, chains, sm, bars, sc0, sc1, lane);
-      wgrad_layer<2>(a2, wg, it, half, chains, sm, bars, sc0, sc1, lane);
-      wgrad_layer<1>(a1, wg, it, half, chains, sm, bars, sc0, sc1, lane);
+      wgrad_layer<7>(a7, wg, it, half, cnt, sm, bars, sc0, sc1, lane);
+      wgrad_layer<6>(a6, wg, it, half, cnt, sm, bars, sc0, sc1, lane);
+      wgrad_layer<5>(a5, wg, it, half, cnt, sm, bars, sc0, sc1, lane);
+      wgrad_layer<4>(a4, wg, it, half, cnt, sm, bars, sc0, sc1, lane);
+      wgrad_layer<3>(a3, wg, it, half, cnt, sm, bars, sc0, sc1, lane);
+      wgrad_layer<2>(a2, wg, it, half, cnt, sm, bars, sc0, sc1, lane);
+      wgrad_layer<1>(a1, wg, it, half, cnt, sm, bars, sc0, sc1, lane);
     }
     wgrad_flush<1>(a1, wg, outp, lane);
     wgrad_flush<2>(a2, wg, outp, lane);
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   } else {
     // =========================================== chain warps ===========================================
     const int c = warp;
-    const int n_tiles = c < chains ? my_rounds : 0;
+    const int n_tiles = cnt > c ? (cnt - c + CHAINS - 1) / CHAINS : 0;      // tiles j = c, c + 4, ... of this CTA
     double* stash = sm + SM_STASH + c * STASH_PER_WARP;
     const double l1 = p.ide ? Wsm[P_NET] : 1.0;
     const double kap = p.ide ? exp(Wsm[P_NET + 1]) : p.nu;
@@ -374,8 +377,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     // coordinates of this lane's point in tile `it`; the next tile's pair is prefetched one tile ahead so that neither
     // the L2/HBM latency nor (zero-copy mode: p.xc in pinned host memory) the PCIe latency is exposed
     auto load_xt = [&](int it, double& xo, double& to) {
-      const long long rnd = blockIdx.x + (long long)it * gridDim.x;
-      long long pt = rnd * round_pts + c * TILE + g;
+      long long pt = (first_tile + 4 * it + c) * TILE + g;
       if (pt >= p.n_total) pt = p.n_total - 1;
       if (p.xc && pt >= p.c0 && pt < p.c0 + p.n_c) {
         xo = __ldg(p.xc + (pt - p.c0)); to = __ldg(p.tc + (pt - p.c0));
@@ -388,8 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
 
 #pragma unroll 1
     for (int it = 0; it < n_tiles; it++) {
-      const long long rnd = blockIdx.x + (long long)it * gridDim.x;
-      const long long pt = rnd * round_pts + c * TILE + g;
+      const long long pt = (first_tile + 4 * it + c) * TILE + g;
       const bool in_set = pt < p.n_total;
       const double xr = xr_next, tr = tr_next;
       if (it + 1 < n_tiles) load_xt(it + 1, xr_next, tr_next);
@@ -411,15 +412,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         V[3][j] = 0.0;
       }
       act_forward5(V);
-      // the a-only stash of layer 0 is still the A operand of the previous tile's layer-1 task (J = 6): wait until it has
-      // been consumed; consumers retire tasks in order
+      // the stash is still the A operand of the previous tile's weight-gradient tasks: wait until its last one, the layer-1
+      // task (J = 6), has been consumed; consumers retire tasks in order
       if (it > 0) wait_consumed(bars, c, 7 * (it - 1) + 6);
-      {
-        double* r0 = stash + pg * W;
-        *reinterpret_cast<double2*>(r0 + 2 * q) = make_double2(V[0][0], V[0][1]);
-        *reinterpret_cast<double2*>(r0 + 8 + 2 * q) = make_double2(V[0][2], V[0][3]);
-        r0[u5[4]] = V[0][4];
-      }
+      stage5(stash, V, lane);
       // ---------------- hidden layers 1..7: DMMA chain
 #pragma unroll 1
       for (int l = 1; l < NHID; l++) {
@@ -506,22 +502,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           c_to_v5(A, An, lane);
         }
       }
-      // ---------------- backward: layer 0: outputs rebuilt from the a-only stash; its weight gradient is 3 rows (x^, t^, bias)
-      // -- 25 FMAs per lane here instead of 24 DMMAs in a weight-gradient warp
+      // ---------------- backward: layer 0: its weight gradient is 3 rows (x^, t^, bias) -- 25 FMAs per lane here instead of 24
+      // DMMAs in a weight-gradient warp
       {
-        const double* r0 = stash + pg * W;
-        const double2 c0 = *reinterpret_cast<const double2*>(r0 + 2 * q);
-        const double2 c1 = *reinterpret_cast<const double2*>(r0 + 8 + 2 * q);
-        const double av[5] = {c0.x, c0.y, c1.x, c1.y, r0[u5[4]]};
-#pragma unroll
-        for (int j = 0; j < 5; j++) {
-          const double a = av[j], s = fma(-a, a, 1.0);
-          const double zx = sc0 * Wsm[u5[j]], zt = sc1 * Wsm[W + u5[j]];
-          V[0][j] = a;
-          V[1][j] = s * zx;
-          V[2][j] = s * zt;
-          V[3][j] = -2.0 * a * s * zx * zx;
-        }
+        load5(V, stash, lane);
         act_backward5(A, V);
 #pragma unroll
         for (int j = 0; j < 5; j++) {

@@ -47,10 +47,50 @@ struct Args {
   double* scrS;               // [grid][2][pts*4*out]      head outputs, seeds
   long long h_per_cta, a_per_cta;
   int pts, maxw;
+  int dmma;                   // hidden-to-hidden layers on DMMA.8x8x4 (default); 0: plain DFMA everywhere (PINN_GENERIC_DFMA=1)
   double* partials;           // [grid][pstride]: [grad p_net | dl1 dl2 - part0 part1 part2]
   int pstride;
   const int* run_flag;
 };
+
+// ---- DMMA.8x8x4 building block for the hidden layers: operands straight from global memory (the per-CTA scratch is L1/L2
+// resident, the weights come through the read-only path); no shared-memory staging, so it works for any width.
+constexpr int NTW = 4;                       // N tiles (of 8 columns) per work item
+
+// C[s][j] += A_s[8 rows x K] * B[K x 8 columns of tile j],  s = 4 streams sharing the B fragments.
+//   A_s(row g, k) = arow[s * sstride + k]  (arow already points at this lane's row);  B(k, n) = B[k * ldk + n * ldn]
+// k >= K / n >= N contribute zero through B (the A address is clamped, its value is finite).
+__device__ __forceinline__ void dmma_rows(double (&C)[4][NTW][2], const double* arow, size_t sstride, int K, const double* B,
+                                          size_t ldk, size_t ldn, int n0, int N, int ntn, int g, int q) {
+  const int ksteps = (K + 3) >> 2;
+#pragma unroll 2
+  for (int ks = 0; ks < ksteps; ks++) {
+    const int k = 4 * ks + q;
+    const int kc = k < K ? k : K - 1;
+    double a[4], b[NTW];
+#pragma unroll
+    for (int st = 0; st < 4; st++) a[st] = arow[st * sstride + kc];
+#pragma unroll
+    for (int j = 0; j < NTW; j++) {
+      const int n = n0 + 8 * j + g;
+      b[j] = (j < ntn && k < K && n < N) ? __ldg(B + kc * ldk + (size_t)(n < N ? n : N - 1) * ldn) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NTW; j++)
+      if (j < ntn) {
+#pragma unroll
+        for (int st = 0; st < 4; st++) dmma(C[st][j], a[st], b[j]);
+      }
+  }
+}
+
+// work items are handed out through a shared-memory counter (every output element is produced by exactly one warp in a
+// fixed summation order, so the result does not depend on which warp takes which item)
+__device__ __forceinline__ int next_item(int* ctr, int lane) {
+  int it = 0;
+  if (lane == 0) it = atomicAdd(ctr, 1);
+  return __shfl_sync(0xffffffffu, it, 0);
+}
 
 __device__ __forceinline__ void block_reduce_store(double v, double* red, double* dst) {
   v = warp_sum(v);
@@ -67,9 +107,11 @@ __device__ __forceinline__ void block_reduce_store(double v, double* red, double
 
 __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
   __shared__ double red[THREADS / 32];
+  __shared__ int work_ctr;
   pdl_launch_dependents();                 // the tail kernel's blocks may be placed as SMs free up; they park in pdl_wait()
   if (p.run_flag && *p.run_flag != 0) return;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
   const NetDesc& nd = p.nd;
   const int L = nd.n_layers;                 // Dense layers; hidden 0..L-2, head L-1
   const int out = nd.dims[L];
@@ -104,6 +146,45 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
     const double* Hp = l > 0 ? Hs + hoff[l - 1] : nullptr;
     double* Ho = Hs + hoff[l];
     const size_t sp = (size_t)pts * fi, so = (size_t)pts * fo;
+    if (l > 0 && p.dmma) {
+      // [4 streams x 8 points] x [fi x fo] on the tensor pipe: item = (group of 8 points, group of <= NTW column tiles)
+      const int nt = (fo + 7) >> 3, ngrp = (nt + NTW - 1) / NTW, tpg = (nt + ngrp - 1) / ngrp;
+      const int items = ((npts + 7) >> 3) * ngrp;
+      if (tid == 0) work_ctr = 0;
+      __syncthreads();
+      for (int it = next_item(&work_ctr, lane); it < items; it = next_item(&work_ctr, lane)) {
+        const int pgp = it / ngrp, grp = it - pgp * ngrp;
+        const int n0 = 8 * grp * tpg, ntn = min(tpg, nt - grp * tpg);
+        const int pt = 8 * pgp + g, ptc = pt < npts ? pt : npts - 1;
+        double C[4][NTW][2];
+#pragma unroll
+        for (int j = 0; j < NTW; j++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int u = n0 + 8 * j + 2 * q + e;
+            C[0][j][e] = (j < ntn && u < fo) ? __ldg(bl + u) : 0.0;
+            C[1][j][e] = C[2][j][e] = C[3][j][e] = 0.0;
+          }
+        dmma_rows(C, Hp + (size_t)ptc * fi, sp, fi, Wl, fo, 1, n0, fo, ntn, g, q);
+        if (pt < npts) {
+#pragma unroll
+          for (int j = 0; j < NTW; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int u = n0 + 8 * j + 2 * q + e;
+              if (j < ntn && u < fo) {
+                const double a = tanh_fast(C[0][j][e]);
+                const double sd = fma(-a, a, 1.0), zx = C[1][j][e];
+                double* o = Ho + (size_t)pt * fo + u;
+                o[0] = a;
+                o[so] = sd * zx;
+                o[2 * so] = sd * C[2][j][e];
+                o[3 * so] = sd * fma(-2.0 * a * zx, zx, C[3][j][e]);
+              }
+            }
+        }
+      }
+    } else
     for (int idx = tid; idx < npts * fo; idx += THREADS) {
       const int pt = idx / fo, j = idx - pt * fo;
       double z = __ldg(bl + j), zx = 0.0, zt = 0.0, zxx = 0.0;
@@ -334,6 +415,85 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
       Aoth[3 * so + q] = s * Bxx;
     }
     __syncthreads();
+    if (l > 0 && p.dmma) {
+      // (2)+(3) on the tensor pipe, one item list: weight-gradient items (long: K = 4 streams x points) first, then the
+      // input-adjoint items.  Both only read Z-bar (Aoth), the layer inputs and W_l; the adjoint overwrites Acur.
+      const int nto = (fo + 7) >> 3, ngo = (nto + NTW - 1) / NTW, tpo = (nto + ngo - 1) / ngo;     // column tiles over fo
+      const int nti = (fi + 7) >> 3, ngi = (nti + NTW - 1) / NTW, tpi = (nti + ngi - 1) / ngi;     // column tiles over fi
+      const int mt_w = (fi + 1 + 7) >> 3;                                                          // row tiles of [W_l ; b_l]
+      const int items_w = mt_w * ngo, items = items_w + ((npts + 7) >> 3) * ngi;
+      if (tid == 0) work_ctr = 0;
+      __syncthreads();
+      for (int it = next_item(&work_ctr, lane); it < items; it = next_item(&work_ctr, lane)) {
+        if (it < items_w) {
+          // G[i][j] = sum_{s, pt} Hin[s][pt][i] Z[s][pt][j];  row fi: ones on the value stream (bias)
+          const int mt = it / ngo, grp = it - mt * ngo;
+          const int n0 = 8 * grp * tpo, ntn = min(tpo, nto - grp * tpo);
+          const int i = 8 * mt + g, ic = i < fi ? i : fi - 1;
+          double G[NTW][2];
+#pragma unroll
+          for (int j = 0; j < NTW; j++) G[j][0] = G[j][1] = 0.0;
+          int nc[NTW];
+#pragma unroll
+          for (int j = 0; j < NTW; j++) { const int n = n0 + 8 * j + g; nc[j] = n < fo ? n : fo - 1; }
+          for (int st = 0; st < 4; st++) {
+            const double* hp = Hp + st * sp + ic;
+            const double* zp = Aoth + st * so;
+            const double one = st == 0 ? 1.0 : 0.0;
+#pragma unroll 2
+            for (int pt0 = 0; pt0 < npts; pt0 += 4) {
+              const int pt = pt0 + q;
+              const bool ok = pt < npts;
+              const size_t ptc = ok ? pt : npts - 1;
+              const double hv = hp[ptc * fi];
+              const double a = i == fi ? one : hv;                 // rows beyond fi are never stored
+              double b[NTW];
+#pragma unroll
+              for (int j = 0; j < NTW; j++) b[j] = (ok && j < ntn) ? zp[ptc * fo + nc[j]] : 0.0;
+#pragma unroll
+              for (int j = 0; j < NTW; j++)
+                if (j < ntn) dmma(G[j], a, b[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < NTW; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int n = n0 + 8 * j + 2 * q + e;
+              if (j < ntn && n < fo) {
+                if (i < fi) outp[nd.woff[l] + i * fo + n] = G[j][e];
+                else if (i == fi) outp[nd.boff[l] + n] = G[j][e];
+              }
+            }
+        } else {
+          // A-bar[l-1][s][pt][i] = sum_j Z[s][pt][j] W_l[i][j]
+          const int ia = it - items_w;
+          const int pgp = ia / ngi, grp = ia - pgp * ngi;
+          const int n0 = 8 * grp * tpi, ntn = min(tpi, nti - grp * tpi);
+          const int pt = 8 * pgp + g, ptc = pt < npts ? pt : npts - 1;
+          double C[4][NTW][2];
+#pragma unroll
+          for (int st = 0; st < 4; st++)
+#pragma unroll
+            for (int j = 0; j < NTW; j++) C[st][j][0] = C[st][j][1] = 0.0;
+          dmma_rows(C, Aoth + (size_t)ptc * fo, so, fo, Wl, 1, fo, n0, fi, ntn, g, q);
+          if (pt < npts) {
+#pragma unroll
+            for (int j = 0; j < NTW; j++)
+#pragma unroll
+              for (int e = 0; e < 2; e++) {
+                const int i = n0 + 8 * j + 2 * q + e;
+                if (j < ntn && i < fi) {
+                  double* a = Acur + (size_t)pt * fi + i;
+                  a[0] = C[0][j][e]; a[sp] = C[1][j][e]; a[2 * sp] = C[2][j][e]; a[3 * sp] = C[3][j][e];
+                }
+              }
+          }
+        }
+      }
+      __syncthreads();
+      continue;
+    }
     // (2) weight gradient: thread per entry (i, j), i == fi is the bias
     for (int e = tid; e < (fi + 1) * fo; e += THREADS) {
       const int i = e / fo, j = e - i * fo;

@@ -375,19 +375,12 @@ int burgers_launch_eval(pinn_t* h, const int* run_flag) {
   a.nu = h->nu; a.ide = ide ? 1 : 0;
   a.partials = h->d_partials;
   a.run_flag = run_flag;
-  // v2: few points -> fewer chain warps per CTA and more CTAs (a launch then lasts one tile on lightly loaded SMs)
-  int chains = 4;
-  if (h->burgers_kernel >= 2) {
-    const long long n_tiles = (n_total + B::TILE - 1) / B::TILE;
-    if (n_tiles < 4LL * h->n_cta) {
-      chains = (int)((n_tiles + h->n_cta - 1) / h->n_cta);
-      if (chains < 1) chains = 1;
-    }
-  }
-  a.chains = chains;
-  const long long round_pts = (long long)chains * B::TILE;
-  const long long rounds = (n_total + round_pts - 1) / round_pts;
-  int grid = (int)(rounds < h->n_cta ? rounds : h->n_cta);
+  // v2: tile-granular distribution inside the kernel (any grid <= tiles); v1: rounds of 32 points striped over the CTAs
+  a.chains = 4;
+  const long long n_tiles = (n_total + B::TILE - 1) / B::TILE;
+  const long long rounds = (n_total + B::ROUND - 1) / B::ROUND;
+  const long long units = h->burgers_kernel == 2 ? n_tiles : rounds;
+  int grid = (int)(units < h->n_cta ? units : h->n_cta);
   if (h->burgers_kernel == 2)
     pinn::burgers2::fused_loss_grad<<<grid, pinn::burgers2::THREADS, pinn::burgers2::SMEM_BYTES, h->stream>>>(a);
   else
@@ -482,6 +475,8 @@ int generic_launch_eval(pinn_t* h, const int* run_flag) {
   a.scrH = h->d_gH; a.scrA = h->d_gA; a.scrS = h->d_gS;
   a.h_per_cta = hsum; a.a_per_cta = a_per;
   a.pts = (int)pts; a.maxw = maxw;
+  static const bool generic_dfma = [] { const char* e = getenv("PINN_GENERIC_DFMA"); return e && e[0] == '1'; }();
+  a.dmma = generic_dfma ? 0 : 1;
   a.partials = h->d_partials; a.pstride = h->pstride; a.run_flag = run_flag;
   G::fused_loss_grad<<<grid, G::THREADS, 0, h->stream>>>(a);
   CUDA_TRY(cudaGetLastError());
