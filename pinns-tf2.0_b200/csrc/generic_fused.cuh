@@ -62,19 +62,40 @@ constexpr int NTW = 4;                       // N tiles (of 8 columns) per work 
 // k >= K / n >= N contribute zero through B (the A address is clamped, its value is finite).
 __device__ __forceinline__ void dmma_rows(double (&C)[4][NTW][2], const double* arow, size_t sstride, int K, const double* B,
                                           size_t ldk, size_t ldn, int n0, int N, int ntn, int g, int q) {
-  const int ksteps = (K + 3) >> 2;
-#pragma unroll 2
-  for (int ks = 0; ks < ksteps; ks++) {
-    const int k = 4 * ks + q;
-    const int kc = k < K ? k : K - 1;
+  const double* bp[NTW];
+  bool bok[NTW];
+#pragma unroll
+  for (int j = 0; j < NTW; j++) {
+    const int n = n0 + 8 * j + g;
+    bok[j] = j < ntn && n < N;
+    bp[j] = B + (size_t)(n < N ? n : N - 1) * ldn;
+  }
+  const double* ap = arow + q;
+  const int kfull = K >> 2;
+  // full k-steps: no guard on k
+#pragma unroll 4
+  for (int ks = 0; ks < kfull; ks++) {
+    double a[4], b[NTW];
+#pragma unroll
+    for (int st = 0; st < 4; st++) a[st] = ap[st * sstride + 4 * ks];
+#pragma unroll
+    for (int j = 0; j < NTW; j++) b[j] = bok[j] ? __ldg(bp[j] + (size_t)(4 * ks + q) * ldk) : 0.0;
+#pragma unroll
+    for (int j = 0; j < NTW; j++)
+      if (j < ntn) {
+#pragma unroll
+        for (int st = 0; st < 4; st++) dmma(C[st][j], a[st], b[j]);
+      }
+  }
+  if (K & 3) {
+    const int k = 4 * kfull + q;
+    const bool kok = k < K;
+    const int kc = kok ? k : K - 1;
     double a[4], b[NTW];
 #pragma unroll
     for (int st = 0; st < 4; st++) a[st] = arow[st * sstride + kc];
 #pragma unroll
-    for (int j = 0; j < NTW; j++) {
-      const int n = n0 + 8 * j + g;
-      b[j] = (j < ntn && k < K && n < N) ? __ldg(B + kc * ldk + (size_t)(n < N ? n : N - 1) * ldn) : 0.0;
-    }
+    for (int j = 0; j < NTW; j++) b[j] = (bok[j] && kok) ? __ldg(bp[j] + (size_t)kc * ldk) : 0.0;
 #pragma unroll
     for (int j = 0; j < NTW; j++)
       if (j < ntn) {
@@ -399,6 +420,11 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
     const double* Ho = Hs + hoff[l];
     const double* Hp = l > 0 ? Hs + hoff[l - 1] : nullptr;
     const size_t so = (size_t)pts * fo, sp = (size_t)pts * fi;
+    // the layer inputs were written a whole forward pass ago: start pulling them towards L2 for the weight gradient below
+    if (l > 0 && p.dmma && tid == 0) {
+      const size_t bytes = (size_t)4 * pts * fi * 8;
+      for (size_t o = 0; o < bytes; o += 65536) prefetch_l2_bulk(reinterpret_cast<const char*>(Hp) + o, (uint32_t)min((size_t)65536, bytes - o));
+    }
     // (1) Z-bar
     for (int idx = tid; idx < npts * fo; idx += THREADS) {
       const size_t q = idx;                               // == pt*fo + j
@@ -436,20 +462,32 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
           int nc[NTW];
 #pragma unroll
           for (int j = 0; j < NTW; j++) { const int n = n0 + 8 * j + g; nc[j] = n < fo ? n : fo - 1; }
+          const int kfull = npts >> 2;
           for (int st = 0; st < 4; st++) {
-            const double* hp = Hp + st * sp + ic;
-            const double* zp = Aoth + st * so;
+            const double* hq = Hp + st * sp + ic + (size_t)q * fi;           // row pt0 + q of the layer inputs
+            const double* zq = Aoth + st * so + (size_t)q * fo;              // ... and of Z-bar
             const double one = st == 0 ? 1.0 : 0.0;
-#pragma unroll 2
-            for (int pt0 = 0; pt0 < npts; pt0 += 4) {
-              const int pt = pt0 + q;
-              const bool ok = pt < npts;
-              const size_t ptc = ok ? pt : npts - 1;
-              const double hv = hp[ptc * fi];
-              const double a = i == fi ? one : hv;                 // rows beyond fi are never stored
+            const bool bias_row = i == fi;                                   // rows beyond fi are never stored
+#pragma unroll 4
+            for (int kk = 0; kk < kfull; kk++) {
+              const double hv = hq[(size_t)(4 * kk) * fi];
+              const double a = bias_row ? one : hv;
               double b[NTW];
 #pragma unroll
-              for (int j = 0; j < NTW; j++) b[j] = (ok && j < ntn) ? zp[ptc * fo + nc[j]] : 0.0;
+              for (int j = 0; j < NTW; j++) b[j] = j < ntn ? zq[(size_t)(4 * kk) * fo + nc[j]] : 0.0;
+#pragma unroll
+              for (int j = 0; j < NTW; j++)
+                if (j < ntn) dmma(G[j], a, b[j]);
+            }
+            if (npts & 3) {
+              const int pt = 4 * kfull + q;
+              const bool ok = pt < npts;
+              const size_t ptc = ok ? pt : npts - 1;
+              const double hv = Hp[st * sp + ic + ptc * fi];
+              const double a = bias_row ? one : hv;
+              double b[NTW];
+#pragma unroll
+              for (int j = 0; j < NTW; j++) b[j] = (ok && j < ntn) ? Aoth[st * so + ptc * fo + nc[j]] : 0.0;
 #pragma unroll
               for (int j = 0; j < NTW; j++)
                 if (j < ntn) dmma(G[j], a, b[j]);

@@ -10,11 +10,14 @@
 //             cp.async (double buffered); DMMA GEMM [64 rows x 100] x [100 x 100]; tanh + Taylor streams in the
 //             epilogue;                                                outputs -> scratch H[l]
 //   OUT       head (100 -> 2), residuals f_u, f_v, initial/boundary terms, loss parts, seeds; head gradient
-//   B3..B1    per round: Z-bar from (H[l], A-bar[l]) -> smem; input adjoint A-bar[l-1] = Z-bar W_l^T (DMMA);
-//             weight gradient G_l += H[l-1]^T Z-bar (DMMA, K = 64 rows per round).  The 13x13 output tiles of G_l
-//             are OWNED by warps, so their accumulators stay in registers for the whole pass over the CTA's points
-//             and are written once (bias gradient = virtual ones-row 100).
-//   B0        layer-0 gradient, direct.
+//   B3..B1    per round: Z-bar[l] (activation adjoint of layer l, from scratch) and H[l-1] stream in through cp.async;
+//             input adjoint A-bar[l-1] = Z-bar W_l^T (DMMA) stays in registers and is turned into Z-bar[l-1] in the
+//             epilogue with the H[l-1] values of the staged slab -> scratch (so A-bar never round-trips through global
+//             memory and H[l] is not re-read);  weight gradient G_l += H[l-1]^T Z-bar (DMMA, K = 64 rows per round).
+//             The 13x13 output tiles of G_l are OWNED by warps, so their accumulators stay in registers for the whole
+//             pass over the CTA's points and are written once (bias gradient = virtual ones-row 100).
+//             Z-bar[3] comes out of the head phase (same loop as the head gradient).
+//   B0        layer-0 gradient from Z-bar[0], direct.
 // The activations (4 streams x 100 units x 4 layers = 12.8 KB per point) live in a per-CTA global scratch that is
 // streamed, not re-read: algorithmic HBM traffic is 16 B/point, implementation traffic ~67 KB/point.
 //
@@ -47,8 +50,7 @@ constexpr int SM_W = 0;
 constexpr int SM_S0 = SM_W + W * W;
 constexpr int SM_S1 = SM_S0 + SLAB;
 constexpr int SM_RED = SM_S1 + SLAB;
-constexpr int SM_W4 = SM_RED + 64;        // head weights W_4 (100 x 2): read per element by the layer-3 adjoint epilogue
-constexpr int SM_BAR = SM_W4 + 2 * W;
+constexpr int SM_BAR = SM_RED + 64;
 constexpr int SM_DOUBLES = SM_BAR + 2;
 constexpr int SMEM_BYTES = SM_DOUBLES * 8;     // 182,928 B
 
@@ -130,6 +132,21 @@ __device__ __forceinline__ void load_weights_tma(double* Wsm, const double* src,
   }
   mbar_wait(bar, phase);
   phase ^= 1;
+}
+
+// activation adjoint of one tanh unit carried with its (value, x, t, xx) streams (division-free form):
+// outputs (a, a_x, a_t, a_xx), adjoint of the outputs (A0, Ax, At, Axx)  ->  adjoint of the pre-activation streams
+__device__ __forceinline__ void zbar(double (&z)[4], double a, double ax, double at, double axx, double A0, double Ax, double At,
+                                     double Axx) {
+  const double s = fma(-a, a, 1.0);
+  const double u1 = fma(ax, Ax, at * At);
+  const double u2 = fma(a, axx, ax * ax);
+  double zz = fma(-2.0 * a, u1, s * A0);
+  zz = fma(-2.0 * Axx, u2, zz);
+  z[0] = zz;
+  z[1] = fma(-4.0 * a * ax, Axx, s * Ax);
+  z[2] = s * At;
+  z[3] = s * Axx;
 }
 
 __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
@@ -319,20 +336,31 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       outp[IDX_L0 + tid] = s;
     }
     // head gradient: G4[k][o] = sum_pt sum_s H3[s][pt][k] seed[pt][s][o];  bias: sum_pt seed[pt][0][o]
+    // and, from the same H3 values, the activation adjoint of the last hidden layer:
+    //   A-bar[3][s][pt][k] = sum_o seed[pt][s][o] W4[k][o]  ->  Z-bar[3]  (scratch buffer 1; padded points have zero seeds)
     {
       const int k = tid & 127, half = tid >> 7;
       const int npad = nrounds * RPTS;
       const int p0 = half * (npad / 2), p1 = half ? npad : npad / 2;
       double g0 = 0.0, g1 = 0.0, gb = 0.0;
       if (k < W) {
-#pragma unroll 4
+        const double w40 = __ldg(W4 + 2 * k), w41 = __ldg(W4 + 2 * k + 1);
+        double* Z3 = A + (size_t)4 * SSZ;
+#pragma unroll 2
         for (int pt = p0; pt < p1; pt++) {
+          double hv[4], ab[4];
 #pragma unroll
           for (int s = 0; s < 4; s++) {
-            const double hv = H3[s * SSZ + (size_t)pt * W + k];
-            g0 = fma(hv, SEED[pt * 8 + 2 * s], g0);
-            g1 = fma(hv, SEED[pt * 8 + 2 * s + 1], g1);
+            hv[s] = H3[s * SSZ + (size_t)pt * W + k];
+            const double s0 = SEED[pt * 8 + 2 * s], s1 = SEED[pt * 8 + 2 * s + 1];
+            g0 = fma(hv[s], s0, g0);
+            g1 = fma(hv[s], s1, g1);
+            ab[s] = fma(s0, w40, s1 * w41);
           }
+          double z[4];
+          zbar(z, hv[0], hv[1], hv[2], hv[3], ab[0], ab[1], ab[2], ab[3]);
+#pragma unroll
+          for (int s = 0; s < 4; s++) Z3[s * SSZ + (size_t)pt * W + k] = z[s];
         }
       } else if (k < W + 2) {
         for (int pt = p0; pt < p1; pt++) gb += SEED[pt * 8 + (k - W)];
@@ -361,14 +389,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   const int n_first = wide ? 0 : 7;
   const int sn0 = 3 * wb;                        // strip: first N tile
   const int snn = wide ? 0 : (wb == 3 ? 4 : 3);  // strip: number of N tiles
-  for (int i = tid; i < 2 * W; i += THREADS) sm[SM_W4 + i] = __ldg(p.w + woff(4) + i);
   for (int l = 3; l >= 1; l--) {
     load_weights_tma(Wsm, p.w + woff(l), bar, wphase);
-    const double* Hl = H + (size_t)l * LSZ;              // outputs of layer l (for the activation adjoint)
-    const double* Hin = H + (size_t)(l - 1) * LSZ;       // inputs of layer l (A operand of the weight gradient)
-    const double* Ain = A + (size_t)((l & 1) ? 0 : 1) * 4 * SSZ;    // adjoint of layer-l outputs (l < 3)
-    double* Aout = A + (size_t)((l & 1) ? 1 : 0) * 4 * SSZ;         // adjoint of layer-(l-1) outputs
-    const double* W4 = sm + SM_W4;
+    const double* Hin = H + (size_t)(l - 1) * LSZ;                  // inputs of layer l: A operand of the weight gradient, and
+                                                                     // the outputs the activation adjoint of layer l-1 needs
+    const double* Zin = A + (size_t)(l & 1) * 4 * SSZ;               // Z-bar[l]   (written by the head phase / the pass above)
+    double* Zout = A + (size_t)((l & 1) ^ 1) * 4 * SSZ;              // Z-bar[l-1]
     double G[3][7][2], GS[4][2];
 #pragma unroll
     for (int m = 0; m < 3; m++)
@@ -377,83 +403,43 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
 #pragma unroll
     for (int n = 0; n < 4; n++) GS[n][0] = GS[n][1] = 0.0;
 
+    // cp.async groups are committed in the order Z_0, H_0, [per round: (L2 prefetch), Z_{r+1}+H_{r+1}]
+    if (nrounds > 0) {
+      stage_round(S1, Zin, pts, 0); cp_async_commit();
+      stage_round(S0, Hin, pts, 0); cp_async_commit();
+    }
     for (int r = 0; r < nrounds; r++) {
-      // (1) stage the layer inputs of this round (A operand of the weight gradient)
-      stage_round(S0, Hin, pts, r * RPTS);
-      cp_async_commit();
-      // (2) activation adjoint Z-bar for this lane's point and units -> S1 (row layout)
       const int pt = r * RPTS + myp;
-#pragma unroll
-      for (int jb = 0; jb < 4; jb += 2) {
-        // issue the global loads of two N tiles back to back, then do the arithmetic (hides the L2/HBM latency)
-        double hv[2][4][2], av[2][4][2];
-#pragma unroll
-        for (int jj = 0; jj < 2; jj++) {
-          const int j = jb + jj;
-          const int u = 8 * (nt0 + j) + 2 * q;
-          const bool on = j < ntn && u < W;
-#pragma unroll
-          for (int s = 0; s < 4; s++) {
-            double2 h2 = make_double2(0.0, 0.0), a2 = make_double2(0.0, 0.0);
-            if (on) {
-              h2 = *reinterpret_cast<const double2*>(Hl + s * SSZ + (size_t)pt * W + u);
-              if (l == 3) {
-                // adjoint of the last hidden layer's outputs straight from the seeds: A[s][u] = sum_o seed[s][o] W4[u][o]
-                const double s0 = SEED[pt * 8 + 2 * s], s1 = SEED[pt * 8 + 2 * s + 1];
-                a2.x = fma(s0, W4[2 * u], s1 * W4[2 * u + 1]);
-                a2.y = fma(s0, W4[2 * u + 2], s1 * W4[2 * u + 3]);
-              } else {
-                a2 = *reinterpret_cast<const double2*>(Ain + s * SSZ + (size_t)pt * W + u);
-              }
-            }
-            hv[jj][s][0] = h2.x; hv[jj][s][1] = h2.y;
-            av[jj][s][0] = a2.x; av[jj][s][1] = a2.y;
-          }
-        }
-#pragma unroll
-        for (int jj = 0; jj < 2; jj++) {
-          const int j = jb + jj;
-          const int u = 8 * (nt0 + j) + 2 * q;
-          if (j < ntn && u < W) {
-            double z[4][2];
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const double a = hv[jj][0][e], ax = hv[jj][1][e], at = hv[jj][2][e], axx = hv[jj][3][e];
-              const double A0 = av[jj][0][e], Ax = av[jj][1][e], At = av[jj][2][e], Axx = av[jj][3][e];
-              const double s = fma(-a, a, 1.0);
-              const double u1 = fma(ax, Ax, at * At);
-              const double u2 = fma(a, axx, ax * ax);
-              double zz = fma(-2.0 * a, u1, s * A0);
-              zz = fma(-2.0 * Axx, u2, zz);
-              z[0][e] = zz;
-              z[1][e] = fma(-4.0 * a * ax, Axx, s * Ax);
-              z[2][e] = s * At;
-              z[3][e] = s * Axx;
-            }
-#pragma unroll
-            for (int s = 0; s < 4; s++)
-              *reinterpret_cast<double2*>(S1 + (16 * s + myp) * W + u) = make_double2(z[s][0], z[s][1]);
-          }
-        }
+      // pull the next round's slabs towards L2 while this round computes (they are loaded into S1/S0 when the round is over)
+      if (tid < 8 && r + 1 < nrounds) {
+        const double* src = (tid < 4 ? Zin : Hin) + (size_t)(tid & 3) * SSZ + (size_t)(r + 1) * RPTS * W;
+        prefetch_l2_bulk(src, RPTS * W * 8);
       }
-      cp_async_wait<0>();
+      cp_async_wait<1>();                            // Z_r has landed (H_r may still be in flight)
       __syncthreads();
       // (3) input adjoint: A-bar[l-1] = Z-bar * W_l^T   (K = units of layer l)
-      {
-        double C[4][4][2];
+      double C[4][4][2];
 #pragma unroll
-        for (int s = 0; s < 4; s++)
+      for (int s = 0; s < 4; s++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) C[s][j][0] = C[s][j][1] = 0.0;
-        gemm_rows(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
+        for (int j = 0; j < 4; j++) C[s][j][0] = C[s][j][1] = 0.0;
+      gemm_rows(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
+      cp_async_wait<0>();                            // H_r
+      __syncthreads();
+      // (3b) Z-bar[l-1] for this lane's point and units from A-bar (registers) and H[l-1] (slab S0) -> scratch
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int u = 8 * (nt0 + j) + 2 * q;
-          if (j < ntn && u < W) {
+      for (int j = 0; j < 4; j++) {
+        const int u = 8 * (nt0 + j) + 2 * q;
+        if (j < ntn && u < W) {
+          double2 h[4];
 #pragma unroll
-            for (int s = 0; s < 4; s++)
-              *reinterpret_cast<double2*>(Aout + s * SSZ + (size_t)pt * W + u) = make_double2(C[s][j][0], C[s][j][1]);
-          }
+          for (int s = 0; s < 4; s++) h[s] = *reinterpret_cast<const double2*>(S0 + (16 * s + myp) * W + u);
+          double z0[4], z1[4];
+          zbar(z0, h[0].x, h[1].x, h[2].x, h[3].x, C[0][j][0], C[1][j][0], C[2][j][0], C[3][j][0]);
+          zbar(z1, h[0].y, h[1].y, h[2].y, h[3].y, C[0][j][1], C[1][j][1], C[2][j][1], C[3][j][1]);
+#pragma unroll
+          for (int s = 0; s < 4; s++)
+            *reinterpret_cast<double2*>(Zout + s * SSZ + (size_t)pt * W + u) = make_double2(z0[s], z1[s]);
         }
       }
       // (4) weight gradient: G[i][j] += sum_rows S0[row][i] * S1[row][j]   (unit i == 100: ones on the value stream)
@@ -488,6 +474,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         }
       }
       __syncthreads();
+      if (r + 1 < nrounds) {
+        stage_round(S1, Zin, pts, (r + 1) * RPTS); cp_async_commit();
+        stage_round(S0, Hin, pts, (r + 1) * RPTS); cp_async_commit();
+      }
     }
     // (5) flush this warp's tiles of G_l
 #pragma unroll
@@ -527,7 +517,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   {
     // warp w takes the points pt = w, w+8, ...; lane covers units lane, lane+32, lane+64, lane+96 (coalesced rows);
     // many independent loads in flight per thread, then a fixed-order combine over the 8 warps.
-    const double* A0 = A + (size_t)1 * 4 * SSZ;            // written by l = 1
+    const double* Z0 = A;                                  // Z-bar[0]: scratch buffer 0, written by the l = 1 pass
     double gx[4] = {0, 0, 0, 0}, gt[4] = {0, 0, 0, 0}, gb[4] = {0, 0, 0, 0};
     const int npad = nrounds * RPTS;
 #pragma unroll 2
@@ -540,15 +530,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         const int u = lane + 32 * c;
         if (u < W) {
           const size_t o = (size_t)pt * W + u;
-          const double a = H[o], ax = H[SSZ + o], at = H[2 * SSZ + o], axx = H[3 * SSZ + o];
-          const double B0 = A0[o], Bx = A0[SSZ + o], Bt = A0[2 * SSZ + o], Bxx = A0[3 * SSZ + o];
-          const double s = fma(-a, a, 1.0);
-          const double u1 = fma(ax, Bx, at * Bt);
-          const double u2 = fma(a, axx, ax * ax);
-          double z = fma(-2.0 * a, u1, s * B0);
-          z = fma(-2.0 * Bxx, u2, z);
-          const double zbx = fma(-4.0 * a * ax, Bxx, s * Bx);
-          const double zbt = s * Bt;
+          const double z = Z0[o], zbx = Z0[SSZ + o], zbt = Z0[2 * SSZ + o];
           gx[c] = fma(xh, z, fma(sc0, zbx, gx[c]));
           gt[c] = fma(th, z, fma(sc1, zbt, gt[c]));
           gb[c] += z;

@@ -8,6 +8,8 @@ from bench import synthetic_problem, init_weights, LB, UB, NU, ADAM_LR, timed_ad
 out = {}
 for name, L, n in [("8x40", [2] + [40] * 8 + [1], 20000), ("8x40_100k", [2] + [40] * 8 + [1], 100000), ("4x100", [2] + [100] * 4 + [1], 20000),
                    ("8x20g", [2] + [20] * 8 + [1], 100000), ("3x50", [2, 50, 50, 50, 1], 20000)]:
+    if len(sys.argv) > 1 and name not in sys.argv[1:]:
+        continue
     if name == "8x20g":
         os.environ["PINN_FORCE_GENERIC"] = "1"
     X_f, X_u, u = synthetic_problem(40, n)

@@ -29,7 +29,8 @@ def rand_w(layers, seed):
 
 
 @pytest.mark.parametrize("layers,n_f,n_u", [([2, 10, 10, 1], 333, 17), ([2, 37, 5, 64, 1], 1000, 100),
-                                             ([2] + [8] * 12 + [1], 77, 5), ([2, 128, 1], 2000, 0), ([2, 20, 20, 20, 1], 1, 1)])
+                                             ([2] + [8] * 12 + [1], 77, 5), ([2, 128, 1], 2000, 0), ([2, 20, 20, 20, 1], 1, 1),
+                                             ([2] + [40] * 8 + [1], 1500, 60), ([2, 50, 50, 50, 1], 90, 9), ([2, 3, 7, 1], 50, 4)])
 def test_burgers_any_layers(cabi, layers, n_f, n_u):
     from oracle import taylor as ty
     rng = np.random.default_rng(len(layers) * 100 + n_f)
@@ -112,3 +113,40 @@ def test_generic_net_trains_like_the_oracle(cabi):
                              tol_fun=np.finfo(float).eps)
     r = p.lbfgs(5, learning_rate=0.8, n_correction=50, tol_fun=np.finfo(float).eps, want_x_final=True)
     assert r["n_iter"] == tr.n_iter and rel(r["x_final"], tr.x_final) < 1e-7
+
+
+def test_tensor_core_and_dfma_forms_of_the_hidden_layers_agree():
+    """The generic kernel runs its hidden-to-hidden layers on DMMA.8x8x4 by default; PINN_GENERIC_DFMA=1 keeps the plain DFMA
+    form.  Same inputs, both forms, upstream's 8 x 40 net and an odd-width one: loss and gradient agree to rounding."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r'''
+import os, sys, json, numpy as np
+ROOT = %r
+sys.path[:0] = [ROOT, os.path.join(ROOT, "pinns-tf2.0_b200", "utils")]
+import pinn_cabi
+out = {}
+for name, layers, n_f in (("8x40", [2] + [40] * 8 + [1], 3001), ("odd", [2, 37, 5, 64, 13, 1], 777)):
+    rng = np.random.default_rng(5)
+    lb, ub = np.array([-1.0, 0.0]), np.array([1.0, 0.99])
+    X_f = lb + (ub - lb) * rng.random((n_f, 2)); X_u = lb + (ub - lb) * rng.random((40, 2)); u = rng.uniform(-1, 1, (40, 1))
+    P = sum(layers[i] * layers[i + 1] + layers[i + 1] for i in range(len(layers) - 1))
+    w = 0.3 * rng.standard_normal(P)
+    p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, layers, lb, ub)
+    p.set_pde_params([0.01 / np.pi]); p.set_collocation(X_f[:, 0], X_f[:, 1]); p.set_data(X_u, u)
+    loss, grad, parts = p.loss_grad(w=w)
+    out[name] = {"loss": loss, "grad": np.asarray(grad).tolist()}
+print(json.dumps(out))
+''' % ROOT
+    res = {}
+    for mode in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PINN_GENERIC_DFMA=mode), capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    for name in ("8x40", "odd"):
+        a, b = res["0"][name], res["1"][name]
+        assert abs(a["loss"] - b["loss"]) <= 1e-12 * abs(b["loss"]) and rel(a["grad"], b["grad"]) < 1e-12
+        assert a["grad"] != b["grad"]          # two different summation orders actually ran
