@@ -452,8 +452,8 @@ def measure_extras(pinn_cabi, n_f, with_cpu=True):
         out["schrodinger"] = d
     except Exception as e:  # pragma: no cover
         out["schrodinger"] = {"error": str(e)}
-    # ---- a net the specialised DMMA kernel does not cover: upstream's 8 x 40 table (Burgers_systematic.py:187-202) on the
-    # generic fused kernel (plain DFMA) -- reported so that the cliff next to the [2,20x8,1] path has a number
+    # ---- a net the specialised DMMA kernels do not cover: upstream's 8 x 40 table (Burgers_systematic.py:187-202) on the
+    # generic fused kernel (any width; hidden-to-hidden layers on DMMA.8x8x4 with operands from global memory)
     try:
         L40 = [2] + [40] * 8 + [1]
         n40 = 20000
@@ -466,7 +466,7 @@ def measure_extras(pinn_cabi, n_f, with_cpu=True):
         p.sync()
         ms = float(np.mean(timed_adam_steps(p, 10, flush=False)))
         k_ms = p.time_kernel_ms(5) / 5
-        out["burgers_8x40_generic"] = {"config": "[2,40x8,1] tanh (upstream's systematic table), N_f=%d, generic fused kernel (DFMA, no tensor cores)" % n40,
+        out["burgers_8x40_generic"] = {"config": "[2,40x8,1] tanh (upstream's systematic table), N_f=%d, generic fused kernel (any layer list; hidden layers on DMMA.8x8x4)" % n40,
                                        "ms_per_step": ms, "points_per_s": n40 / (ms * 1e-3), "kernel_ms": k_ms,
                                        "roofline_frac_fp64": (n40 * 24.0 * S40 + N_U * 6.0 * S40) / (k_ms * 1e-3) / 1e12 / peak}
         p.close()

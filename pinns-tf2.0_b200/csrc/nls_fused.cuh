@@ -51,7 +51,7 @@ constexpr int SM_S0 = SM_W + W * W;
 constexpr int SM_S1 = SM_S0 + SLAB;
 constexpr int SM_RED = SM_S1 + SLAB;
 constexpr int SM_BAR = SM_RED + 64;
-constexpr int SM_DOUBLES = SM_BAR + 2;
+constexpr int SM_DOUBLES = SM_BAR + 4;    // mbarriers: weights, slab S0, slab S1
 constexpr int SMEM_BYTES = SM_DOUBLES * 8;     // 182,928 B
 
 inline int grid_size(int n_sm) { return n_sm; }
@@ -74,21 +74,13 @@ struct Args {
 
 __device__ __forceinline__ int prow(int g) { return (g & 4) | ((g & 1) << 1) | ((g & 2) >> 1); }
 
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // stage one round (16 points x 4 streams x 100 units) of a scratch layer [4][pts][W] into a slab [64 rows][W],
-// row = 16*s + p.  51 200 B = 3200 x 16 B -> 12.5 cp.async per thread.
-__device__ __forceinline__ void stage_round(double* slab, const double* src, int pts, int p0) {
-  for (int i = threadIdx.x; i < RROWS * (W / 2); i += THREADS) {
-    const int row = i / (W / 2), c2 = i - row * (W / 2);
-    const int s = row >> 4, p = row & 15;
-    cp_async16(slab + row * W + 2 * c2, src + ((size_t)s * pts + p0 + p) * W + 2 * c2);
-  }
+// row = 16*s + p.  Each stream block is contiguous on both sides (12 800 B): four TMA bulk copies completing on one
+// mbarrier, issued by ONE thread (the per-thread cp.async form cost 19 k instructions per warp, 2/3 of the DMMA count).
+__device__ __forceinline__ void stage_round_tma(double* slab, const double* src, int pts, int p0, uint64_t* bar) {
+  mbar_expect_tx(bar, RROWS * W * 8);
+#pragma unroll
+  for (int s = 0; s < 4; s++) tma_bulk_g2s(slab + 16 * s * W, src + ((size_t)s * pts + p0) * W, RPTS * W * 8, bar);
 }
 
 // warp -> (point group, N tiles) for the row-parallel GEMMs (forward, input adjoint): 2 groups x 13 tiles over 8 warps;
@@ -125,7 +117,8 @@ __device__ __forceinline__ void gemm_rows(double (&C)[4][4][2], const double* sl
 }
 
 __device__ __forceinline__ void load_weights_tma(double* Wsm, const double* src, uint64_t* bar, uint32_t& phase) {
-  __syncthreads();                       // everybody is done with the previous contents of Wsm
+  fence_proxy_async();                   // this thread's scratch / slab writes of the previous phase precede the TMA reads below
+  __syncthreads();                       // everybody is done with the previous contents of Wsm and of the slabs
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, W * W * 8);
     tma_bulk_g2s(Wsm, src, W * W * 8, bar);
@@ -160,8 +153,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SM_BAR);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
-  uint32_t wphase = 0;
-  if (tid == 0) mbar_init(bar, 1);
+  uint64_t* bar0 = bar + 1;                // slab S0
+  uint64_t* bar1 = bar + 2;                // slab S1
+  uint32_t wphase = 0, ph0 = 0, ph1 = 0;
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar0, 1); mbar_init(bar1, 1); }
   __syncthreads();
 
   const int pts = p.pts;
@@ -178,18 +173,35 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   const size_t SSZ = (size_t)pts * W;                              // one stream
 
   // =============================== F0: layer 0 (2 -> 100), direct ===============================
-  for (int i = tid; i < nrounds * RPTS * W; i += THREADS) {
-    const int pt = i / W, u = i - pt * W;
-    const long long gp = base + (pt < npts ? pt : npts - 1);       // padded points replicate the last valid one
-    const double xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;   // utils/neuralnetwork.py:29-30
-    const double th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
-    const double w0 = __ldg(p.w + u), w1 = __ldg(p.w + W + u), b = __ldg(p.w + 2 * W + u);
-    const double a = tanh_fast(fma(xh, w0, fma(th, w1, b)));
-    const double s = fma(-a, a, 1.0), zx = sc0 * w0, zt = sc1 * w1;
-    H[0 * SSZ + (size_t)pt * W + u] = a;
-    H[1 * SSZ + (size_t)pt * W + u] = s * zx;
-    H[2 * SSZ + (size_t)pt * W + u] = s * zt;
-    H[3 * SSZ + (size_t)pt * W + u] = -2.0 * a * s * zx * zx;
+  // warp per point, lanes over the units (lane, lane+32, lane+64, lane+96): the input normalisation (two fp64 divisions)
+  // is evaluated once per point and warp, the layer-0 weights are per-lane constants
+  {
+    double w0c[4], w1c[4], bc[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int u = lane + 32 * c;
+      w0c[c] = u < W ? __ldg(p.w + u) : 0.0;
+      w1c[c] = u < W ? __ldg(p.w + W + u) : 0.0;
+      bc[c] = u < W ? __ldg(p.w + 2 * W + u) : 0.0;
+    }
+#pragma unroll 2
+    for (int pt = warp; pt < nrounds * RPTS; pt += WARPS) {
+      const long long gp = base + (pt < npts ? pt : npts - 1);       // padded points replicate the last valid one
+      const double xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;   // utils/neuralnetwork.py:29-30
+      const double th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int u = lane + 32 * c;
+        if (u < W) {
+          const double a = tanh_fast(fma(xh, w0c[c], fma(th, w1c[c], bc[c])));
+          const double s = fma(-a, a, 1.0), zx = sc0 * w0c[c], zt = sc1 * w1c[c];
+          H[0 * SSZ + (size_t)pt * W + u] = a;
+          H[1 * SSZ + (size_t)pt * W + u] = s * zx;
+          H[2 * SSZ + (size_t)pt * W + u] = s * zt;
+          H[3 * SSZ + (size_t)pt * W + u] = -2.0 * a * s * zx * zx;
+        }
+      }
+    }
   }
   __syncthreads();
 
@@ -203,12 +215,12 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     const double* Hin = H + (size_t)(l - 1) * LSZ;
     double* Hout = H + (size_t)l * LSZ;
     const double* bias = p.w + boff(l);
-    if (nrounds > 0) { stage_round(S0, Hin, pts, 0); cp_async_commit(); }
+    if (nrounds > 0 && tid == 0) stage_round_tma(S0, Hin, pts, 0, bar0);
     for (int r = 0; r < nrounds; r++) {
       double* cur = (r & 1) ? S1 : S0;
-      if (r + 1 < nrounds) { stage_round((r & 1) ? S0 : S1, Hin, pts, (r + 1) * RPTS); cp_async_commit(); cp_async_wait<1>(); }
-      else cp_async_wait<0>();
-      __syncthreads();
+      // the other slab was last read in round r-1 (block barrier at its end): refill it while this round computes
+      if (r + 1 < nrounds && tid == 0) stage_round_tma((r & 1) ? S0 : S1, Hin, pts, (r + 1) * RPTS, (r & 1) ? bar0 : bar1);
+      if (r & 1) { mbar_wait(bar1, ph1); ph1 ^= 1; } else { mbar_wait(bar0, ph0); ph0 ^= 1; }
       double C[4][4][2];
 #pragma unroll
       for (int j = 0; j < 4; j++)
@@ -338,43 +350,60 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     // head gradient: G4[k][o] = sum_pt sum_s H3[s][pt][k] seed[pt][s][o];  bias: sum_pt seed[pt][0][o]
     // and, from the same H3 values, the activation adjoint of the last hidden layer:
     //   A-bar[3][s][pt][k] = sum_o seed[pt][s][o] W4[k][o]  ->  Z-bar[3]  (scratch buffer 1; padded points have zero seeds)
+    // warp per point, lanes over the units: 16 independent H3 loads per lane and iteration; fixed-order combine over the warps
     {
-      const int k = tid & 127, half = tid >> 7;
       const int npad = nrounds * RPTS;
-      const int p0 = half * (npad / 2), p1 = half ? npad : npad / 2;
-      double g0 = 0.0, g1 = 0.0, gb = 0.0;
-      if (k < W) {
-        const double w40 = __ldg(W4 + 2 * k), w41 = __ldg(W4 + 2 * k + 1);
-        double* Z3 = A + (size_t)4 * SSZ;
-#pragma unroll 2
-        for (int pt = p0; pt < p1; pt++) {
-          double hv[4], ab[4];
+      double w40c[4], w41c[4], g0[4] = {0, 0, 0, 0}, g1[4] = {0, 0, 0, 0};
 #pragma unroll
-          for (int s = 0; s < 4; s++) {
-            hv[s] = H3[s * SSZ + (size_t)pt * W + k];
-            const double s0 = SEED[pt * 8 + 2 * s], s1 = SEED[pt * 8 + 2 * s + 1];
-            g0 = fma(hv[s], s0, g0);
-            g1 = fma(hv[s], s1, g1);
-            ab[s] = fma(s0, w40, s1 * w41);
-          }
-          double z[4];
-          zbar(z, hv[0], hv[1], hv[2], hv[3], ab[0], ab[1], ab[2], ab[3]);
-#pragma unroll
-          for (int s = 0; s < 4; s++) Z3[s * SSZ + (size_t)pt * W + k] = z[s];
-        }
-      } else if (k < W + 2) {
-        for (int pt = p0; pt < p1; pt++) gb += SEED[pt * 8 + (k - W)];
+      for (int c = 0; c < 4; c++) {
+        const int k = lane + 32 * c;
+        w40c[c] = k < W ? __ldg(W4 + 2 * k) : 0.0;
+        w41c[c] = k < W ? __ldg(W4 + 2 * k + 1) : 0.0;
       }
-      double* comb = S0;
-      if (half == 1) { comb[k] = g0; comb[128 + k] = g1; comb[256 + k] = gb; }
-      __syncthreads();
-      if (half == 0) {
-        if (k < W) {
-          outp[woff(4) + 2 * k] = g0 + comb[k];
-          outp[woff(4) + 2 * k + 1] = g1 + comb[128 + k];
-        } else if (k < W + 2) {
-          outp[boff(4) + (k - W)] = gb + comb[256 + k];
+      double* Z3 = A + (size_t)4 * SSZ;
+#pragma unroll 2
+      for (int pt = warp; pt < npad; pt += WARPS) {
+        double sd[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) sd[c] = SEED[pt * 8 + c];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int k = lane + 32 * c;
+          if (k < W) {
+            double hv[4], ab[4], z[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) hv[s] = H3[s * SSZ + (size_t)pt * W + k];
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+              g0[c] = fma(hv[s], sd[2 * s], g0[c]);
+              g1[c] = fma(hv[s], sd[2 * s + 1], g1[c]);
+              ab[s] = fma(sd[2 * s], w40c[c], sd[2 * s + 1] * w41c[c]);
+            }
+            zbar(z, hv[0], hv[1], hv[2], hv[3], ab[0], ab[1], ab[2], ab[3]);
+#pragma unroll
+            for (int s = 0; s < 4; s++) Z3[s * SSZ + (size_t)pt * W + k] = z[s];
+          }
         }
+      }
+      double* comb = S0;                                       // [warp][2][128]
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int k = lane + 32 * c;
+        comb[(warp * 2 + 0) * 128 + k] = g0[c];
+        comb[(warp * 2 + 1) * 128 + k] = g1[c];
+      }
+      __syncthreads();
+      for (int i = tid; i < 2 * W; i += THREADS) {
+        const int k = i >> 1, o = i & 1;
+        double sum = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < WARPS; w8++) sum += comb[(w8 * 2 + o) * 128 + k];
+        outp[woff(4) + i] = sum;
+      }
+      if (tid < 2) {
+        double gb = 0.0;
+        for (int pt = 0; pt < npad; pt++) gb += SEED[pt * 8 + tid];
+        outp[boff(4) + tid] = gb;
       }
     }
     __syncthreads();
@@ -403,10 +432,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
 #pragma unroll
     for (int n = 0; n < 4; n++) GS[n][0] = GS[n][1] = 0.0;
 
-    // cp.async groups are committed in the order Z_0, H_0, [per round: (L2 prefetch), Z_{r+1}+H_{r+1}]
-    if (nrounds > 0) {
-      stage_round(S1, Zin, pts, 0); cp_async_commit();
-      stage_round(S0, Hin, pts, 0); cp_async_commit();
+    if (nrounds > 0 && tid == 0) {
+      stage_round_tma(S1, Zin, pts, 0, bar1);
+      stage_round_tma(S0, Hin, pts, 0, bar0);
     }
     for (int r = 0; r < nrounds; r++) {
       const int pt = r * RPTS + myp;
@@ -415,8 +443,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         const double* src = (tid < 4 ? Zin : Hin) + (size_t)(tid & 3) * SSZ + (size_t)(r + 1) * RPTS * W;
         prefetch_l2_bulk(src, RPTS * W * 8);
       }
-      cp_async_wait<1>();                            // Z_r has landed (H_r may still be in flight)
-      __syncthreads();
+      mbar_wait(bar1, ph1); ph1 ^= 1;                // Z_r has landed (H_r may still be in flight)
       // (3) input adjoint: A-bar[l-1] = Z-bar * W_l^T   (K = units of layer l)
       double C[4][4][2];
 #pragma unroll
@@ -424,8 +451,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
 #pragma unroll
         for (int j = 0; j < 4; j++) C[s][j][0] = C[s][j][1] = 0.0;
       gemm_rows(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
-      cp_async_wait<0>();                            // H_r
-      __syncthreads();
+      mbar_wait(bar0, ph0); ph0 ^= 1;                // H_r
       // (3b) Z-bar[l-1] for this lane's point and units from A-bar (registers) and H[l-1] (slab S0) -> scratch
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -473,10 +499,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           }
         }
       }
-      __syncthreads();
-      if (r + 1 < nrounds) {
-        stage_round(S1, Zin, pts, (r + 1) * RPTS); cp_async_commit();
-        stage_round(S0, Hin, pts, (r + 1) * RPTS); cp_async_commit();
+      __syncthreads();                               // both slabs are free
+      if (r + 1 < nrounds && tid == 0) {
+        stage_round_tma(S1, Zin, pts, (r + 1) * RPTS, bar1);
+        stage_round_tma(S0, Hin, pts, (r + 1) * RPTS, bar0);
       }
     }
     // (5) flush this warp's tiles of G_l
