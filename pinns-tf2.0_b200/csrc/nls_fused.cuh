@@ -51,7 +51,7 @@ constexpr int SM_S0 = SM_W + W * W;
 constexpr int SM_S1 = SM_S0 + SLAB;
 constexpr int SM_RED = SM_S1 + SLAB;
 constexpr int SM_BAR = SM_RED + 64;
-constexpr int SM_DOUBLES = SM_BAR + 4;    // mbarriers: weights, slab S0, slab S1
+constexpr int SM_DOUBLES = SM_BAR + 8;    // mbarriers: weights, slab S0, slab S1 (forward); Z lo, Z hi, H, lo-halves-free (backward)
 constexpr int SMEM_BYTES = SM_DOUBLES * 8;     // 182,928 B
 
 inline int grid_size(int n_sm) { return n_sm; }
@@ -83,6 +83,13 @@ __device__ __forceinline__ void stage_round_tma(double* slab, const double* src,
   for (int s = 0; s < 4; s++) tma_bulk_g2s(slab + 16 * s * W, src + ((size_t)s * pts + p0) * W, RPTS * W * 8, bar);
 }
 
+// half a round: streams 2*half, 2*half+1 (rows 32*half .. 32*half+31 of the slab)
+__device__ __forceinline__ void stage_half_tma(double* slab, const double* src, int pts, int p0, int half, uint64_t* bar) {
+  mbar_expect_tx(bar, RROWS * W * 4);
+#pragma unroll
+  for (int s = 2 * half; s < 2 * half + 2; s++) tma_bulk_g2s(slab + 16 * s * W, src + ((size_t)s * pts + p0) * W, RPTS * W * 8, bar);
+}
+
 // warp -> (point group, N tiles) for the row-parallel GEMMs (forward, input adjoint): 2 groups x 13 tiles over 8 warps;
 // the 4-tile warp sits on a different sub-partition in each group (loads 7,7,6,6).
 __device__ __forceinline__ void gemm_role(int warp, int& pg, int& nt0, int& ntn) {
@@ -93,6 +100,9 @@ __device__ __forceinline__ void gemm_role(int warp, int& pg, int& nt0, int& ntn)
 }
 
 // C[s][j][:] (+)= A(rows of group pg, streams s) * B,   B[k][n] = Wsm[k*ldk + n*ldn];  n >= 100 reads as zero
+// streams S_LO .. S_HI-1 only (the backward pass runs the two stream halves separately: the second half of the slab lands
+// while the first is being multiplied)
+template <int S_LO = 0, int S_HI = 4>
 __device__ __forceinline__ void gemm_rows(double (&C)[4][4][2], const double* slab, const double* Wsm, int ldk, int ldn,
                                           int pg, int nt0, int ntn, int lane) {
   const int g = lane >> 2, q = lane & 3;
@@ -101,7 +111,7 @@ __device__ __forceinline__ void gemm_rows(double (&C)[4][4][2], const double* sl
   for (int ks = 0; ks < KS; ks++) {
     double a[4], b[4];
 #pragma unroll
-    for (int s = 0; s < 4; s++) a[s] = slab[(16 * s + 8 * pg + prow_g) * W + 4 * ks + q];
+    for (int s = S_LO; s < S_HI; s++) a[s] = slab[(16 * s + 8 * pg + prow_g) * W + 4 * ks + q];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int n = 8 * (nt0 + j) + g;
@@ -111,7 +121,7 @@ __device__ __forceinline__ void gemm_rows(double (&C)[4][4][2], const double* sl
     for (int j = 0; j < 4; j++)
       if (j < ntn) {
 #pragma unroll
-        for (int s = 0; s < 4; s++) dmma(C[s][j], a[s], b[j]);
+        for (int s = S_LO; s < S_HI; s++) dmma(C[s][j], a[s], b[j]);
       }
   }
 }
@@ -155,8 +165,15 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   const int g = lane >> 2, q = lane & 3;
   uint64_t* bar0 = bar + 1;                // slab S0
   uint64_t* bar1 = bar + 2;                // slab S1
-  uint32_t wphase = 0, ph0 = 0, ph1 = 0;
-  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar0, 1); mbar_init(bar1, 1); }
+  uint64_t* bZl = bar + 3;                 // backward: Z-bar slab, streams 0-1 / 2-3; H slab (two half copies); lo halves free
+  uint64_t* bZh = bar + 4;
+  uint64_t* bH = bar + 5;
+  uint64_t* bFree = bar + 6;
+  uint32_t wphase = 0, ph0 = 0, ph1 = 0, phZl = 0, phZh = 0, phH = 0, phF = 0;
+  if (tid == 0) {
+    mbar_init(bar, 1); mbar_init(bar0, 1); mbar_init(bar1, 1);
+    mbar_init(bZl, 1); mbar_init(bZh, 1); mbar_init(bH, 2); mbar_init(bFree, WARPS);
+  }
   __syncthreads();
 
   const int pts = p.pts;
@@ -433,8 +450,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     for (int n = 0; n < 4; n++) GS[n][0] = GS[n][1] = 0.0;
 
     if (nrounds > 0 && tid == 0) {
-      stage_round_tma(S1, Zin, pts, 0, bar1);
-      stage_round_tma(S0, Hin, pts, 0, bar0);
+      stage_half_tma(S1, Zin, pts, 0, 0, bZl); stage_half_tma(S1, Zin, pts, 0, 1, bZh);
+      stage_half_tma(S0, Hin, pts, 0, 0, bH); stage_half_tma(S0, Hin, pts, 0, 1, bH);
     }
     for (int r = 0; r < nrounds; r++) {
       const int pt = r * RPTS + myp;
@@ -443,15 +460,18 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         const double* src = (tid < 4 ? Zin : Hin) + (size_t)(tid & 3) * SSZ + (size_t)(r + 1) * RPTS * W;
         prefetch_l2_bulk(src, RPTS * W * 8);
       }
-      mbar_wait(bar1, ph1); ph1 ^= 1;                // Z_r has landed (H_r may still be in flight)
-      // (3) input adjoint: A-bar[l-1] = Z-bar * W_l^T   (K = units of layer l)
+      // (3) input adjoint: A-bar[l-1] = Z-bar * W_l^T   (K = units of layer l), streams 0-1 then 2-3: the lo halves of the
+      // slabs were refilled in the middle of the previous round's weight gradient, the hi halves at its end
       double C[4][4][2];
 #pragma unroll
       for (int s = 0; s < 4; s++)
 #pragma unroll
         for (int j = 0; j < 4; j++) C[s][j][0] = C[s][j][1] = 0.0;
-      gemm_rows(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
-      mbar_wait(bar0, ph0); ph0 ^= 1;                // H_r
+      mbar_wait(bZl, phZl); phZl ^= 1;
+      gemm_rows<0, 2>(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
+      mbar_wait(bZh, phZh); phZh ^= 1;
+      gemm_rows<2, 4>(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
+      mbar_wait(bH, phH); phH ^= 1;                  // H_r (both halves)
       // (3b) Z-bar[l-1] for this lane's point and units from A-bar (registers) and H[l-1] (slab S0) -> scratch
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -469,8 +489,10 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         }
       }
       // (4) weight gradient: G[i][j] += sum_rows S0[row][i] * S1[row][j]   (unit i == 100: ones on the value stream)
+#pragma unroll 1
+      for (int hf = 0; hf < 2; hf++) {
 #pragma unroll 2
-      for (int ks = 0; ks < RROWS / 4; ks++) {
+      for (int ks = 8 * hf; ks < 8 * hf + 8; ks++) {
         const double* ar = S0 + (4 * ks + q) * W;
         const double* br = S1 + (4 * ks + q) * W;
         double av[3], bv[7];
@@ -499,10 +521,23 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           }
         }
       }
-      __syncthreads();                               // both slabs are free
+        if (hf == 0) {
+          // rows 0..31 (streams 0-1) of both slabs are dead once every warp is past them: refill them now
+          if (lane == 0) mbar_arrive(bFree);
+          if (tid == 0) {
+            if (r + 1 < nrounds) {
+              mbar_wait(bFree, phF);
+              stage_half_tma(S1, Zin, pts, (r + 1) * RPTS, 0, bZl);
+              stage_half_tma(S0, Hin, pts, (r + 1) * RPTS, 0, bH);
+            }
+            phF ^= 1;
+          }
+        }
+      }
+      __syncthreads();                               // the hi halves are free
       if (r + 1 < nrounds && tid == 0) {
-        stage_round_tma(S1, Zin, pts, (r + 1) * RPTS, bar1);
-        stage_round_tma(S0, Hin, pts, (r + 1) * RPTS, bar0);
+        stage_half_tma(S1, Zin, pts, (r + 1) * RPTS, 1, bZh);
+        stage_half_tma(S0, Hin, pts, (r + 1) * RPTS, 1, bH);
       }
     }
     // (5) flush this warp's tiles of G_l
