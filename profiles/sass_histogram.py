@@ -21,7 +21,8 @@ for line in sass.splitlines():
         funcs[cur][key] += 1
 print("# Static SASS opcode histogram of the hot kernels (`cuobjdump -sass pinns-tf2.0_b200/lib/libpinn_b200.so`, sm_100a)\n")
 print("FP64 tensor work is `DMMA.8x8x4` (tcgen05 has no FP64 kind: no UTC*MMA / LDTM is expected); `UBLKCP` = TMA bulk copy,\n"
-      "`SYNCS.*` = mbarrier, `LDGSTS` = cp.async.  No LDL/STL (local-memory spill traffic) in the fused kernels.\n")
+      "`SYNCS.*` = mbarrier, `LDGSTS` = cp.async.  LDL+STL counts local-memory (spill) instructions: none in the two specialised fused\n"
+      "kernels; the generic kernel (128-register cap for 2 CTAs per SM) spills a few values.\n")
 for name, c in funcs.items():
     if not any(w in name for w in WANT):
         continue
