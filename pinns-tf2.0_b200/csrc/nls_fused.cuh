@@ -9,14 +9,15 @@
 //   F1..F3    W_l staged once per pass with ONE TMA bulk copy; 16-point rounds of H[l-1] stream in through
 //             cp.async (double buffered); DMMA GEMM [64 rows x 100] x [100 x 100]; tanh + Taylor streams in the
 //             epilogue;                                                outputs -> scratch H[l]
-//   OUT       head (100 -> 2), residuals f_u, f_v, initial/boundary terms, loss parts, seeds; head gradient
+//   OUT       (head outputs come out of the F3 epilogue) residuals f_u, f_v, initial/boundary terms, loss parts, seeds
 //   B3..B1    per round: Z-bar[l] (activation adjoint of layer l, from scratch) and H[l-1] stream in through cp.async;
 //             input adjoint A-bar[l-1] = Z-bar W_l^T (DMMA) stays in registers and is turned into Z-bar[l-1] in the
 //             epilogue with the H[l-1] values of the staged slab -> scratch (so A-bar never round-trips through global
 //             memory and H[l] is not re-read);  weight gradient G_l += H[l-1]^T Z-bar (DMMA, K = 64 rows per round).
 //             The 13x13 output tiles of G_l are OWNED by warps, so their accumulators stay in registers for the whole
 //             pass over the CTA's points and are written once (bias gradient = virtual ones-row 100).
-//             Z-bar[3] comes out of the head phase (same loop as the head gradient).
+//             The l = 3 pass stages H[3] instead and turns it into Z-bar[3] IN the slab (seeds x head weights, one block
+//             barrier more per round), accumulating the head gradient from the same shared-memory values.
 //   B0        layer-0 gradient from Z-bar[0], direct.
 // The activations (4 streams x 100 units x 4 layers = 12.8 KB per point) live in a per-CTA global scratch that is
 // streamed, not re-read: algorithmic HBM traffic is 16 B/point, implementation traffic ~67 KB/point.
@@ -50,7 +51,10 @@ constexpr int SM_W = 0;
 constexpr int SM_S0 = SM_W + W * W;
 constexpr int SM_S1 = SM_S0 + SLAB;
 constexpr int SM_RED = SM_S1 + SLAB;
-constexpr int SM_BAR = SM_RED + 64;
+constexpr int SM_W4 = SM_RED + 64;          // head weights W_4 (100 x 2)
+constexpr int SM_HO = SM_W4 + 2 * W;        // head-output partials of a forward round: [2 (round parity)][4 warps][16 points][8]
+constexpr int SM_GH = SM_HO + 2 * 4 * RPTS * 8;   // head-gradient accumulators [2 point halves][2 outputs][128 units]
+constexpr int SM_BAR = SM_GH + 2 * 2 * 128;
 constexpr int SM_DOUBLES = SM_BAR + 8;    // mbarriers: weights, slab S0, slab S1 (forward); Z lo, Z hi, H, lo-halves-free (backward)
 constexpr int SMEM_BYTES = SM_DOUBLES * 8;     // 182,928 B
 
@@ -160,6 +164,9 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   double* S0 = sm + SM_S0;
   double* S1 = sm + SM_S1;
   double* red = sm + SM_RED;
+  double* W4s = sm + SM_W4;
+  double* HO = sm + SM_HO;
+  double* GH = sm + SM_GH;
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SM_BAR);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
@@ -176,6 +183,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   }
   __syncthreads();
 
+  for (int i = tid; i < 2 * W; i += THREADS) W4s[i] = __ldg(p.w + woff(4) + i);
+  for (int i = tid; i < 2 * 2 * 128; i += THREADS) GH[i] = 0.0;
   const int pts = p.pts;
   const long long base = (long long)blockIdx.x * pts;              // first point of this CTA
   long long navail = p.n_total - base;
@@ -249,6 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
         }
       gemm_rows(C, cur, Wsm, W, 1, pg, nt0, ntn, lane);
       const int pt = r * RPTS + myp;
+      double ho[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // l == 3: this lane's share of the head outputs out[pt][2 s + o]
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int u = 8 * (nt0 + j) + 2 * q;
@@ -266,51 +276,48 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
 #pragma unroll
           for (int s = 0; s < 4; s++)
             *reinterpret_cast<double2*>(Hout + s * SSZ + (size_t)pt * W + u) = make_double2(o[s][0], o[s][1]);
+          if (l == 3) {
+            const double2 wa = *reinterpret_cast<const double2*>(W4s + 2 * u);          // W4[u][0..1]
+            const double2 wb = *reinterpret_cast<const double2*>(W4s + 2 * u + 2);      // W4[u+1][0..1]
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+              ho[2 * s] = fma(o[s][0], wa.x, fma(o[s][1], wb.x, ho[2 * s]));
+              ho[2 * s + 1] = fma(o[s][0], wa.y, fma(o[s][1], wb.y, ho[2 * s + 1]));
+            }
+          }
+        }
+      }
+      if (l == 3) {
+        // head (100 -> 2) from the values still in registers: quad reduction, then one partial per warp of the point group
+        double* hop = HO + (r & 1) * (4 * RPTS * 8);
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          ho[c] += shfl_xor_d(ho[c], 1);
+          ho[c] += shfl_xor_d(ho[c], 2);
+        }
+        if (q == 0) {
+#pragma unroll
+          for (int c = 0; c < 8; c++) hop[((warp & 3) * RPTS + myp) * 8 + c] = ho[c];
         }
       }
       __syncthreads();
+      if (l == 3 && tid < RPTS * 8) {
+        // fixed-order sum over the four warps of a point group -> OUTV (the adjoint scratch is still unused at this point);
+        // the partial buffer alternates with the round, so the next round's writers cannot overtake these reads
+        const double* hop = HO + (r & 1) * (4 * RPTS * 8);
+        const int pp = tid >> 3, c = tid & 7;
+        double v = c < 2 ? __ldg(p.w + boff(4) + c) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v += hop[(k * RPTS + pp) * 8 + c];
+        A[(r * RPTS + pp) * 8 + c] = v;
+      }
     }
   }
 
   // =============================== OUT: head (100 -> 2), residuals, seeds ===============================
   {
-    const double* H3 = H + (size_t)3 * LSZ;
-    const double* W4 = p.w + woff(4);
-    // head outputs out[pt][2s+o] -> OUTV (the adjoint scratch is still unused at this point).
-    // One warp per point, lanes over the 100 hidden units (coalesced), 8 partial sums reduced by shuffles.
+    // head outputs out[pt][2s+o]: written to OUTV by the F3 epilogue
     double* OUTV = A;
-    {
-      double w40[4], w41[4];
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int k = lane + 32 * c;
-        w40[c] = k < W ? __ldg(W4 + 2 * k) : 0.0;
-        w41[c] = k < W ? __ldg(W4 + 2 * k + 1) : 0.0;
-      }
-      const double b40 = __ldg(p.w + boff(4)), b41 = __ldg(p.w + boff(4) + 1);
-      for (int pt = warp; pt < nrounds * RPTS; pt += WARPS) {
-        double acc[8];
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-          double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const int k = lane + 32 * c;
-            const double hv = k < W ? H3[s * SSZ + (size_t)pt * W + k] : 0.0;
-            a0 = fma(hv, w40[c], a0);
-            a1 = fma(hv, w41[c], a1);
-          }
-          acc[2 * s] = a0; acc[2 * s + 1] = a1;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; c++) acc[c] = warp_sum(acc[c]);
-        if (lane == 0) {
-          acc[0] += b40; acc[1] += b41;
-#pragma unroll
-          for (int c = 0; c < 8; c++) OUTV[pt * 8 + c] = acc[c];
-        }
-      }
-    }
     __syncthreads();
     double l0 = 0.0, lbd = 0.0, lf = 0.0;
     // one thread per point; a boundary point reads its partner's outputs (pairs are adjacent and never straddle a
@@ -364,64 +371,11 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       for (int w8 = 0; w8 < WARPS; w8++) s += red[w8 * 3 + tid];
       outp[IDX_L0 + tid] = s;
     }
-    // head gradient: G4[k][o] = sum_pt sum_s H3[s][pt][k] seed[pt][s][o];  bias: sum_pt seed[pt][0][o]
-    // and, from the same H3 values, the activation adjoint of the last hidden layer:
-    //   A-bar[3][s][pt][k] = sum_o seed[pt][s][o] W4[k][o]  ->  Z-bar[3]  (scratch buffer 1; padded points have zero seeds)
-    // warp per point, lanes over the units: 16 independent H3 loads per lane and iteration; fixed-order combine over the warps
-    {
-      const int npad = nrounds * RPTS;
-      double w40c[4], w41c[4], g0[4] = {0, 0, 0, 0}, g1[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int k = lane + 32 * c;
-        w40c[c] = k < W ? __ldg(W4 + 2 * k) : 0.0;
-        w41c[c] = k < W ? __ldg(W4 + 2 * k + 1) : 0.0;
-      }
-      double* Z3 = A + (size_t)4 * SSZ;
-#pragma unroll 2
-      for (int pt = warp; pt < npad; pt += WARPS) {
-        double sd[8];
-#pragma unroll
-        for (int c = 0; c < 8; c++) sd[c] = SEED[pt * 8 + c];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          const int k = lane + 32 * c;
-          if (k < W) {
-            double hv[4], ab[4], z[4];
-#pragma unroll
-            for (int s = 0; s < 4; s++) hv[s] = H3[s * SSZ + (size_t)pt * W + k];
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-              g0[c] = fma(hv[s], sd[2 * s], g0[c]);
-              g1[c] = fma(hv[s], sd[2 * s + 1], g1[c]);
-              ab[s] = fma(sd[2 * s], w40c[c], sd[2 * s + 1] * w41c[c]);
-            }
-            zbar(z, hv[0], hv[1], hv[2], hv[3], ab[0], ab[1], ab[2], ab[3]);
-#pragma unroll
-            for (int s = 0; s < 4; s++) Z3[s * SSZ + (size_t)pt * W + k] = z[s];
-          }
-        }
-      }
-      double* comb = S0;                                       // [warp][2][128]
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int k = lane + 32 * c;
-        comb[(warp * 2 + 0) * 128 + k] = g0[c];
-        comb[(warp * 2 + 1) * 128 + k] = g1[c];
-      }
-      __syncthreads();
-      for (int i = tid; i < 2 * W; i += THREADS) {
-        const int k = i >> 1, o = i & 1;
-        double sum = 0.0;
-#pragma unroll
-        for (int w8 = 0; w8 < WARPS; w8++) sum += comb[(w8 * 2 + o) * 128 + k];
-        outp[woff(4) + i] = sum;
-      }
-      if (tid < 2) {
-        double gb = 0.0;
-        for (int pt = 0; pt < npad; pt++) gb += SEED[pt * 8 + tid];
-        outp[boff(4) + tid] = gb;
-      }
+    // head bias gradient: sum_pt seed[pt][0][o]  (the head weight gradient and Z-bar[3] are formed in the l = 3 pass below)
+    if (tid < 2) {
+      double gb = 0.0;
+      for (int pt = 0; pt < nrounds * RPTS; pt++) gb += SEED[pt * 8 + tid];
+      outp[boff(4) + tid] = gb;
     }
     __syncthreads();
   }
@@ -439,7 +393,8 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     load_weights_tma(Wsm, p.w + woff(l), bar, wphase);
     const double* Hin = H + (size_t)(l - 1) * LSZ;                  // inputs of layer l: A operand of the weight gradient, and
                                                                      // the outputs the activation adjoint of layer l-1 needs
-    const double* Zin = A + (size_t)(l & 1) * 4 * SSZ;               // Z-bar[l]   (written by the head phase / the pass above)
+    // Z-bar[l], written by the pass above; l = 3: H[3], turned into Z-bar[3] in the slab
+    const double* Zin = l == 3 ? H + (size_t)3 * LSZ : A + (size_t)(l & 1) * 4 * SSZ;
     double* Zout = A + (size_t)((l & 1) ^ 1) * 4 * SSZ;              // Z-bar[l-1]
     double G[3][7][2], GS[4][2];
 #pragma unroll
@@ -468,9 +423,42 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
 #pragma unroll
         for (int j = 0; j < 4; j++) C[s][j][0] = C[s][j][1] = 0.0;
       mbar_wait(bZl, phZl); phZl ^= 1;
-      gemm_rows<0, 2>(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
-      mbar_wait(bZh, phZh); phZh ^= 1;
-      gemm_rows<2, 4>(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
+      if (l == 3) {
+        // the slab holds H[3] (outputs of the last hidden layer): per (point, unit)
+        //   A-bar[3][s] = sum_o seed[pt][s][o] W4[u][o]  ->  Z-bar[3] written back in place;
+        //   head gradient G4[u][o] += sum_s H3[s] seed[pt][s][o]   (accumulators in shared memory, one slot per thread)
+        mbar_wait(bZh, phZh); phZh ^= 1;
+        const int u = tid & 127, ph = tid >> 7;
+        if (u < W) {
+          const double w40 = W4s[2 * u], w41 = W4s[2 * u + 1];
+          double g0 = 0.0, g1 = 0.0;
+#pragma unroll 2
+          for (int pp = 8 * ph; pp < 8 * ph + 8; pp++) {
+            const double* sdp = SEED + (size_t)(r * RPTS + pp) * 8;
+            double hv[4], ab[4], z[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+              hv[s] = S1[(16 * s + pp) * W + u];
+              const double s0 = sdp[2 * s], s1 = sdp[2 * s + 1];
+              g0 = fma(hv[s], s0, g0);
+              g1 = fma(hv[s], s1, g1);
+              ab[s] = fma(s0, w40, s1 * w41);
+            }
+            zbar(z, hv[0], hv[1], hv[2], hv[3], ab[0], ab[1], ab[2], ab[3]);
+#pragma unroll
+            for (int s = 0; s < 4; s++) S1[(16 * s + pp) * W + u] = z[s];
+          }
+          GH[(ph * 2 + 0) * 128 + u] += g0;
+          GH[(ph * 2 + 1) * 128 + u] += g1;
+        }
+        fence_proxy_async();                         // these generic writes precede the TMA refills of the slab
+        __syncthreads();
+        gemm_rows<0, 4>(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
+      } else {
+        gemm_rows<0, 2>(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
+        mbar_wait(bZh, phZh); phZh ^= 1;
+        gemm_rows<2, 4>(C, S1, Wsm, 1, W, pg, nt0, ntn, lane);
+      }
       mbar_wait(bH, phH); phH ^= 1;                  // H_r (both halves)
       // (3b) Z-bar[l-1] for this lane's point and units from A-bar (registers) and H[l-1] (slab S0) -> scratch
 #pragma unroll
@@ -538,6 +526,13 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       if (r + 1 < nrounds && tid == 0) {
         stage_half_tma(S1, Zin, pts, (r + 1) * RPTS, 1, bZh);
         stage_half_tma(S0, Hin, pts, (r + 1) * RPTS, 1, bH);
+      }
+    }
+    if (l == 3) {
+      // head weight gradient: the two point halves in a fixed order (the last round's barrier ordered the accumulators)
+      for (int i = tid; i < 2 * W; i += THREADS) {
+        const int u = i >> 1, o = i & 1;
+        outp[woff(4) + i] = GH[(0 * 2 + o) * 128 + u] + GH[(1 * 2 + o) * 128 + u];
       }
     }
     // (5) flush this warp's tiles of G_l
