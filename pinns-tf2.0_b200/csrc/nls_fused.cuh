@@ -156,6 +156,16 @@ __device__ __forceinline__ void zbar(double (&z)[4], double a, double ax, double
   z[3] = s * Axx;
 }
 
+// normalised coordinates of point pt of this CTA (utils/neuralnetwork.py:29-30); padded points replicate the last valid one
+__device__ __forceinline__ void norm_coords(const Args& p, long long base, int npts, int npad, int pt, double& xh, double& th) {
+  xh = th = 0.0;
+  if (pt < npad) {
+    const long long gp = base + (pt < npts ? pt : npts - 1);
+    xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;
+    th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
   extern __shared__ __align__(16) double sm[];
   pdl_launch_dependents();                 // the tail kernel's blocks may be placed as SMs free up; they park in pdl_wait()
@@ -210,11 +220,16 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
       w1c[c] = u < W ? __ldg(p.w + W + u) : 0.0;
       bc[c] = u < W ? __ldg(p.w + 2 * W + u) : 0.0;
     }
+    const int npad0 = nrounds * RPTS;
+    for (int chunk = 0; warp + WARPS * 32 * chunk < npad0; chunk++) {
+      // the lanes fetch and normalise the coordinates of the warp's next 32 points in one go (no load latency per point)
+      double xl, tl;
+      norm_coords(p, base, npts, npad0, warp + WARPS * (32 * chunk + lane), xl, tl);
 #pragma unroll 2
-    for (int pt = warp; pt < nrounds * RPTS; pt += WARPS) {
-      const long long gp = base + (pt < npts ? pt : npts - 1);       // padded points replicate the last valid one
-      const double xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;   // utils/neuralnetwork.py:29-30
-      const double th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
+      for (int i = 0; i < 32; i++) {
+      const int pt = warp + WARPS * (32 * chunk + i);
+      if (pt >= npad0) break;
+      const double xh = __shfl_sync(0xffffffffu, xl, i), th = __shfl_sync(0xffffffffu, tl, i);
 #pragma unroll
       for (int c = 0; c < 4; c++) {
         const int u = lane + 32 * c;
@@ -226,6 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
           H[2 * SSZ + (size_t)pt * W + u] = s * zt;
           H[3 * SSZ + (size_t)pt * W + u] = -2.0 * a * s * zx * zx;
         }
+      }
       }
     }
   }
@@ -576,20 +592,24 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     const double* Z0 = A;                                  // Z-bar[0]: scratch buffer 0, written by the l = 1 pass
     double gx[4] = {0, 0, 0, 0}, gt[4] = {0, 0, 0, 0}, gb[4] = {0, 0, 0, 0};
     const int npad = nrounds * RPTS;
-#pragma unroll 2
-    for (int pt = warp; pt < npad; pt += WARPS) {
-      const long long gp = base + (pt < npts ? pt : npts - 1);
-      const double xh = 2.0 * (__ldg(p.x + gp) - p.lb0) / p.dx0 - 1.0;
-      const double th = 2.0 * (__ldg(p.t + gp) - p.lb1) / p.dx1 - 1.0;
+    for (int chunk = 0; warp + WARPS * 32 * chunk < npad; chunk++) {
+      double xl, tl;
+      norm_coords(p, base, npts, npad, warp + WARPS * (32 * chunk + lane), xl, tl);
+#pragma unroll 4
+      for (int i = 0; i < 32; i++) {
+        const int pt = warp + WARPS * (32 * chunk + i);
+        if (pt >= npad) break;
+        const double xh = __shfl_sync(0xffffffffu, xl, i), th = __shfl_sync(0xffffffffu, tl, i);
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const int u = lane + 32 * c;
-        if (u < W) {
-          const size_t o = (size_t)pt * W + u;
-          const double z = Z0[o], zbx = Z0[SSZ + o], zbt = Z0[2 * SSZ + o];
-          gx[c] = fma(xh, z, fma(sc0, zbx, gx[c]));
-          gt[c] = fma(th, z, fma(sc1, zbt, gt[c]));
-          gb[c] += z;
+        for (int c = 0; c < 4; c++) {
+          const int u = lane + 32 * c;
+          if (u < W) {
+            const size_t o = (size_t)pt * W + u;
+            const double z = Z0[o], zbx = Z0[SSZ + o], zbt = Z0[2 * SSZ + o];
+            gx[c] = fma(xh, z, fma(sc0, zbx, gx[c]));
+            gt[c] = fma(th, z, fma(sc1, zbt, gt[c]));
+            gb[c] += z;
+          }
         }
       }
     }
