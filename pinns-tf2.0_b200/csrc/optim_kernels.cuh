@@ -41,23 +41,39 @@ struct ReduceMap {
   int n_extra;
 };
 
-// 8 lanes per output entry: each lane sums every 8th CTA partial, then a 3-step shuffle tree in fixed order
-// (deterministic).  blockDim = 256 -> 32 entries per block.
-__global__ void reduce_partials(const double* __restrict__ partials, int n_cta, int stride, double* __restrict__ R,
-                                ReduceMap map, const int* __restrict__ run_flag) {
+// Fixed-order sum of the per-CTA partials, 32 entries per block of 256 threads: warp w adds the partials of CTAs w, w+8, ...
+// for entry `lane` (every load is one coalesced 256-byte row segment, all of a thread's loads are independent), the eight
+// warp sums meet in shared memory and are combined as ((0+1)+(2+3))+((4+5)+(6+7)) -- deterministic, and the same order as
+// the 8-lanes-per-entry shuffle tree of round 1 (which read 8 x 32 bytes per load and took ~8 us for 148 partials).
+// Contains ONE block barrier; returns the total of entry (threadIdx.x & 31) to every thread.
+__device__ __forceinline__ double combine8(const double* red, int lane) {
+  return ((red[lane] + red[32 + lane]) + (red[64 + lane] + red[96 + lane])) +
+         ((red[128 + lane] + red[160 + lane]) + (red[192 + lane] + red[224 + lane]));
+}
+__device__ __forceinline__ double reduce_block_entries(const double* __restrict__ partials, int n_cta, int stride, int src, bool ok,
+                                                       double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double s = 0.0;
+  if (ok) {
+    const double* col = partials + src;
+#pragma unroll 8
+    for (int b = warp; b < n_cta; b += 8) s += col[(size_t)b * stride];
+  }
+  red[warp * 32 + lane] = s;
+  __syncthreads();
+  return combine8(red, lane);
+}
+
+__global__ void __launch_bounds__(256) reduce_partials(const double* __restrict__ partials, int n_cta, int stride,
+                                                       double* __restrict__ R, ReduceMap map, const int* __restrict__ run_flag) {
+  __shared__ double red[256];
   pdl_wait();                                       // the fused kernel that wrote the partials has completed
   if (run_flag && *run_flag != 0) return;
-  const int sub = threadIdx.x & 7;
-  const int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
   const bool ok = i < map.n_out;
   const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
-  double s = 0.0;
-  if (ok)
-    for (int b = sub; b < n_cta; b += 8) s += partials[(size_t)b * stride + src];
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (ok && sub == 0) R[i] = s;
+  const double s = reduce_block_entries(partials, n_cta, stride, src, ok, red);
+  if (ok && threadIdx.x < 32) R[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -100,19 +116,14 @@ __global__ void reduce_adam(const double* __restrict__ partials, int n_cta, int 
                             double* __restrict__ w, double* __restrict__ m, double* __restrict__ v, int P,
                             int* __restrict__ step, double lr, double b1, double b2, double eps,
                             double* __restrict__ loss_ring, int ring) {
+  __shared__ double red[256];
   pdl_wait();                                       // the fused kernel that wrote the partials has completed
   const int t = step[0] + 1;
-  const int sub = threadIdx.x & 7;
-  const int i = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
   const bool ok = i < map.n_out;
   const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
-  double s = 0.0;
-  if (ok)
-    for (int b = sub; b < n_cta; b += 8) s += partials[(size_t)b * stride + src];
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (ok && sub == 0) {
+  const double s = reduce_block_entries(partials, n_cta, stride, src, ok, red);
+  if (ok && threadIdx.x < 32) {
     R[i] = s;
     if (i < P) adam_entry(w, m, v, s, i, t, lr, b1, b2, eps);
   }
@@ -138,7 +149,7 @@ __global__ void reduce_adam(const double* __restrict__ partials, int n_cta, int 
 //
 // Every rank owns an IPC-exported exchange buffer   data[2 parities][world][slot_len] doubles, flag[2][world][n_blocks] u64.
 // Block b of rank r reduces its 32 entries of the per-CTA partials (fixed order), STORES them into slot [parity][r] of EVERY
-// rank's buffer (sub-lane k of an entry writes to peer k: remote stores are fire-and-forget, nobody pulls), fences, and
+// rank's buffer (warp k of a block writes its 32 entries to peer k: remote stores are fire-and-forget, nobody pulls), fences, and
 // raises flag[parity][r][b] = seq on every peer.  It then waits on its LOCAL flags of all ranks for the same block --
 // a local spin, no NVLink round trips -- sums the world slots in a fixed butterfly order (bitwise identical on all ranks,
 // so replicated optimiser state never diverges) and applies Adam to its entries in the same pass.
@@ -186,20 +197,16 @@ reduce_exchange(const double* __restrict__ partials, int n_cta, int stride, Redu
   if (run_flag && *run_flag != 0) return;          // identical on every rank (replicated L-BFGS state)
   const unsigned long long seq = (unsigned long long)(*(volatile int*)xseq) + 1;
   const int parity = (int)(seq & 1);
-  const int sub = threadIdx.x & 7;
+  const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;       // entry within the virtual block; warp = partial slice, then peer rank
   const int t = adam ? step[0] + 1 : 0;
   bool dead = false;
+  __shared__ double red[256], red2[256];
   for (int vb = blockIdx.x; vb < peers.n_blocks; vb += gridDim.x) {
-    const int i = vb * (blockDim.x >> 3) + (threadIdx.x >> 3);
+    const int i = vb * 32 + lane;
     const bool ok = i < map.n_out;
     const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
-    double s = 0.0;
-    if (ok)
-      for (int b = sub; b < n_cta; b += 8) s += partials[(size_t)b * stride + src];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);          // every sub-lane holds the entry's local sum
-    // ---- push: sub-lane k stores the entry into rank k's buffer, slot [parity][my rank]
+    const double s = reduce_block_entries(partials, n_cta, stride, src, ok, red);   // every warp holds the 32 local sums
+    // ---- push: warp k stores the 32 entries into rank k's buffer (one 256-byte row), slot [parity][my rank]
     const size_t slot = ((size_t)parity * peers.world + peers.rank) * peers.slot_len;
     if (ok && sub < peers.world) peers.data[sub][slot + i] = s;
     // publication: the block barrier orders every thread's data stores before the flag writers, whose release at system
@@ -221,13 +228,13 @@ reduce_exchange(const double* __restrict__ partials, int n_cta, int stride, Redu
     }
     __syncthreads();
     dead = dead || *(volatile int*)err != 0;        // a peer never published: leave R, weights and optimiser state untouched
-    // ---- sum over ranks: sub-lane k loads rank k's value from the LOCAL buffer, butterfly in a fixed order
-    double tot = 0.0;
+    // ---- sum over ranks: warp k loads rank k's 32 values from the LOCAL buffer, combined in the fixed order of combine8
+    double part = 0.0;
     if (ok && sub < peers.world)
-      tot = __ldcv(peers.data[peers.rank] + ((size_t)parity * peers.world + sub) * peers.slot_len + i);
-    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-    tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+      part = __ldcv(peers.data[peers.rank] + ((size_t)parity * peers.world + sub) * peers.slot_len + i);
+    red2[sub * 32 + lane] = part;
+    __syncthreads();
+    const double tot = combine8(red2, lane);
     if (ok && sub == 0 && !dead) {
       R[i] = tot;
       if (adam && i < P) adam_entry(w, m, v, tot, i, t, lr, b1, b2, eps);
