@@ -710,4 +710,12 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line.  C libraries loaded into this process write to file descriptor 1 on their own (NCCL
+    # prints its version banner there whatever NCCL_DEBUG_FILE says), so descriptor 1 is pointed at stderr for the whole run
+    # and Python's sys.stdout keeps the real one.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w", buffering=1)
     main()
+    sys.stdout.flush()
