@@ -131,9 +131,15 @@ int pinn_loss_grad(pinn_t* h, const double* w_or_null, double* loss_out, double*
 
 /* tf_optimization_step (utils/neuralnetwork.py:112-116) with TF-2.0 Keras Adam semantics
  * (alpha_t = lr sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= alpha_t m/(sqrt(v)+eps)).
- * loss_out == NULL: fully asynchronous (two kernel launches enqueued on the handle's stream, no host sync; the loss goes to
- * a device ring, see pinn_last_loss).  The loss is the one evaluated BEFORE the update, as in the reference. */
+ * loss_out == NULL: fully asynchronous (one launch on a single GPU with the specialised Burgers kernel -- the last CTAs of the
+ * fused kernel reduce the partials and apply Adam --, two launches otherwise; no host sync; the loss goes to a device ring, see
+ * pinn_last_loss).  The loss is the one evaluated BEFORE the update, as in the reference. */
 int pinn_adam_step(pinn_t* h, double lr, double b1, double b2, double eps, double* loss_out_or_null);
+
+/* n consecutive asynchronous Adam steps (the body of tf_optimization's epoch loop, utils/neuralnetwork.py:105-110, without the
+ * per-epoch logger call) enqueued by ONE call: for small point sets the per-call cost of a binding (ctypes: several microseconds)
+ * is comparable to the step itself.  Losses go to the device ring as for pinn_adam_step(loss_out == NULL). */
+int pinn_adam_steps(pinn_t* h, int n, double lr, double b1, double b2, double eps);
 int pinn_adam_reset(pinn_t* h);
 /* Loss values of the last n asynchronous Adam steps are kept in a device ring; read the most recent one. */
 int pinn_last_loss(pinn_t* h, double* loss_out);

@@ -19,7 +19,7 @@
 // [20(+1 ones row = bias) x 32 rows] x [32 rows x 20] GEMM.  Per-CTA accumulation is deterministic
 // (fixed warp order), the cross-CTA reduction is a second tiny kernel (reduce_partials).
 #pragma once
-#include "pinn_common.cuh"
+#include "optim_kernels.cuh"
 
 namespace pinn {
 namespace burgers {
@@ -69,6 +69,7 @@ struct Args {
   double* partials;       // [gridDim.x][PSTRIDE]
   const int* run_flag;    // optional: skip the whole launch when *run_flag != 0 (L-BFGS stopped on device)
   int chains;             // unused (kept for ABI stability of the launch struct within this library)
+  FusedTail tail;         // v2, single-GPU Adam step: reduction + Adam by the last CTAs of this launch (optim_kernels.cuh)
 };
 
 // ---------------------------------------------------------------------------------------------------

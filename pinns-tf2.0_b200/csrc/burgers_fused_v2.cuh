@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(THREADS, 1) fused_loss_grad(const Args p) {
     if (t == 36) outp[IDX_DL2] = sum4(3);
     if (t == 37) outp[3023] = 0.0;
   }
+  if (p.tail.enabled) fused_tail(p.tail, p.partials, PSTRIDE, sm + SM_STASH);     // the stash is dead; all 256 threads arrive
 }
 
 }  // namespace burgers2

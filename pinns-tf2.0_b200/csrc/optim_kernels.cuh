@@ -57,7 +57,7 @@ __device__ __forceinline__ double reduce_block_entries(const double* __restrict_
   if (ok) {
     const double* col = partials + src;
 #pragma unroll 8
-    for (int b = warp; b < n_cta; b += 8) s += col[(size_t)b * stride];
+    for (int b = warp; b < n_cta; b += 8) s += __ldcg(col + (size_t)b * stride);   // L2: other CTAs of a running launch may have written it
   }
   red[warp * 32 + lane] = s;
   __syncthreads();
@@ -109,6 +109,77 @@ __global__ void adam_update(double* __restrict__ w, double* __restrict__ m, doub
   if (i < P) adam_entry(w, m, v, R[i], i, t, lr, b1, b2, eps);
   if (i == 0) loss_ring[(t - 1) % ring] = R[P] + R[P + 1] + R[P + 2];
   adam_finish(step, gridDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same reduction + Adam INSIDE the fused loss/gradient launch (single GPU, Adam step): the last CTAs to finish wait for
+// the stragglers and share the 32-entry blocks among themselves -- no second launch, no kernel boundary (about 5 us per step;
+// what the step of a 2000-point set is made of).  Every CTA of the launch must be resident (grid <= number of SMs, one CTA per
+// SM), which holds for the persistent kernels that use it.  Same summation order as reduce_adam: identical trajectories.
+// ------------------------------------------------------------------------------------------------
+struct FusedTail {
+  int enabled;
+  int* ctr;               // [0] CTAs that have written their partials, [1] tail CTAs that are done (both left at 0)
+  double* R;
+  ReduceMap map;
+  double *w, *m, *v;
+  int P;
+  int* step;
+  double lr, b1, b2, eps;
+  double* loss_ring;
+  int ring;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by ALL threads of every CTA after the CTA's partial vector has been written.  red: >= 256 doubles of shared memory
+// nobody else uses any more.
+__device__ __forceinline__ void fused_tail(const FusedTail& ft, const double* __restrict__ partials, int stride, double* red) {
+  __shared__ int s_slot;
+  const int nb = (ft.map.n_out + 31) / 32;
+  const int K = (int)gridDim.x < nb ? (int)gridDim.x : nb;            // tail CTAs: the last K to arrive
+  __threadfence();                                                    // this thread's partial entries, device-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(ft.ctr, 1);
+    const int slot = ticket - ((int)gridDim.x - K);
+    if (slot >= 0)
+      while (ld_acquire_gpu(ft.ctr) < (int)gridDim.x) __nanosleep(40);  // every partial vector is complete
+    s_slot = slot;
+  }
+  __syncthreads();
+  const int slot = s_slot;
+  if (slot < 0) return;
+  const int t = *(volatile int*)ft.step + 1;
+  for (int vb = slot; vb < nb; vb += K) {
+    const int i = vb * 32 + (threadIdx.x & 31);
+    const bool ok = i < ft.map.n_out;
+    const int src = ok ? (i < ft.map.p_net ? i : ft.map.extra_src[i - ft.map.p_net]) : 0;
+    const double s = reduce_block_entries(partials, (int)gridDim.x, stride, src, ok, red);
+    if (ok && threadIdx.x < 32) {
+      ft.R[i] = s;
+      if (i < ft.P) adam_entry(ft.w, ft.m, ft.v, s, i, t, ft.lr, ft.b1, ft.b2, ft.eps);
+    }
+    __syncthreads();                                                  // red is rewritten by the next block of entries
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(ft.ctr + 1, 1);
+    if (done == K - 1) {                                              // the last tail CTA: loss, step counter, counters back to 0
+      __threadfence();
+      const volatile double* Rv = ft.R;
+      ft.loss_ring[(t - 1) % ft.ring] = Rv[ft.P] + Rv[ft.P + 1] + Rv[ft.P + 2];
+      ft.ctr[0] = 0;
+      ft.ctr[1] = 0;
+      *(volatile int*)ft.step = t;
+      __threadfence();
+    }
+  }
 }
 
 // Single-GPU step: fixed-order reduction of the per-CTA partials fused with the Adam update (no collective between).

@@ -352,7 +352,9 @@ int launch_tail(pinn_t* h, const int* run_flag, const AdamArgs* ad) {
   return 0;
 }
 
-int burgers_launch_eval(pinn_t* h, const int* run_flag) {
+// ad != nullptr on one GPU with the v2 kernel: the launch also reduces the partials and applies Adam (fused_tail); *tail_done
+// tells the caller that no tail kernel is needed.  PINN_FUSED_TAIL=0 keeps the two-launch step.
+int burgers_launch_eval(pinn_t* h, const int* run_flag, const AdamArgs* ad = nullptr, bool* tail_done = nullptr) {
   namespace B = pinn::burgers;
   const bool ide = h->pde == PINN_BURGERS_IDE;
   const long long n_total = ide ? h->n_d : h->n_d + h->n_c;
@@ -381,12 +383,6 @@ int burgers_launch_eval(pinn_t* h, const int* run_flag) {
   const long long rounds = (n_total + B::ROUND - 1) / B::ROUND;
   const long long units = h->burgers_kernel == 2 ? n_tiles : rounds;
   int grid = (int)(units < h->n_cta ? units : h->n_cta);
-  if (h->burgers_kernel == 2)
-    pinn::burgers2::fused_loss_grad<<<grid, pinn::burgers2::THREADS, pinn::burgers2::SMEM_BYTES, h->stream>>>(a);
-  else
-    B::fused_loss_grad<<<grid, B::THREADS, B::SMEM_BYTES, h->stream>>>(a);
-  CUDA_TRY(cudaGetLastError());
-  h->launches++;
   pinn::ReduceMap map{};
   map.p_net = B::P_NET;
   map.n_extra = 0;
@@ -395,6 +391,21 @@ int burgers_launch_eval(pinn_t* h, const int* run_flag) {
   map.extra_src[map.n_extra++] = 3023;        // (boundary part: always 0 for Burgers)
   map.extra_src[map.n_extra++] = B::IDX_LF;
   map.n_out = map.p_net + map.n_extra;
+  static const bool fused_tail_on = [] { const char* e = getenv("PINN_FUSED_TAIL"); return !(e && e[0] == '0'); }();
+  if (ad && tail_done && fused_tail_on && h->world == 1 && h->burgers_kernel == 2 && !run_flag && grid <= h->n_sm) {
+    pinn::FusedTail& ft = a.tail;
+    ft.enabled = 1; ft.ctr = h->d_step + 2; ft.R = h->d_R; ft.map = map;
+    ft.w = h->d_w; ft.m = h->d_m; ft.v = h->d_v; ft.P = h->P; ft.step = h->d_step;
+    ft.lr = ad->lr; ft.b1 = ad->b1; ft.b2 = ad->b2; ft.eps = ad->eps;
+    ft.loss_ring = h->d_loss_ring; ft.ring = LOSS_RING;
+    *tail_done = true;
+  }
+  if (h->burgers_kernel == 2)
+    pinn::burgers2::fused_loss_grad<<<grid, pinn::burgers2::THREADS, pinn::burgers2::SMEM_BYTES, h->stream>>>(a);
+  else
+    B::fused_loss_grad<<<grid, B::THREADS, B::SMEM_BYTES, h->stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
   h->last_map = map; h->last_grid = grid; h->last_stride = B::PSTRIDE;
   return 0;
 }
@@ -402,11 +413,12 @@ int burgers_launch_eval(pinn_t* h, const int* run_flag) {
 // one evaluation: the fused loss/gradient kernel of the handle's PDE, then (unless fused_only) the tail
 int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false, const AdamArgs* ad = nullptr) {
   int rc;
+  bool tail_done = false;
   if (h->kernel_kind == 2) rc = generic_launch_eval(h, run_flag);
-  else if (h->pde == PINN_BURGERS_INF || h->pde == PINN_BURGERS_IDE) rc = burgers_launch_eval(h, run_flag);
+  else if (h->pde == PINN_BURGERS_INF || h->pde == PINN_BURGERS_IDE) rc = burgers_launch_eval(h, run_flag, fused_only ? nullptr : ad, &tail_done);
   else rc = nls_launch_eval(h, run_flag);
   if (rc) return -1;
-  if (fused_only) return 0;
+  if (fused_only || tail_done) return 0;
   return launch_tail(h, run_flag, ad);
 }
 
@@ -1013,6 +1025,18 @@ int pinn_adam_step(pinn_t* h, double lr, double b1, double b2, double eps, doubl
     CUDA_TRY(cudaMemcpyAsync(loss_out_or_null, h->d_loss_ring + ((h->adam_steps - 1) % LOSS_RING), 8, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (check_p2p(h)) return -1;
+  }
+  return 0;
+}
+
+int pinn_adam_steps(pinn_t* h, int n, double lr, double b1, double b2, double eps) {
+  if (!h) return fail("null handle");
+  if (n < 0) return fail("pinn_adam_steps: n < 0");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const AdamArgs ad{lr, b1, b2, eps};
+  for (int i = 0; i < n; i++) {
+    if (launch_eval(h, nullptr, false, &ad)) return -1;
+    h->adam_steps++;
   }
   return 0;
 }

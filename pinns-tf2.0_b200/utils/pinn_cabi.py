@@ -44,6 +44,7 @@ SIGNATURES = {
     "pinn_get_weights": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "pinn_loss_grad": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
     "pinn_adam_step": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, _dp]),
+    "pinn_adam_steps": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]),
     "pinn_adam_reset": (C.c_int, [C.c_void_p]),
     "pinn_last_loss": (C.c_int, [C.c_void_p, _dp]),
     "pinn_lbfgs": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, LOG_CB, C.c_void_p,
@@ -231,6 +232,10 @@ class Pinn(object):
             return loss.value
         self._ck(self.lib.pinn_adam_step(self.h, lr, b1, b2, eps, None))
         return None
+
+    def adam_steps(self, n, lr, b1=0.9, b2=0.999, eps=1e-7):
+        """n asynchronous Adam steps enqueued by one native call (no per-step binding overhead)."""
+        self._ck(self.lib.pinn_adam_steps(self.h, int(n), lr, b1, b2, eps))
 
     def adam_reset(self):
         self._ck(self.lib.pinn_adam_reset(self.h))

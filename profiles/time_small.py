@@ -15,6 +15,8 @@ for _ in range(20):
 p.sync()
 out["cfg1_10k_step_ms"] = float(np.median(timed_adam_steps(p, 400, flush=False)))
 out["cfg1_kernel_ms"] = p.time_kernel_ms(50) / 50
+p.event_record(0); p.adam_steps(400, ADAM_LR); p.event_record(1); p.sync()
+out["cfg1_10k_step_ms_batched"] = p.event_elapsed_ms(0, 1) / 400
 p.close()
 rng = np.random.default_rng(3)
 X = LB + (UB - LB) * rng.random((2000, 2)); uu = rng.uniform(-1, 1, (2000, 1))
@@ -25,5 +27,7 @@ for _ in range(20):
 q.sync()
 out["cfg4_2k_step_ms"] = float(np.median(timed_adam_steps(q, 400, flush=False)))
 out["cfg4_kernel_ms"] = q.time_kernel_ms(50) / 50
+q.event_record(0); q.adam_steps(400, ADAM_LR); q.event_record(1); q.sync()
+out["cfg4_2k_step_ms_batched"] = q.event_elapsed_ms(0, 1) / 400
 q.close()
 print(json.dumps(out))

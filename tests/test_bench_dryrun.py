@@ -31,6 +31,9 @@ class FakePinn(object):
         self.launches += 2
         return 0.5 if sync else None
 
+    def adam_steps(self, n, lr, b1=0.9, b2=0.999, eps=1e-7):
+        self.launches += 2 * n
+
     def event_record(self, idx):
         self.events[idx] = True
 

@@ -339,3 +339,41 @@ print(json.dumps(out))
         assert a["n_iter"] == b["n_iter"] and a["n_eval"] == b["n_eval"]
         assert rel(b["f"], a["f"]) < tol and rel(b["x"], a["x"]) < tol
     assert rel(res["gram"]["50"]["f"], g["lbfgs_f"]) < 1e-7
+
+
+def test_batched_adam_steps_and_the_in_kernel_tail_leave_the_trajectory_unchanged():
+    """pinn_adam_steps(n) == n x pinn_adam_step, and the single-launch step (reduction + Adam done by the last CTAs of the fused
+    kernel) == the two-launch step (PINN_FUSED_TAIL=0): same summation order, so weights and losses agree bit for bit."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r'''
+import os, sys, json, numpy as np
+ROOT = %r
+sys.path[:0] = [ROOT, os.path.join(ROOT, "pinns-tf2.0_b200", "utils")]
+import pinn_cabi
+g = np.load(os.path.join(ROOT, "tests", "golden", "burgers_inf.npz"))
+out = {}
+for mode in ("single", "batched"):
+    p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, [2] + [20] * 8 + [1], g["lb"], g["ub"])
+    p.set_pde_params([float(g["nu"])]); p.set_collocation(g["X_f"][:, 0], g["X_f"][:, 1]); p.set_data(g["X_u"], g["u"]); p.set_weights(g["w"])
+    if mode == "single":
+        for _ in range(25):
+            p.adam_step(0.01, sync=False)
+    else:
+        p.adam_steps(25, 0.01)
+    out[mode] = {"w": p.get_weights().tolist(), "loss": p.last_loss(), "launches": p.kernel_info().get("launches")}
+print(json.dumps(out))
+''' % ROOT
+    res = {}
+    for tail in ("1", "0"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PINN_FUSED_TAIL=tail), capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tail] = json.loads(r.stdout.strip().splitlines()[-1])
+    ref = res["0"]["single"]
+    for tail in ("1", "0"):
+        for mode in ("single", "batched"):
+            assert res[tail][mode]["w"] == ref["w"] and res[tail][mode]["loss"] == ref["loss"], (tail, mode)
