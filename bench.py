@@ -567,8 +567,12 @@ def main():
     handle.append(p)
     import sharding
     used_p2p = sharding.connect_p2p(dist, p, world) if dist is not None else False
-    exchange = "none" if world == 1 else ("fused reduce + NVLink all-to-all push + Adam kernel (reduce_exchange, P2P stores into peer memory)"
-                                          if used_p2p else "reduce_partials + ncclAllReduce + adam_update")
+    fused_tail = os.environ.get("PINN_FUSED_TAIL", "1") != "0"
+    exchange = "none" if world == 1 else (
+        ("inside the fused kernel: its last CTAs reduce the partials, push over NVLink into every peer's memory, sum in rank order and "
+         "apply Adam (fused_tail / exchange_block; one launch per step)" if fused_tail else
+         "fused reduce + NVLink all-to-all push + Adam kernel (reduce_exchange, P2P stores into peer memory)")
+        if used_p2p else "reduce_partials + ncclAllReduce + adam_update")
     p.set_pde_params([NU])
     p.set_data(X_u, u, weight=1.0 if rank == 0 else 0.0)
     # pinned host copies of this rank's collocation batch (e2e leg uploads them every step)

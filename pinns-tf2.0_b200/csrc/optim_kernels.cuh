@@ -111,77 +111,6 @@ __global__ void adam_update(double* __restrict__ w, double* __restrict__ m, doub
   adam_finish(step, gridDim.x);
 }
 
-// ------------------------------------------------------------------------------------------------
-// The same reduction + Adam INSIDE the fused loss/gradient launch (single GPU, Adam step): the last CTAs to finish wait for
-// the stragglers and share the 32-entry blocks among themselves -- no second launch, no kernel boundary (about 5 us per step;
-// what the step of a 2000-point set is made of).  Every CTA of the launch must be resident (grid <= number of SMs, one CTA per
-// SM), which holds for the persistent kernels that use it.  Same summation order as reduce_adam: identical trajectories.
-// ------------------------------------------------------------------------------------------------
-struct FusedTail {
-  int enabled;
-  int* ctr;               // [0] CTAs that have written their partials, [1] tail CTAs that are done (both left at 0)
-  double* R;
-  ReduceMap map;
-  double *w, *m, *v;
-  int P;
-  int* step;
-  double lr, b1, b2, eps;
-  double* loss_ring;
-  int ring;
-};
-
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// Called by ALL threads of every CTA after the CTA's partial vector has been written.  red: >= 256 doubles of shared memory
-// nobody else uses any more.
-__device__ __forceinline__ void fused_tail(const FusedTail& ft, const double* __restrict__ partials, int stride, double* red) {
-  __shared__ int s_slot;
-  const int nb = (ft.map.n_out + 31) / 32;
-  const int K = (int)gridDim.x < nb ? (int)gridDim.x : nb;            // tail CTAs: the last K to arrive
-  __threadfence();                                                    // this thread's partial entries, device-wide
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int ticket = atomicAdd(ft.ctr, 1);
-    const int slot = ticket - ((int)gridDim.x - K);
-    if (slot >= 0)
-      while (ld_acquire_gpu(ft.ctr) < (int)gridDim.x) __nanosleep(40);  // every partial vector is complete
-    s_slot = slot;
-  }
-  __syncthreads();
-  const int slot = s_slot;
-  if (slot < 0) return;
-  const int t = *(volatile int*)ft.step + 1;
-  for (int vb = slot; vb < nb; vb += K) {
-    const int i = vb * 32 + (threadIdx.x & 31);
-    const bool ok = i < ft.map.n_out;
-    const int src = ok ? (i < ft.map.p_net ? i : ft.map.extra_src[i - ft.map.p_net]) : 0;
-    const double s = reduce_block_entries(partials, (int)gridDim.x, stride, src, ok, red);
-    if (ok && threadIdx.x < 32) {
-      ft.R[i] = s;
-      if (i < ft.P) adam_entry(ft.w, ft.m, ft.v, s, i, t, ft.lr, ft.b1, ft.b2, ft.eps);
-    }
-    __syncthreads();                                                  // red is rewritten by the next block of entries
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int done = atomicAdd(ft.ctr + 1, 1);
-    if (done == K - 1) {                                              // the last tail CTA: loss, step counter, counters back to 0
-      __threadfence();
-      const volatile double* Rv = ft.R;
-      ft.loss_ring[(t - 1) % ft.ring] = Rv[ft.P] + Rv[ft.P + 1] + Rv[ft.P + 2];
-      ft.ctr[0] = 0;
-      ft.ctr[1] = 0;
-      *(volatile int*)ft.step = t;
-      __threadfence();
-    }
-  }
-}
-
 // Single-GPU step: fixed-order reduction of the per-CTA partials fused with the Adam update (no collective between).
 __global__ void reduce_adam(const double* __restrict__ partials, int n_cta, int stride, double* __restrict__ R, ReduceMap map,
                             double* __restrict__ w, double* __restrict__ m, double* __restrict__ v, int P,
@@ -254,6 +183,58 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// One 32-entry virtual block of the exchange, executed by a whole block of 256 threads: local reduction of the partials, push
+// to every rank, publication, wait for every rank's copy, rank-ordered sum, optional Adam.  red/red2: 256 doubles each.
+struct AdamDev {
+  int on;
+  double *w, *m, *v;
+  int P, t;
+  double lr, b1, b2, eps;
+};
+__device__ __forceinline__ void exchange_block(int vb, const double* __restrict__ partials, int n_cta, int stride, const ReduceMap& map,
+                                               const XchgPeers& peers, unsigned long long seq, int* __restrict__ err,
+                                               double* __restrict__ R, const AdamDev& ad, double* red, double* red2, bool& dead) {
+  const int parity = (int)(seq & 1);
+  const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;       // entry within the virtual block; warp = partial slice, then peer rank
+  const int i = vb * 32 + lane;
+  const bool ok = i < map.n_out;
+  const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
+  const double s = reduce_block_entries(partials, n_cta, stride, src, ok, red);   // every warp holds the 32 local sums
+  // ---- push: warp k stores the 32 entries into rank k's buffer (one 256-byte row), slot [parity][my rank]
+  const size_t slot = ((size_t)parity * peers.world + peers.rank) * peers.slot_len;
+  if (ok && sub < peers.world) peers.data[sub][slot + i] = s;
+  // publication: the block barrier orders every thread's data stores before the flag writers, whose release at system
+  // scope (fence + store) is cumulative over what they have observed through the barrier -- ONE system-scope fence per
+  // block and peer instead of one per thread
+  __syncthreads();
+  if (threadIdx.x < peers.world) {
+    __threadfence_system();
+    st_release_sys(peers.flag[threadIdx.x] + ((size_t)parity * peers.world + peers.rank) * peers.n_blocks + vb, seq);
+  }
+  // ---- wait for every rank's copy of this virtual block's entries (local flags)
+  if (threadIdx.x < peers.world) {
+    const unsigned long long* f = peers.flag[peers.rank] + ((size_t)parity * peers.world + threadIdx.x) * peers.n_blocks + vb;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(f) < seq) {
+      if (globaltimer_ns() - t0 > 20000000000ULL) { atomicExch(err, 1); break; }
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+  dead = dead || *(volatile int*)err != 0;        // a peer never published: leave R, weights and optimiser state untouched
+  // ---- sum over ranks: warp k loads rank k's 32 values from the LOCAL buffer, combined in the fixed order of combine8
+  double part = 0.0;
+  if (ok && sub < peers.world)
+    part = __ldcv(peers.data[peers.rank] + ((size_t)parity * peers.world + sub) * peers.slot_len + i);
+  red2[sub * 32 + lane] = part;
+  __syncthreads();
+  const double tot = combine8(red2, lane);
+  if (ok && sub == 0 && !dead) {
+    R[i] = tot;
+    if (ad.on && i < ad.P) adam_entry(ad.w, ad.m, ad.v, tot, i, ad.t, ad.lr, ad.b1, ad.b2, ad.eps);
+  }
+}
+
 // xseq[0] = published evaluations so far, xseq[1] = blocks finished in the current launch.
 // The grid is capped at a size that is certainly co-resident (the host passes min(n_vblocks, 2 x SMs)); every block walks
 // the 32-entry "virtual blocks" vb = blockIdx.x, blockIdx.x + gridDim.x, ... in increasing order.  A block waiting for the
@@ -267,50 +248,12 @@ reduce_exchange(const double* __restrict__ partials, int n_cta, int stride, Redu
   pdl_wait();                                       // the fused kernel that wrote the partials has completed
   if (run_flag && *run_flag != 0) return;          // identical on every rank (replicated L-BFGS state)
   const unsigned long long seq = (unsigned long long)(*(volatile int*)xseq) + 1;
-  const int parity = (int)(seq & 1);
-  const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;       // entry within the virtual block; warp = partial slice, then peer rank
   const int t = adam ? step[0] + 1 : 0;
+  const AdamDev ad{adam, w, m, v, P, t, lr, b1, b2, eps};
   bool dead = false;
   __shared__ double red[256], red2[256];
-  for (int vb = blockIdx.x; vb < peers.n_blocks; vb += gridDim.x) {
-    const int i = vb * 32 + lane;
-    const bool ok = i < map.n_out;
-    const int src = ok ? (i < map.p_net ? i : map.extra_src[i - map.p_net]) : 0;
-    const double s = reduce_block_entries(partials, n_cta, stride, src, ok, red);   // every warp holds the 32 local sums
-    // ---- push: warp k stores the 32 entries into rank k's buffer (one 256-byte row), slot [parity][my rank]
-    const size_t slot = ((size_t)parity * peers.world + peers.rank) * peers.slot_len;
-    if (ok && sub < peers.world) peers.data[sub][slot + i] = s;
-    // publication: the block barrier orders every thread's data stores before the flag writers, whose release at system
-    // scope (fence + store) is cumulative over what they have observed through the barrier -- ONE system-scope fence per
-    // block and peer instead of one per thread
-    __syncthreads();
-    if (threadIdx.x < peers.world) {
-      __threadfence_system();
-      st_release_sys(peers.flag[threadIdx.x] + ((size_t)parity * peers.world + peers.rank) * peers.n_blocks + vb, seq);
-    }
-    // ---- wait for every rank's copy of this virtual block's entries (local flags)
-    if (threadIdx.x < peers.world) {
-      const unsigned long long* f = peers.flag[peers.rank] + ((size_t)parity * peers.world + threadIdx.x) * peers.n_blocks + vb;
-      const unsigned long long t0 = globaltimer_ns();
-      while (ld_acquire_sys(f) < seq) {
-        if (globaltimer_ns() - t0 > 20000000000ULL) { atomicExch(err, 1); break; }
-        __nanosleep(32);
-      }
-    }
-    __syncthreads();
-    dead = dead || *(volatile int*)err != 0;        // a peer never published: leave R, weights and optimiser state untouched
-    // ---- sum over ranks: warp k loads rank k's 32 values from the LOCAL buffer, combined in the fixed order of combine8
-    double part = 0.0;
-    if (ok && sub < peers.world)
-      part = __ldcv(peers.data[peers.rank] + ((size_t)parity * peers.world + sub) * peers.slot_len + i);
-    red2[sub * 32 + lane] = part;
-    __syncthreads();
-    const double tot = combine8(red2, lane);
-    if (ok && sub == 0 && !dead) {
-      R[i] = tot;
-      if (adam && i < P) adam_entry(w, m, v, tot, i, t, lr, b1, b2, eps);
-    }
-  }
+  for (int vb = blockIdx.x; vb < peers.n_blocks; vb += gridDim.x)
+    exchange_block(vb, partials, n_cta, stride, map, peers, seq, err, R, ad, red, red2, dead);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -324,6 +267,98 @@ reduce_exchange(const double* __restrict__ partials, int n_cta, int stride, Redu
       }
       xseq[1] = 0;
       xseq[0] += 1;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The tail INSIDE the fused loss/gradient launch (Adam steps with the specialised Burgers kernel): every CTA takes a ticket
+// after writing its partial vector; the last K to arrive (one per 32-entry block when the grid is large enough) wait for the
+// stragglers and then run the code of reduce_adam (one GPU) or of reduce_exchange (several: push exchange over NVLink) on
+// their blocks -- no second launch, no kernel boundary in the middle of a step.  Every CTA of the launch must be resident
+// (grid <= number of SMs, one CTA per SM), which holds for the persistent kernels that use it.  Same summation orders as the
+// stand-alone kernels: identical trajectories.  Across GPUs a tail CTA that waits for the peers' copy of block vb depends on
+// the peers' tail CTA that owns vb, which exists as soon as enough of the peer's CTAs have finished -- the peers' kernels run
+// to completion independently of the exchange, so there is no cycle.
+// ------------------------------------------------------------------------------------------------
+struct FusedTail {
+  int enabled;
+  int* ctr;               // [0] CTAs that have written their partials, [1] tail CTAs that are done (both left at 0)
+  double* R;
+  ReduceMap map;
+  double *w, *m, *v;
+  int P;
+  int* step;
+  double lr, b1, b2, eps;
+  double* loss_ring;
+  int ring;
+  int xchg;               // world > 1: exchange over peer memory
+  XchgPeers peers;
+  int* xseq;
+  int* err;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by ALL threads of every CTA after the CTA's partial vector has been written.  red: >= 512 doubles of shared memory
+// nobody else uses any more.
+__device__ __forceinline__ void fused_tail(const FusedTail& ft, const double* __restrict__ partials, int stride, double* red) {
+  __shared__ int s_slot;
+  const int nb = (ft.map.n_out + 31) / 32;
+  const int K = (int)gridDim.x < nb ? (int)gridDim.x : nb;            // tail CTAs: the last K to arrive
+  __threadfence();                                                    // this thread's partial entries, device-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(ft.ctr, 1);
+    const int slot = ticket - ((int)gridDim.x - K);
+    if (slot >= 0)
+      while (ld_acquire_gpu(ft.ctr) < (int)gridDim.x) __nanosleep(40);  // every partial vector is complete
+    s_slot = slot;
+  }
+  __syncthreads();
+  const int slot = s_slot;
+  if (slot < 0) return;
+  const int t = *(volatile int*)ft.step + 1;
+  bool dead = false;
+  if (ft.xchg) {
+    const unsigned long long seq = (unsigned long long)(*(volatile int*)ft.xseq) + 1;
+    const AdamDev ad{1, ft.w, ft.m, ft.v, ft.P, t, ft.lr, ft.b1, ft.b2, ft.eps};
+    for (int vb = slot; vb < nb; vb += K) {
+      exchange_block(vb, partials, (int)gridDim.x, stride, ft.map, ft.peers, seq, ft.err, ft.R, ad, red, red + 256, dead);
+      __syncthreads();                                                // red / red2 are rewritten by the next block of entries
+    }
+  } else {
+    for (int vb = slot; vb < nb; vb += K) {
+      const int i = vb * 32 + (threadIdx.x & 31);
+      const bool ok = i < ft.map.n_out;
+      const int src = ok ? (i < ft.map.p_net ? i : ft.map.extra_src[i - ft.map.p_net]) : 0;
+      const double s = reduce_block_entries(partials, (int)gridDim.x, stride, src, ok, red);
+      if (ok && threadIdx.x < 32) {
+        ft.R[i] = s;
+        if (i < ft.P) adam_entry(ft.w, ft.m, ft.v, s, i, t, ft.lr, ft.b1, ft.b2, ft.eps);
+      }
+      __syncthreads();                                                // red is rewritten by the next block of entries
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(ft.ctr + 1, 1);
+    if (done == K - 1) {                                              // the last tail CTA: loss, step counter, counters back to 0
+      __threadfence();
+      if (!(ft.xchg && *(volatile int*)ft.err != 0)) {                // a peer never published: optimiser state untouched
+        const volatile double* Rv = ft.R;
+        ft.loss_ring[(t - 1) % ft.ring] = Rv[ft.P] + Rv[ft.P + 1] + Rv[ft.P + 2];
+        *(volatile int*)ft.step = t;
+      }
+      ft.ctr[0] = 0;
+      ft.ctr[1] = 0;
+      if (ft.xchg) *(volatile int*)ft.xseq = *(volatile int*)ft.xseq + 1;
       __threadfence();
     }
   }

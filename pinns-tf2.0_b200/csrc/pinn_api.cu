@@ -392,9 +392,11 @@ int burgers_launch_eval(pinn_t* h, const int* run_flag, const AdamArgs* ad = nul
   map.extra_src[map.n_extra++] = B::IDX_LF;
   map.n_out = map.p_net + map.n_extra;
   static const bool fused_tail_on = [] { const char* e = getenv("PINN_FUSED_TAIL"); return !(e && e[0] == '0'); }();
-  if (ad && tail_done && fused_tail_on && h->world == 1 && h->burgers_kernel == 2 && !run_flag && grid <= h->n_sm) {
+  const bool xchg_ok = h->world > 1 && h->p2p_ready && (map.n_out + 31) / 32 == h->peers.n_blocks && map.n_out <= h->peers.slot_len;
+  if (ad && tail_done && fused_tail_on && (h->world == 1 || xchg_ok) && h->burgers_kernel == 2 && !run_flag && grid <= h->n_sm) {
     pinn::FusedTail& ft = a.tail;
     ft.enabled = 1; ft.ctr = h->d_step + 2; ft.R = h->d_R; ft.map = map;
+    if (h->world > 1) { ft.xchg = 1; ft.peers = h->peers; ft.xseq = h->d_xseq; ft.err = h->d_p2p_err; }
     ft.w = h->d_w; ft.m = h->d_m; ft.v = h->d_v; ft.P = h->P; ft.step = h->d_step;
     ft.lr = ad->lr; ft.b1 = ad->b1; ft.b2 = ad->b2; ft.eps = ad->eps;
     ft.loss_ring = h->d_loss_ring; ft.ring = LOSS_RING;
