@@ -270,17 +270,37 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
       NB[idx] = l1 * o[j] * o[out + j] - kap * o[3 * out + j];       // inference: l1 = 1, kap = nu
     }
     __syncthreads();
+    // (i) stage products  S[pt][k] = sum_j N[pt][j] M_pt[k][j]  -> RB.  One warp per (point, stage), lanes over j: the rows of the
+    // stage matrix are read coalesced and all 16 loads of a lane are in flight at once (q <= 512).  (Round 1: a thread per
+    // (point, stage) walking its own row -- 41 % of this model's step.)
+    for (int it = tid >> 5; it < npts * out; it += THREADS / 32) {
+      const int pt = it / out, k = it - pt * out;
+      const long long gp = base + pt;
+      if (idd || gp < p.n_d) {
+        const double* nrow = NB + (size_t)pt * q;
+        const double* irow = p.irk + ((idd && gp >= p.n_d) ? (size_t)q * q : 0) + (size_t)k * q;
+        double mv[16], nv[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          const int j = lane + 32 * c;
+          mv[c] = j < q ? __ldg(irow + j) : 0.0;
+          nv[c] = j < q ? nrow[j] : 0.0;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; c++) acc = fma(nv[c], mv[c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) RB[it] = acc;
+      }
+    }
+    __syncthreads();
     for (int idx = tid; idx < npts * out; idx += THREADS) {
       const int pt = idx / out, k = idx - pt * out;
       const long long gp = base + pt;
       const double uk = OUTV[(size_t)pt * 4 * out + k];
       if (idd || gp < p.n_d) {
         const bool second = idd && gp >= p.n_d;
-        const double* nrow = NB + (size_t)pt * q;
-        const double* irow = p.irk + (second ? (size_t)q * q : 0) + (size_t)k * q;
-        double acc = 0.0;
-        for (int j = 0; j < q; j++) acc = fma(nrow[j], __ldg(irow + j), acc);
-        const double r = fma(p.dt, acc, uk) - __ldg(p.tgt + gp);      // targets: [u_0 | u_1]
+        const double r = fma(p.dt, RB[idx], uk) - __ldg(p.tgt + gp);  // targets: [u_0 | u_1]
         if (second) part1 = fma(r, r, part1); else part0 = fma(r, r, part0);
         RB[idx] = 2.0 * r;
       } else {
@@ -289,6 +309,8 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
       }
     }
     __syncthreads();
+    // (ii) N-bar[pt][j] = dt sum_k RB[pt][k] M_pt[k][j]: thread per (point, column j) (coalesced over j), the k loop unrolled so
+    // that 16 independent matrix loads are in flight per thread
     for (int idx = tid; idx < npts * q; idx += THREADS) {
       const int pt = idx / q, j = idx - pt * q;
       const long long gp = base + pt;
@@ -296,8 +318,22 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
       if (idd || gp < p.n_d) {
         const double* rrow = RB + (size_t)pt * out;
         const double* mcol = p.irk + ((idd && gp >= p.n_d) ? (size_t)q * q : 0) + j;
-        for (int k = 0; k < out; k++) acc = fma(rrow[k], __ldg(mcol + (size_t)k * q), acc);
-        acc *= p.dt;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = 0;
+        for (; k + 16 <= out; k += 16) {
+          double mv[16];
+#pragma unroll
+          for (int c = 0; c < 16; c++) mv[c] = __ldg(mcol + (size_t)(k + c) * q);
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            a0 = fma(rrow[k + c], mv[c], a0);
+            a1 = fma(rrow[k + c + 1], mv[c + 1], a1);
+            a2 = fma(rrow[k + c + 2], mv[c + 2], a2);
+            a3 = fma(rrow[k + c + 3], mv[c + 3], a3);
+          }
+        }
+        for (; k < out; k++) a0 = fma(rrow[k], __ldg(mcol + (size_t)k * q), a0);
+        acc = ((a0 + a1) + (a2 + a3)) * p.dt;
       }
       NB[idx] = acc;                          // N-bar (0 on boundary points)
     }
