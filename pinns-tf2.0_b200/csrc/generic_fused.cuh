@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
     const int pt = idx / (4 * out), so_ = idx - pt * 4 * out, s = so_ / out, o = so_ - s * out;
     const double* h = Hl + s * sl + (size_t)pt * fl;
     double acc = s == 0 ? __ldg(p.w + nd.boff[L - 1] + o) : 0.0;
+#pragma unroll 10
     for (int i = 0; i < fl; i++) acc = fma(h[i], __ldg(Wh + (size_t)i * out + o), acc);
     OUTV[idx] = acc;
   }
@@ -437,6 +438,30 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
   }
   double* Acur = A0;      // adjoint of the current layer's outputs: [4][pts][w]
   double* Aoth = A1;
+  if (out >= 64) {
+    // wide heads (discrete-time models: out = q or q+1): a warp per (point, unit), lanes over the outputs -- coalesced rows of
+    // the head weights, all loads of a lane in flight at once (out <= 512), four stream sums reduced by shuffles
+    for (int it = tid >> 5; it < npts * fl; it += THREADS / 32) {
+      const int pt = it / fl, i = it - pt * fl;
+      const double* sd = SEED + (size_t)pt * 4 * out;
+      const double* wr = Wh + (size_t)i * out;
+      double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+      for (int c = 0; c < 16; c++) {
+        const int o = lane + 32 * c;
+        if (o < out) {
+          const double wv = __ldg(wr + o);
+#pragma unroll
+          for (int s = 0; s < 4; s++) a4[s] = fma(sd[s * out + o], wv, a4[s]);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        const double v = warp_sum(a4[s]);
+        if (lane == 0) Acur[s * sl + (size_t)pt * fl + i] = v;
+      }
+    }
+  } else
   for (int idx = tid; idx < npts * fl; idx += THREADS) {
     const int pt = idx / fl, i = idx - pt * fl;
     const double* sd = SEED + (size_t)pt * 4 * out;
