@@ -529,13 +529,22 @@ __global__ void __launch_bounds__(THREADS, 2) fused_loss_grad(const Args p) {
             const double* zq = Aoth + st * so + (size_t)q * fo;              // ... and of Z-bar
             const double one = st == 0 ? 1.0 : 0.0;
             const bool bias_row = i == fi;                                   // rows beyond fi are never stored
+            const double* hp = hq;
+            const double* zp[NTW];
+#pragma unroll
+            for (int j = 0; j < NTW; j++) zp[j] = zq + nc[j];
+            const size_t hs = (size_t)4 * fi, zs = (size_t)4 * fo;           // one k-step = 4 points further down
 #pragma unroll 4
             for (int kk = 0; kk < kfull; kk++) {
-              const double hv = hq[(size_t)(4 * kk) * fi];
+              const double hv = *hp;
+              hp += hs;
               const double a = bias_row ? one : hv;
               double b[NTW];
 #pragma unroll
-              for (int j = 0; j < NTW; j++) b[j] = j < ntn ? zq[(size_t)(4 * kk) * fo + nc[j]] : 0.0;
+              for (int j = 0; j < NTW; j++) {
+                b[j] = j < ntn ? *zp[j] : 0.0;
+                zp[j] += zs;
+              }
 #pragma unroll
               for (int j = 0; j < NTW; j++)
                 if (j < ntn) dmma(G[j], a, b[j]);
