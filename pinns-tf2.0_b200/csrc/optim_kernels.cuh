@@ -284,6 +284,7 @@ reduce_exchange(const double* __restrict__ partials, int n_cta, int stride, Redu
 // ------------------------------------------------------------------------------------------------
 struct FusedTail {
   int enabled;
+  int adam;               // 1: Adam step (update, loss ring, step counter); 0: evaluation only (L-BFGS, loss/gradient queries)
   int* ctr;               // [0] CTAs that have written their partials, [1] tail CTAs that are done (both left at 0)
   double* R;
   ReduceMap map;
@@ -323,11 +324,11 @@ __device__ __forceinline__ void fused_tail(const FusedTail& ft, const double* __
   __syncthreads();
   const int slot = s_slot;
   if (slot < 0) return;
-  const int t = *(volatile int*)ft.step + 1;
+  const int t = ft.adam ? *(volatile int*)ft.step + 1 : 0;
   bool dead = false;
   if (ft.xchg) {
     const unsigned long long seq = (unsigned long long)(*(volatile int*)ft.xseq) + 1;
-    const AdamDev ad{1, ft.w, ft.m, ft.v, ft.P, t, ft.lr, ft.b1, ft.b2, ft.eps};
+    const AdamDev ad{ft.adam, ft.w, ft.m, ft.v, ft.P, t, ft.lr, ft.b1, ft.b2, ft.eps};
     for (int vb = slot; vb < nb; vb += K) {
       exchange_block(vb, partials, (int)gridDim.x, stride, ft.map, ft.peers, seq, ft.err, ft.R, ad, red, red + 256, dead);
       __syncthreads();                                                // red / red2 are rewritten by the next block of entries
@@ -340,7 +341,7 @@ __device__ __forceinline__ void fused_tail(const FusedTail& ft, const double* __
       const double s = reduce_block_entries(partials, (int)gridDim.x, stride, src, ok, red);
       if (ok && threadIdx.x < 32) {
         ft.R[i] = s;
-        if (i < ft.P) adam_entry(ft.w, ft.m, ft.v, s, i, t, ft.lr, ft.b1, ft.b2, ft.eps);
+        if (ft.adam && i < ft.P) adam_entry(ft.w, ft.m, ft.v, s, i, t, ft.lr, ft.b1, ft.b2, ft.eps);
       }
       __syncthreads();                                                // red is rewritten by the next block of entries
     }
@@ -351,7 +352,7 @@ __device__ __forceinline__ void fused_tail(const FusedTail& ft, const double* __
     const int done = atomicAdd(ft.ctr + 1, 1);
     if (done == K - 1) {                                              // the last tail CTA: loss, step counter, counters back to 0
       __threadfence();
-      if (!(ft.xchg && *(volatile int*)ft.err != 0)) {                // a peer never published: optimiser state untouched
+      if (ft.adam && !(ft.xchg && *(volatile int*)ft.err != 0)) {     // a peer never published: optimiser state untouched
         const volatile double* Rv = ft.R;
         ft.loss_ring[(t - 1) % ft.ring] = Rv[ft.P] + Rv[ft.P + 1] + Rv[ft.P + 2];
         *(volatile int*)ft.step = t;

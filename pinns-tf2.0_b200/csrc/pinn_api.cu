@@ -352,8 +352,8 @@ int launch_tail(pinn_t* h, const int* run_flag, const AdamArgs* ad) {
   return 0;
 }
 
-// ad != nullptr on one GPU with the v2 kernel: the launch also reduces the partials and applies Adam (fused_tail); *tail_done
-// tells the caller that no tail kernel is needed.  PINN_FUSED_TAIL=0 keeps the two-launch step.
+// v2 kernel with tail_done != nullptr: the launch also reduces the partials (+ exchanges them, + applies Adam when ad != nullptr) in
+// its last CTAs (fused_tail); *tail_done tells the caller that no tail kernel is needed.  PINN_FUSED_TAIL=0 keeps the tail kernels.
 int burgers_launch_eval(pinn_t* h, const int* run_flag, const AdamArgs* ad = nullptr, bool* tail_done = nullptr) {
   namespace B = pinn::burgers;
   const bool ide = h->pde == PINN_BURGERS_IDE;
@@ -393,12 +393,14 @@ int burgers_launch_eval(pinn_t* h, const int* run_flag, const AdamArgs* ad = nul
   map.n_out = map.p_net + map.n_extra;
   static const bool fused_tail_on = [] { const char* e = getenv("PINN_FUSED_TAIL"); return !(e && e[0] == '0'); }();
   const bool xchg_ok = h->world > 1 && h->p2p_ready && (map.n_out + 31) / 32 == h->peers.n_blocks && map.n_out <= h->peers.slot_len;
-  if (ad && tail_done && fused_tail_on && (h->world == 1 || xchg_ok) && h->burgers_kernel == 2 && !run_flag && grid <= h->n_sm) {
+  // every evaluation of the v2 kernel carries its own tail: Adam steps (ad != nullptr) and plain evaluations (L-BFGS, loss/gradient
+  // queries; a launch skipped through run_flag skips its tail with it, exactly like the stand-alone tail kernels)
+  if (tail_done && fused_tail_on && (h->world == 1 || xchg_ok) && h->burgers_kernel == 2 && grid <= h->n_sm) {
     pinn::FusedTail& ft = a.tail;
-    ft.enabled = 1; ft.ctr = h->d_step + 2; ft.R = h->d_R; ft.map = map;
+    ft.enabled = 1; ft.adam = ad ? 1 : 0; ft.ctr = h->d_step + 2; ft.R = h->d_R; ft.map = map;
     if (h->world > 1) { ft.xchg = 1; ft.peers = h->peers; ft.xseq = h->d_xseq; ft.err = h->d_p2p_err; }
     ft.w = h->d_w; ft.m = h->d_m; ft.v = h->d_v; ft.P = h->P; ft.step = h->d_step;
-    ft.lr = ad->lr; ft.b1 = ad->b1; ft.b2 = ad->b2; ft.eps = ad->eps;
+    if (ad) { ft.lr = ad->lr; ft.b1 = ad->b1; ft.b2 = ad->b2; ft.eps = ad->eps; }
     ft.loss_ring = h->d_loss_ring; ft.ring = LOSS_RING;
     *tail_done = true;
   }
@@ -417,7 +419,7 @@ int launch_eval(pinn_t* h, const int* run_flag, bool fused_only = false, const A
   int rc;
   bool tail_done = false;
   if (h->kernel_kind == 2) rc = generic_launch_eval(h, run_flag);
-  else if (h->pde == PINN_BURGERS_INF || h->pde == PINN_BURGERS_IDE) rc = burgers_launch_eval(h, run_flag, fused_only ? nullptr : ad, &tail_done);
+  else if (h->pde == PINN_BURGERS_INF || h->pde == PINN_BURGERS_IDE) rc = burgers_launch_eval(h, run_flag, ad, fused_only ? nullptr : &tail_done);
   else rc = nls_launch_eval(h, run_flag);
   if (rc) return -1;
   if (fused_only || tail_done) return 0;
