@@ -13,9 +13,10 @@
 //   warps 4-7  "wgrad" warps  : consume (stash[l-1], Z-bar_l) pairs of all four chain warps and run the
 //                               weight-gradient GEMM  G_l[i][j] += sum_rows H_{l-1}[row][i] Zbar_l[row][j]  with DMMA.
 //                               The 3x3 output tiles of a layer are OWNED by warps, a ROW of tiles each: position
-//                               k = (warp - layer) & 3 < 3 owns tiles (mt = k; nt = 0,1,2), position 3 rests (the resting
-//                               role rotates with the layer so the four sub-partitions stay balanced).  One A fragment
-//                               feeds three DMMAs, operand column pointers are chosen once per task (padded lanes point
+//                               k = (warp - layer) & 3 < 3 owns tiles (mt = k; nt = 0,1,2), position 3 takes one m-tile off
+//                               the busiest position at layers <= 3 and rests otherwise (ownership masks: 120/128/128/128
+//                               DMMAs per tile and warp; the roles rotate with the layer).  One A fragment
+//                               feeds up to three DMMAs, operand column pointers are chosen once per task (padded lanes point
 //                               into a ones/zeros page), so the unrolled k loop is 4 LDS + 3 DMMA without predicates.
 //                               Accumulators live in registers for the whole kernel: no shared-memory accumulator, no
 //                               atomics, no cross-warp reduction, and a fixed summation order (deterministic results).
@@ -35,6 +36,9 @@
 //
 // Work distribution is tile-granular (8 points): the tiles are dealt evenly to the CTAs and round-robin to a CTA's four chain
 // warps, so the slowest CTA carries at most one tile more than the others and small sets spread over all SMs.
+//
+// The tail of the evaluation runs in this launch too (optim_kernels.cuh: fused_tail): the last CTAs to finish reduce the per-CTA
+// partial vectors in a fixed order, exchange them with the other ranks over NVLink (multi-GPU) and apply Adam (Adam steps).
 //
 // Measured and dropped (profiles/kernel_variants_r02.md): 3-slot ring, per-tile-pair ownership 3/2/2/2 (0.451 -> 0.416 ms
 // with row ownership), holding the weight-gradient DMMAs back while the co-resident chain warp is in a DMMA phase

@@ -308,6 +308,7 @@ cudaError_t launch_tail_kernel(void (*kernel)(KArgs...), int grid, int block, cu
 
 // The tail of an evaluation: fixed-order reduction of the per-CTA partials into R = [grad | loss parts] on every rank,
 // optionally fused with the Adam update.
+// (Evaluations of the specialised Burgers kernel do all of this in their own last CTAs -- fused_tail -- and never get here.)
 //   world == 1      : reduce_partials, or reduce_adam (one kernel)
 //   world > 1, P2P  : reduce_exchange -- reduction + NVLink all-to-all push + rank-ordered sum (+ Adam) in ONE kernel
 //   world > 1, NCCL : reduce_partials + ncclAllReduce(P+3 doubles) (+ adam_update)
