@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "burgers_fused.cuh"
@@ -21,6 +22,13 @@ namespace {
 
 thread_local std::string g_err;
 int fail(const std::string& m) { g_err = m; return -1; }
+
+// Live handles of this process.  A launch with the in-kernel tail (fused_tail) keeps its last CTAs spinning on their SMs until the
+// launch's stragglers arrive; two such launches running CONCURRENTLY on one device (two handles, two streams) could fill every SM
+// with spinning CTAs while both still have CTAs waiting for an SM.  So a handle uses the in-kernel tail only while no OTHER handle on
+// the same device has such a launch in flight (checked with cudaStreamQuery); otherwise it falls back to the tail kernels.
+std::mutex g_live_mu;
+std::vector<struct pinn_handle*> g_live;
 
 #define CUDA_TRY(expr)                                                                                         \
   do {                                                                                                         \
@@ -82,6 +90,7 @@ struct pinn_handle {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_sm = 0;
   long long launches = 0;
+  bool tail_inflight = false;   // a launch with the in-kernel tail may still be running on this handle's stream
   pinn::ReduceMap last_map{};       // reduction map / grid / stride of the most recent fused launch
   int last_grid = 0, last_stride = 0;
   int kernel_kind = 0;              // 0: specialised Burgers DMMA kernel, 1: specialised NLS DMMA kernel, 2: generic
@@ -353,6 +362,18 @@ int launch_tail(pinn_t* h, const int* run_flag, const AdamArgs* ad) {
   return 0;
 }
 
+// true when no other live handle on h's device may still be running a launch with the in-kernel tail
+bool tail_slot_free(pinn_t* h) {
+  std::lock_guard<std::mutex> lk(g_live_mu);
+  for (pinn_t* o : g_live) {
+    if (o == h || o->device != h->device || !o->tail_inflight) continue;
+    if (cudaStreamQuery(o->stream) == cudaSuccess) o->tail_inflight = false;
+    else return false;
+  }
+  (void)cudaGetLastError();               // cudaErrorNotReady from the query is not an error of ours
+  return true;
+}
+
 // v2 kernel with tail_done != nullptr: the launch also reduces the partials (+ exchanges them, + applies Adam when ad != nullptr) in
 // its last CTAs (fused_tail); *tail_done tells the caller that no tail kernel is needed.  PINN_FUSED_TAIL=0 keeps the tail kernels.
 int burgers_launch_eval(pinn_t* h, const int* run_flag, const AdamArgs* ad = nullptr, bool* tail_done = nullptr) {
@@ -396,7 +417,8 @@ int burgers_launch_eval(pinn_t* h, const int* run_flag, const AdamArgs* ad = nul
   const bool xchg_ok = h->world > 1 && h->p2p_ready && (map.n_out + 31) / 32 == h->peers.n_blocks && map.n_out <= h->peers.slot_len;
   // every evaluation of the v2 kernel carries its own tail: Adam steps (ad != nullptr) and plain evaluations (L-BFGS, loss/gradient
   // queries; a launch skipped through run_flag skips its tail with it, exactly like the stand-alone tail kernels)
-  if (tail_done && fused_tail_on && (h->world == 1 || xchg_ok) && h->burgers_kernel == 2 && grid <= h->n_sm) {
+  if (tail_done && fused_tail_on && (h->world == 1 || xchg_ok) && h->burgers_kernel == 2 && grid <= h->n_sm && tail_slot_free(h)) {
+    h->tail_inflight = true;
     pinn::FusedTail& ft = a.tail;
     ft.enabled = 1; ft.adam = ad ? 1 : 0; ft.ctr = h->d_step + 2; ft.R = h->d_R; ft.map = map;
     if (h->world > 1) { ft.xchg = 1; ft.peers = h->peers; ft.xseq = h->d_xseq; ft.err = h->d_p2p_err; }
@@ -762,12 +784,18 @@ int pinn_create(pinn_t** out, int pde_id, int n_layers, const int* layers, const
     int rc = g_nccl.CommInitRank(&h->comm, h->world, id, h->rank);
     if (rc != 0) { fail(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); pinn_destroy(h); return -1; }
   }
+  { std::lock_guard<std::mutex> lk(g_live_mu); g_live.push_back(h); }
   *out = h;
   return 0;
 }
 
 int pinn_destroy(pinn_t* h) {
   if (!h) return 0;
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    for (size_t i = 0; i < g_live.size(); i++)
+      if (g_live[i] == h) { g_live.erase(g_live.begin() + i); break; }
+  }
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int r = 0; r < pinn::P2P_MAX; r++) if (h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);

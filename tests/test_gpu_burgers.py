@@ -377,3 +377,39 @@ print(json.dumps(out))
     for tail in ("1", "0"):
         for mode in ("single", "batched"):
             assert res[tail][mode]["w"] == ref["w"] and res[tail][mode]["loss"] == ref["loss"], (tail, mode)
+
+
+def test_two_handles_stepping_concurrently_on_one_device():
+    """Two handles enqueue asynchronous Adam steps alternately on their own streams.  Only one of two concurrent launches may keep
+    its last CTAs spinning for the in-kernel tail (pinn_api.cu: tail_slot_free); the other falls back to the tail kernels.  The run
+    must finish (a subprocess with a timeout guards the test session) and both trajectories must equal a handle stepped alone."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r'''
+import os, sys, json, numpy as np
+ROOT = %r
+sys.path[:0] = [ROOT, os.path.join(ROOT, "pinns-tf2.0_b200", "utils")]
+import pinn_cabi
+g = np.load(os.path.join(ROOT, "tests", "golden", "burgers_inf.npz"))
+def make():
+    p = pinn_cabi.Pinn(pinn_cabi.BURGERS_INF, [2] + [20] * 8 + [1], g["lb"], g["ub"])
+    p.set_pde_params([float(g["nu"])]); p.set_collocation(g["X_f"][:, 0], g["X_f"][:, 1]); p.set_data(g["X_u"], g["u"]); p.set_weights(g["w"])
+    return p
+a, b = make(), make()
+for _ in range(200):
+    a.adam_step(0.01, sync=False)
+    b.adam_step(0.01, sync=False)
+a.sync(); b.sync()
+wa, wb = a.get_weights().tolist(), b.get_weights().tolist()
+a.close(); b.close()
+c = make()
+c.adam_steps(200, 0.01)
+print(json.dumps({"a": wa, "b": wb, "c": c.get_weights().tolist()}))
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["a"] == d["c"] and d["b"] == d["c"]
